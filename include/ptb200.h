@@ -1,0 +1,342 @@
+/*
+ * ptb200.h — C ABI of the B200-native path tracer (libptb200.so).
+ *
+ * This is the drop-in boundary for the reference's hot path
+ *   ray generation -> BVH traversal (closest hit + shadow) -> material
+ *   shading / MIS / Russian roulette -> float4 accumulation.
+ * The reference (joaovbs96/OptiX-Path-Tracer) has no FFI layer; its scene code
+ * talks to OptiX 6 objects directly.  Every entry point below names the
+ * reference interface it replaces (paths relative to
+ * OptiX-Path-Tracer/ in the reference tree).
+ *
+ * Conventions
+ *   - plain C, no C++ or torch types; every call returns 0 on success or a
+ *     negative pt_status; pt_last_error() gives a thread-local message.
+ *   - the caller owns every input array; the library copies before returning.
+ *   - the library owns device memory until the matching *_destroy.
+ *   - primitive ids are assigned in the order primitives are added
+ *     (first id of every batch is returned through `first_prim_id`).
+ *   - all arithmetic is FP32; RNG is uint32 (programs/random.cuh).
+ *   - there is NO CPU fallback: every compute entry point fails with
+ *     PT_ERR_CUDA when no CUDA device is usable.
+ */
+#ifndef PTB200_H
+#define PTB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PTB200_ABI_VERSION 1
+
+typedef enum pt_status {
+  PT_OK = 0,
+  PT_ERR_INVALID = -1, /* bad argument / bad scene state                     */
+  PT_ERR_CUDA = -2,    /* CUDA runtime error or no device                    */
+  PT_ERR_OOM = -3,     /* host or device allocation failed                   */
+  PT_ERR_STATE = -4    /* call order violated (e.g. render before commit)    */
+} pt_status;
+
+/* ---- primitive / material / texture vocabulary (reference names) -------- */
+
+/* programs/common.hpp:26 `typedef enum { X_AXIS, Y_AXIS, Z_AXIS } AXIS;` */
+enum { PT_X_AXIS = 0, PT_Y_AXIS = 1, PT_Z_AXIS = 2 };
+
+/* primitive kinds: programs/hitables/{triangle,sphere,aarect,box}.cu */
+enum { PT_PRIM_TRIANGLE = 0, PT_PRIM_SPHERE = 1, PT_PRIM_RECT = 2, PT_PRIM_BOX = 3 };
+
+/* host_includes/hitables.hpp:73-128 `Sphere(center, radius, BRDF*)` */
+typedef struct pt_sphere {
+  float center[3];
+  float radius;
+} pt_sphere;
+
+/* host_includes/hitables.hpp:216-270 `AARect(a0,a1,b0,b1,k,flip,axis,BRDF*)`;
+ * axis -> (a,b) mapping: X:(y,z) Y:(x,z) Z:(x,y) (programs/hitables/aarect.cu:20-45) */
+typedef struct pt_rect {
+  float a0, a1, b0, b1, k;
+  int32_t axis; /* PT_*_AXIS */
+  int32_t flip; /* flip normal */
+} pt_rect;
+
+/* host_includes/hitables.hpp:272-311 `Box(p0, p1, BRDF*)` */
+typedef struct pt_box {
+  float bmin[3];
+  float bmax[3];
+} pt_box;
+
+/* host_includes/materials.hpp:42-242 */
+enum {
+  PT_MAT_LAMBERTIAN = 0,        /* Lambertian(tex)                              */
+  PT_MAT_METAL = 1,             /* Metal(tex, fuzz)             p0=fuzz         */
+  PT_MAT_DIELECTRIC = 2,        /* Dielectric(base, ext, ref_idx, density)      */
+                                /*   tex0=base tex1=extinction p0=ref_idx p1=density */
+  PT_MAT_DIFFUSE_LIGHT = 3,     /* Diffuse_Light(tex)                           */
+  PT_MAT_OREN_NAYAR = 4,        /* Oren_Nayar(tex, R)  p0=rA p1=rB (already converted,
+                                   host_includes/materials.hpp:192-198)         */
+  PT_MAT_TORRANCE_SPARROW = 5,  /* Torrance_Sparrow(tex,nu,nv) p0,p1 = alpha =
+                                   max(R,1e-3)^2 (materials.hpp:235-238)        */
+  PT_MAT_ASHIKHMIN_SHIRLEY = 6, /* Ashikhmin_Shirley(diff,spec,nu,nv) tex0=diffuse
+                                   tex1=specular p0=max(1,nu) p1=max(1,nv)      */
+  PT_MAT_NORMAL = 7,            /* Normal_Shader(useShadingNormal) flags bit0   */
+  PT_MAT_TYPE_COUNT = 8
+};
+
+typedef struct pt_material {
+  int32_t type;
+  int32_t tex0, tex1; /* texture ids, -1 if unused */
+  float p0, p1;
+  int32_t flags;
+} pt_material;
+
+/* host_includes/textures.hpp:16-270, programs/textures/ (all .cu files) */
+enum {
+  PT_TEX_CONSTANT = 0, /* color                                               */
+  PT_TEX_CHECKER = 1,  /* a=odd texture id, b=even texture id                 */
+  PT_TEX_IMAGE = 2,    /* a=image id (bilinear, repeat, normalised coords)    */
+  PT_TEX_VECTOR = 3    /* a=first entry in the texture-vector table, b=count  */
+};
+
+typedef struct pt_texture {
+  int32_t type;
+  float color[3];
+  int32_t a, b;
+} pt_texture;
+
+/* host_includes/pdfs.hpp:18-80 `Rectangle_PDF(a0,a1,b0,b1,k,axis)` +
+ * Light_Sampler::emissions (host_includes/host_common.hpp:65-68) */
+enum { PT_LIGHT_RECT = 0 };
+
+typedef struct pt_light {
+  int32_t type;
+  int32_t axis;
+  float a0, a1, b0, b1, k;
+  float emission[3];
+} pt_light;
+
+/* host_includes/camera.hpp:13-51: the seven float3 + three floats the raygen
+ * program reads (programs/raygen.cu:39-48) */
+typedef struct pt_camera {
+  float origin[3];
+  float lower_left_corner[3];
+  float horizontal[3];
+  float vertical[3];
+  float u[3], v[3], w[3];
+  float lens_radius;
+  float time0, time1;
+} pt_camera;
+
+/* host_includes/programs.hpp:32 `enum Miss_Programs {GRADIENT, CONSTANT, IMG, HDR}`,
+ * programs/miss.cu:30-95 */
+enum { PT_MISS_GRADIENT = 0, PT_MISS_CONSTANT = 1, PT_MISS_IMG = 2, PT_MISS_HDR = 3 };
+
+typedef struct pt_miss {
+  int32_t type;
+  float color1[3]; /* GRADIENT: bottom colour; CONSTANT: the colour           */
+  float color2[3]; /* GRADIENT: top colour                                    */
+  int32_t image;   /* IMG/HDR: image id                                       */
+  int32_t spherical; /* HDR: 1 = equirect, 0 = cylindrical (miss.cu:64-95)    */
+  int32_t env_nee; /* 0 = reference semantics (no env importance sampling);
+                      1 = NEW: alias-table env NEE + MIS (not in reference)   */
+} pt_miss;
+
+/* one traversal query; programs/raygen.cu:58-62 `make_Ray(o,d,type,tmin,tmax)` */
+typedef struct pt_ray {
+  float origin[3];
+  float tmin;
+  float dir[3];
+  float tmax;
+} pt_ray;
+
+/* closest-hit answer: rtIntersectionDistance + `geo_index`/`bc` attributes
+ * (programs/hitables/triangle.cu:52-56).  prim = -1 on miss. */
+typedef struct pt_hit {
+  float t;
+  int32_t prim;
+  float u, v; /* triangle barycentrics, 0 for analytic primitives */
+} pt_hit;
+
+/* ---- flat scene description (what commit uploads; what the oracle reads) -- */
+
+typedef struct pt_prim_ref {
+  int32_t type;     /* PT_PRIM_*                                             */
+  int32_t index;    /* index into the typed array                            */
+  int32_t material; /* material id                                           */
+  int32_t xform;    /* -1 = identity, else index into xforms                 */
+} pt_prim_ref;
+
+/* object->world and world->object, row-major 3x4 (Transform node matrices,
+ * host_includes/transforms.hpp:52-64; composed per primitive) */
+typedef struct pt_xform {
+  float o2w[12];
+  float w2o[12];
+} pt_xform;
+
+typedef struct pt_image {
+  int32_t width, height;
+  const float* rgba; /* width*height*4 floats, row 0 first                    */
+} pt_image;
+
+typedef struct pt_scene_desc {
+  int32_t n_prims;
+  const pt_prim_ref* prims;
+  int32_t n_spheres;
+  const pt_sphere* spheres;
+  int32_t n_rects;
+  const pt_rect* rects;
+  int32_t n_boxes;
+  const pt_box* boxes;
+  int32_t n_tris;
+  const float* tri_v;        /* 9 floats / triangle (a,b,c), world space      */
+  const float* tri_n;        /* 9 floats / triangle or NULL                   */
+  const float* tri_uv;       /* 6 floats / triangle or NULL                   */
+  const int32_t* tri_tex;    /* per-triangle texture index (material_buffer,
+                                programs/hitables/triangle.cu:146) or NULL=0  */
+  int32_t n_xforms;
+  const pt_xform* xforms;
+  int32_t n_materials;
+  const pt_material* materials;
+  int32_t n_textures;
+  const pt_texture* textures;
+  int32_t n_texvec;
+  const int32_t* texvec;     /* texture-vector table (programs/textures/vector.cu) */
+  int32_t n_images;
+  const pt_image* images;
+  int32_t n_lights;
+  const pt_light* lights;
+  pt_camera camera;
+  pt_miss miss;
+} pt_scene_desc;
+
+/* ---- scene construction --------------------------------------------------- */
+
+typedef struct pt_scene pt_scene;
+typedef struct pt_renderer pt_renderer;
+
+const char* pt_last_error(void);
+int pt_abi_version(void);
+
+/* replaces Context::create() + createGroup()/createAcceleration("Trbvh")
+ * (host_includes/host_common.hpp:24, host_includes/scenes.hpp:31-32) */
+int pt_scene_create(pt_scene** out);
+int pt_scene_destroy(pt_scene* scene);
+
+/* replaces Sphere/AARect/Box::getGeometryInstance + addAndTransform
+ * (host_includes/hitables.hpp:81-127,233-266,279-307; transforms.hpp:400-419).
+ * xform_o2w: n*12 floats (row-major 3x4 object->world) or NULL for identity;
+ * material: n material ids. */
+int pt_scene_add_spheres(pt_scene* scene, const pt_sphere* prims, const float* xform_o2w,
+                         const int32_t* material, int32_t n, int32_t* first_prim_id);
+int pt_scene_add_rects(pt_scene* scene, const pt_rect* prims, const float* xform_o2w,
+                       const int32_t* material, int32_t n, int32_t* first_prim_id);
+int pt_scene_add_boxes(pt_scene* scene, const pt_box* prims, const float* xform_o2w,
+                       const int32_t* material, int32_t n, int32_t* first_prim_id);
+
+/* replaces Mesh::getGeometryInstance buffers (host_includes/mesh.hpp:158-201):
+ * unindexed per-face arrays.  v: ntris*9; n: ntris*9 or NULL; uv: ntris*6 or
+ * NULL; tex_index: ntris or NULL.  xform_o2w (12 floats or NULL) is applied to
+ * the vertices/normals on the host (the BVH holds world-space triangles). */
+int pt_scene_add_mesh(pt_scene* scene, const float* v, const float* n, const float* uv,
+                      const int32_t* tex_index, int32_t ntris, const float* xform_o2w,
+                      int32_t material, int32_t* first_prim_id);
+
+/* replaces BRDF::assignTo / Texture::assignTo program creation
+ * (host_includes/materials.hpp:47-242, textures.hpp:28-270) */
+int pt_scene_set_materials(pt_scene* scene, const pt_material* m, int32_t n);
+int pt_scene_set_textures(pt_scene* scene, const pt_texture* t, int32_t n);
+int pt_scene_set_texture_vector(pt_scene* scene, const int32_t* texture_ids, int32_t n);
+/* replaces Image_Texture::loadTexture / HDR_Texture::loadHDRTexture buffers
+ * (host_includes/textures.hpp:115-165,178-217): RGBA float, row 0 first. */
+int pt_scene_add_image(pt_scene* scene, const float* rgba, int32_t width, int32_t height,
+                       int32_t* image_id);
+/* replaces setRayGenerationProgram's Light_Sample/Light_PDF/Light_Emissions
+ * buffers (host_includes/programs.hpp:17-30) */
+int pt_scene_set_lights(pt_scene* scene, const pt_light* lights, int32_t n);
+/* replaces Camera::set (host_includes/camera.hpp:40-51) */
+int pt_scene_set_camera(pt_scene* scene, const pt_camera* cam);
+/* replaces setMissProgram (host_includes/programs.hpp:35-92) */
+int pt_scene_set_miss(pt_scene* scene, const pt_miss* miss);
+
+/* replaces the first `renderFrame(ctx,0,0)` ("OptiX Building Time",
+ * main.cpp:99): uploads the scene and builds the BVH on the GPU. */
+int pt_scene_commit(pt_scene* scene);
+
+/* host-side flat description (valid until the scene is modified/destroyed) */
+int pt_scene_get_desc(const pt_scene* scene, pt_scene_desc* out);
+
+typedef struct pt_bvh_info {
+  int32_t n_prims;
+  int32_t n_bvh2_nodes;
+  int32_t n_bvh8_nodes;
+  int32_t n_leaf_records;
+  float sah_cost_lbvh;    /* SAH cost of the BVH2 before refinement          */
+  float sah_cost_refined; /* ... after binned-SAH treelet refinement         */
+  float build_ms;         /* GPU time of the whole build                     */
+  int64_t node_bytes;
+  int64_t leaf_bytes;
+} pt_bvh_info;
+int pt_scene_bvh_info(const pt_scene* scene, pt_bvh_info* out);
+
+/* ---- traversal entry point (hit-ID parity) -------------------------------- */
+
+/* replaces rtTrace(world, ray, prd) for a host ray set (programs/raygen.cu:77):
+ * closest hit in (tmin, tmax), ties -> lowest primitive id.
+ * `counters` (nullable): [0]=BVH8 nodes fetched, [1]=leaf records fetched. */
+int pt_trace_rays(pt_scene* scene, const pt_ray* rays, int64_t n, pt_hit* hits,
+                  uint64_t* counters);
+/* same with device-resident buffers (d_rays/d_hits are CUDA device pointers) */
+int pt_trace_rays_device(pt_scene* scene, const void* d_rays, int64_t n, void* d_hits,
+                         void* cuda_stream);
+
+/* ---- renderer -------------------------------------------------------------- */
+
+/* replaces createFrameBuffer + context["acc_buffer"] (main.cpp:92-93,
+ * host_includes/buffers.hpp:13-18).  d_accum: optional caller-owned device
+ * buffer of width*height float4 (e.g. a torch tensor used as the NCCL reduce
+ * buffer); NULL = library allocates. */
+int pt_renderer_create(pt_scene* scene, int32_t width, int32_t height, void* d_accum,
+                       pt_renderer** out);
+int pt_renderer_destroy(pt_renderer* r);
+
+/* replaces the host loop `context["frame"]->setInt(s); launch(0,W,H)` for
+ * s in [first_frame, first_frame+nframes) (main.cpp:264-293).  frame 0 of a
+ * renderer's life clears the accumulation buffer like raygen.cu:154 does
+ * (clear_accum != 0 forces it).  Asynchronous w.r.t. the host only through
+ * pt_renderer_sync. */
+int pt_render(pt_renderer* r, int32_t first_frame, int32_t nframes, int32_t max_depth,
+              int32_t russian, int32_t clear_accum);
+int pt_renderer_sync(pt_renderer* r);
+
+/* replaces Buffer::map() on accBuffer (host_includes/image_save.hpp:11):
+ * width*height float4, row 0 = top image row, .w = number of samples. */
+int pt_read_accum(pt_renderer* r, float* host_rgba);
+int pt_accum_device_ptr(pt_renderer* r, void** d_ptr);
+
+typedef struct pt_stats {
+  uint64_t samples;        /* camera paths finished                          */
+  uint64_t closest_rays;   /* closest-hit traversal queries                  */
+  uint64_t shadow_rays;    /* shadow traversal queries                       */
+  uint64_t nodes_fetched;  /* BVH8 nodes fetched (instrumented mode only)    */
+  uint64_t leaves_fetched; /* leaf records fetched (instrumented mode only)  */
+  uint64_t iterations;     /* wavefront iterations                           */
+  uint64_t kernel_launches;
+  float ms_total;          /* CUDA-event time of the last pt_render          */
+  float ms_trace_closest;  /* per-kernel-class time (timing mode only)       */
+  float ms_trace_shadow;
+  float ms_shade;
+  float ms_generate;
+} pt_stats;
+int pt_get_stats(pt_renderer* r, pt_stats* out);
+/* bit0: count node/leaf fetches (instrumented kernels); bit1: per-kernel-class
+ * CUDA-event timing (adds synchronisation; off for benchmarking) */
+int pt_renderer_set_flags(pt_renderer* r, int32_t flags);
+/* path-pool capacity (paths in flight); 0 = default */
+int pt_renderer_set_pool(pt_renderer* r, int64_t paths);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PTB200_H */

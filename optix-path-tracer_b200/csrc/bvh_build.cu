@@ -1,0 +1,319 @@
+// bvh_build.cu — GPU BVH builder driver: LBVH (Morton + radix sort + Karras
+// hierarchy) -> bottom-up refit -> binned-SAH treelet refinement -> collapse
+// to the compressed 8-wide BVH.  The per-thread bodies live in bvh_core.h.
+//
+// Replaces the OptiX "Trbvh" builds the reference requests
+// (host_includes/scenes.hpp:205 etc., "OptiX Building Time" main.cpp:99).
+#include <cub/cub.cuh>
+
+#include <cfloat>
+#include <cstdio>
+
+#include "scene_host.h"
+
+namespace {
+
+constexpr int TB = 256;
+inline int nblk(long long n, int tb = TB) { return (int)((n + tb - 1) / tb); }
+
+__device__ __forceinline__ void atomic_min_f(float* addr, float v) {
+  // valid for any sign: order-preserving int mapping
+  if (v >= 0.f) atomicMin((int*)addr, __float_as_int(v));
+  else atomicMax((unsigned*)addr, __float_as_uint(v));
+}
+__device__ __forceinline__ void atomic_max_f(float* addr, float v) {
+  if (v >= 0.f) atomicMax((int*)addr, __float_as_int(v));
+  else atomicMin((unsigned*)addr, __float_as_uint(v));
+}
+
+// scene_bounds: [0..2] centroid min, [3..5] centroid max
+__global__ void k_prim_bounds(BuildIn in, float4* plo, float4* phi, float* scene_bounds) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  float3 c = f3(0.f);
+  bool ok = i < in.n;
+  if (ok) {
+    float3 lo, hi;
+    prim_bounds(in, i, lo, hi);
+    plo[i] = make_float4(lo.x, lo.y, lo.z, 0.f);
+    phi[i] = make_float4(hi.x, hi.y, hi.z, 0.f);
+    c = (lo + hi) * 0.5f;
+  }
+  // warp reduce then one atomic per warp
+  float mn[3] = {ok ? c.x : FLT_MAX, ok ? c.y : FLT_MAX, ok ? c.z : FLT_MAX};
+  float mx[3] = {ok ? c.x : -FLT_MAX, ok ? c.y : -FLT_MAX, ok ? c.z : -FLT_MAX};
+  for (int o = 16; o > 0; o >>= 1)
+    for (int a = 0; a < 3; a++) {
+      mn[a] = fminf(mn[a], __shfl_xor_sync(0xffffffffu, mn[a], o));
+      mx[a] = fmaxf(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], o));
+    }
+  if ((threadIdx.x & 31) == 0)
+    for (int a = 0; a < 3; a++) {
+      if (mn[a] != FLT_MAX) atomic_min_f(scene_bounds + a, mn[a]);
+      if (mx[a] != -FLT_MAX) atomic_max_f(scene_bounds + 3 + a, mx[a]);
+    }
+}
+
+__global__ void k_morton(int n, const float4* plo, const float4* phi, const float* sb, uint64_t* keys,
+                         uint32_t* vals) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float3 smin = f3(sb[0], sb[1], sb[2]);
+  float3 ext = f3(sb[3], sb[4], sb[5]) - smin;
+  float3 sinv = f3(ext.x > 0.f ? 1.f / ext.x : 0.f, ext.y > 0.f ? 1.f / ext.y : 0.f, ext.z > 0.f ? 1.f / ext.z : 0.f);
+  float3 c = (xyz(plo[i]) + xyz(phi[i])) * 0.5f;
+  keys[i] = morton63(c, smin, sinv);
+  vals[i] = (uint32_t)i;
+}
+
+__global__ void k_karras(Bvh2 t) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < t.n - 1) karras_node(t, i);
+}
+
+__device__ __forceinline__ void child_box_cg(const Bvh2& t, int ref, float3& lo, float3& hi, int& cnt) {
+  if (ref >= 0) {  // written by another thread in this kernel: bypass L1
+    const float4* p = (const float4*)(t.nodes + ref);
+    float4 a = __ldcg(p), b = __ldcg(p + 1);
+    lo = f3(a.x, a.y, a.z);
+    hi = f3(b.x, b.y, b.z);
+    cnt = __ldcg(t.count + ref);
+  } else {
+    uint32_t id = t.sorted[~ref];
+    lo = xyz(t.plo[id]);
+    hi = xyz(t.phi[id]);
+    cnt = 1;
+  }
+}
+
+__global__ void k_refit(Bvh2 t) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= t.n) return;
+  int cur = t.leaf_parent[j];
+  while (cur >= 0) {
+    __threadfence();
+    int old = atomicAdd(t.flag + cur, 1);
+    if (old == 0) return;  // sibling subtree not finished yet
+    Bvh2Node nd = t.nodes[cur];
+    float3 llo, lhi, rlo, rhi;
+    int lc, rc;
+    child_box_cg(t, nd.left, llo, lhi, lc);
+    child_box_cg(t, nd.right, rlo, rhi, rc);
+    bvh2_set_box(nd, fmin3(llo, rlo), fmax3(lhi, rhi));
+    t.nodes[cur] = nd;
+    t.count[cur] = lc + rc;
+    cur = t.parent[cur];
+  }
+}
+
+__global__ void k_treelet_mark(Bvh2 t, int* roots, int* n_roots) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= t.n - 1) return;
+  if (treelet_is_root(t, i)) roots[atomicAdd(n_roots, 1)] = i;
+}
+__global__ void k_treelet_sah(Bvh2 t, const int* roots, int n_roots) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_roots) treelet_sah(t, roots[i]);
+}
+
+// SAH cost: sum of inner-node areas (C_trav = 1) + leaf areas (C_isect = 1), over root area
+__global__ void k_sah_cost(Bvh2 t, double* out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double a = 0.0;
+  if (i < t.n - 1) {
+    const Bvh2Node& nd = t.nodes[i];
+    a = (double)box_half_area(f3(nd.lo[0], nd.lo[1], nd.lo[2]), f3(nd.hi[0], nd.hi[1], nd.hi[2]));
+  }
+  for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+  if ((threadIdx.x & 31) == 0 && a != 0.0) atomicAdd(out, a);
+}
+
+__global__ void k_collapse(Collapse c, const uint2* work, int n_work, uint2* out_work, int* out_count) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_work) return;
+  uint2 w = work[i];
+  collapse_node(c, (int)w.x, (int)w.y, out_work, out_count);
+}
+
+template <typename T>
+int upload(DevBuf& b, const std::vector<T>& v) {
+  PT_CUDA(b.alloc(v.size() * sizeof(T)));
+  if (!v.empty()) PT_CUDA(cudaMemcpy(b.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return PT_OK;
+}
+
+}  // namespace
+
+int pt_bvh_build(pt_scene* s) {
+  const int n = (int)s->prims.size();
+  if (n <= 0) {
+    pt_set_error("scene has no primitives");
+    return PT_ERR_INVALID;
+  }
+  cudaEvent_t ev0, ev1;
+  PT_CUDA(cudaEventCreate(&ev0));
+  PT_CUDA(cudaEventCreate(&ev1));
+  PT_CUDA(cudaEventRecord(ev0));
+
+  BuildIn in;
+  in.prim_ref = s->d_prim_ref.as<pt_prim_ref>();
+  in.spheres = s->d_spheres.as<pt_sphere>();
+  in.rects = s->d_rects.as<pt_rect>();
+  in.boxes = s->d_boxes.as<pt_box>();
+  in.tri_v = s->d_tri_v.as<float>();
+  in.xforms = s->d_xforms.as<pt_xform>();
+  in.materials = s->d_materials.as<pt_material>();
+  in.n = n;
+
+  DevBuf plo, phi, sbounds, keys, keys2, vals, vals2, cubtmp;
+  DevBuf nodes2, parent, leaf_parent, count, flag, roots, counters, cost;
+  PT_CUDA(plo.alloc((size_t)n * 16));
+  PT_CUDA(phi.alloc((size_t)n * 16));
+  PT_CUDA(sbounds.alloc(6 * 4));
+  {
+    float init[6] = {FLT_MAX, FLT_MAX, FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX};
+    PT_CUDA(cudaMemcpy(sbounds.p, init, sizeof(init), cudaMemcpyHostToDevice));
+  }
+  k_prim_bounds<<<nblk(n), TB>>>(in, plo.as<float4>(), phi.as<float4>(), sbounds.as<float>());
+  PT_CUDA(cudaGetLastError());
+
+  PT_CUDA(keys.alloc((size_t)n * 8));
+  PT_CUDA(keys2.alloc((size_t)n * 8));
+  PT_CUDA(vals.alloc((size_t)n * 4));
+  PT_CUDA(vals2.alloc((size_t)n * 4));
+  k_morton<<<nblk(n), TB>>>(n, plo.as<float4>(), phi.as<float4>(), sbounds.as<float>(), keys.as<uint64_t>(),
+                            vals.as<uint32_t>());
+  PT_CUDA(cudaGetLastError());
+  {
+    size_t tmp = 0;
+    PT_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp, keys.as<uint64_t>(), keys2.as<uint64_t>(),
+                                            vals.as<uint32_t>(), vals2.as<uint32_t>(), n, 0, 63));
+    PT_CUDA(cubtmp.alloc(tmp));
+    PT_CUDA(cub::DeviceRadixSort::SortPairs(cubtmp.p, tmp, keys.as<uint64_t>(), keys2.as<uint64_t>(),
+                                            vals.as<uint32_t>(), vals2.as<uint32_t>(), n, 0, 63));
+  }
+
+  const int ni = n > 1 ? n - 1 : 1;
+  PT_CUDA(nodes2.alloc((size_t)ni * sizeof(Bvh2Node)));
+  PT_CUDA(parent.alloc((size_t)ni * 4));
+  PT_CUDA(leaf_parent.alloc((size_t)n * 4));
+  PT_CUDA(count.alloc((size_t)ni * 4));
+  PT_CUDA(flag.alloc((size_t)ni * 4));
+  PT_CUDA(cudaMemset(flag.p, 0, (size_t)ni * 4));
+  PT_CUDA(cudaMemset(leaf_parent.p, 0xff, (size_t)n * 4));
+  PT_CUDA(cudaMemset(parent.p, 0xff, (size_t)ni * 4));
+  PT_CUDA(cudaMemset(count.p, 0, (size_t)ni * 4));
+
+  Bvh2 t;
+  t.nodes = nodes2.as<Bvh2Node>();
+  t.parent = parent.as<int>();
+  t.leaf_parent = leaf_parent.as<int>();
+  t.count = count.as<int>();
+  t.flag = flag.as<int>();
+  t.keys = keys2.as<uint64_t>();
+  t.sorted = vals2.as<uint32_t>();
+  t.plo = plo.as<float4>();
+  t.phi = phi.as<float4>();
+  t.n = n;
+
+  double cost_lbvh = 0.0, cost_ref = 0.0;
+  PT_CUDA(counters.alloc(64));
+  PT_CUDA(cost.alloc(16));
+  if (n > 1) {
+    k_karras<<<nblk(n - 1), TB>>>(t);
+    PT_CUDA(cudaGetLastError());
+    k_refit<<<nblk(n), TB>>>(t);
+    PT_CUDA(cudaGetLastError());
+
+    PT_CUDA(cudaMemset(cost.p, 0, 16));
+    k_sah_cost<<<nblk(n - 1), TB>>>(t, cost.as<double>());
+    // treelet refinement
+    PT_CUDA(roots.alloc((size_t)ni * 4));
+    PT_CUDA(cudaMemset(counters.p, 0, 64));
+    k_treelet_mark<<<nblk(n - 1), TB>>>(t, roots.as<int>(), counters.as<int>());
+    PT_CUDA(cudaGetLastError());
+    int n_roots = 0;
+    PT_CUDA(cudaMemcpy(&n_roots, counters.p, 4, cudaMemcpyDeviceToHost));
+    if (n_roots > 0) {
+      k_treelet_sah<<<nblk(n_roots, 64), 64>>>(t, roots.as<int>(), n_roots);
+      PT_CUDA(cudaGetLastError());
+    }
+    k_sah_cost<<<nblk(n - 1), TB>>>(t, cost.as<double>() + 1);
+    double hc[2];
+    PT_CUDA(cudaMemcpy(hc, cost.p, 16, cudaMemcpyDeviceToHost));
+    Bvh2Node root;
+    PT_CUDA(cudaMemcpy(&root, nodes2.p, sizeof(root), cudaMemcpyDeviceToHost));
+    double ra = (double)box_half_area(f3(root.lo[0], root.lo[1], root.lo[2]), f3(root.hi[0], root.hi[1], root.hi[2]));
+    if (ra > 0.0) {
+      cost_lbvh = hc[0] / ra;
+      cost_ref = hc[1] / ra;
+    }
+  }
+
+  // collapse: level-synchronous work lists
+  PT_CUDA(s->d_nodes8.alloc((size_t)(n > 1 ? n : 2) * 80));
+  PT_CUDA(s->d_leaves.alloc((size_t)n * sizeof(LeafRec)));
+  PT_CUDA(s->d_prim_leaf.alloc((size_t)n * 4));
+  DevBuf workA, workB;
+  PT_CUDA(workA.alloc((size_t)n * 8 + 64));
+  PT_CUDA(workB.alloc((size_t)n * 8 + 64));
+  Collapse c;
+  c.t = t;
+  c.in = in;
+  c.nodes8 = s->d_nodes8.as<uint4>();
+  c.leaves = s->d_leaves.as<LeafRec>();
+  c.prim_leaf = s->d_prim_leaf.as<int>();
+  int* d_cnt = counters.as<int>();  // [0]=node counter [1]=leaf counter [2]=work count
+  {
+    int init[3] = {1, 0, 0};
+    PT_CUDA(cudaMemcpy(d_cnt, init, sizeof(init), cudaMemcpyHostToDevice));
+  }
+  c.node_counter = d_cnt;
+  c.leaf_counter = d_cnt + 1;
+  uint2 first = make_uint2(n > 1 ? 0u : (uint32_t)~0, 0u);  // n==1: leaf ref ~0
+  PT_CUDA(cudaMemcpy(workA.p, &first, sizeof(first), cudaMemcpyHostToDevice));
+  int n_work = 1;
+  uint2* wa = workA.as<uint2>();
+  uint2* wb = workB.as<uint2>();
+  int levels = 0;
+  while (n_work > 0) {
+    PT_CUDA(cudaMemset(d_cnt + 2, 0, 4));
+    k_collapse<<<nblk(n_work, 128), 128>>>(c, wa, n_work, wb, d_cnt + 2);
+    PT_CUDA(cudaGetLastError());
+    PT_CUDA(cudaMemcpy(&n_work, d_cnt + 2, 4, cudaMemcpyDeviceToHost));
+    std::swap(wa, wb);
+    if (++levels > 128) {
+      pt_set_error("BVH collapse did not terminate");
+      return PT_ERR_INVALID;
+    }
+  }
+  int hcnt[2];
+  PT_CUDA(cudaMemcpy(hcnt, d_cnt, 8, cudaMemcpyDeviceToHost));
+  PT_CUDA(cudaEventRecord(ev1));
+  PT_CUDA(cudaEventSynchronize(ev1));
+  float ms = 0.f;
+  PT_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
+  cudaEventDestroy(ev0);
+  cudaEventDestroy(ev1);
+  if (hcnt[1] != n) {
+    pt_set_error("BVH collapse wrote %d leaf records for %d primitives", hcnt[1], n);
+    return PT_ERR_INVALID;
+  }
+  // shrink the node array to its final size
+  {
+    DevBuf tight;
+    PT_CUDA(tight.alloc((size_t)hcnt[0] * 80));
+    PT_CUDA(cudaMemcpy(tight.p, s->d_nodes8.p, (size_t)hcnt[0] * 80, cudaMemcpyDeviceToDevice));
+    std::swap(tight.p, s->d_nodes8.p);
+    std::swap(tight.bytes, s->d_nodes8.bytes);
+  }
+  s->info.n_prims = n;
+  s->info.n_bvh2_nodes = n > 1 ? n - 1 : 0;
+  s->info.n_bvh8_nodes = hcnt[0];
+  s->info.n_leaf_records = hcnt[1];
+  s->info.sah_cost_lbvh = (float)cost_lbvh;
+  s->info.sah_cost_refined = (float)cost_ref;
+  s->info.build_ms = ms;
+  s->info.node_bytes = (int64_t)hcnt[0] * 80;
+  s->info.leaf_bytes = (int64_t)hcnt[1] * (int64_t)sizeof(LeafRec);
+  return PT_OK;
+}

@@ -1,0 +1,518 @@
+// bvh_core.h — per-thread bodies of the GPU BVH builder (PT_HD so that
+// tests/hostsim can run the same code serially on the CPU).
+//
+// Replaces OptiX's closed "Trbvh" acceleration build that the reference
+// requests at host_includes/scenes.hpp:32,112,205,278,393 and the
+// Get_Bounds programs (programs/hitables/*.cu).  Pipeline (bvh_build.cu):
+//   1 prim_bounds      world AABB per primitive (+padding), scene bounds
+//   2 morton63         63-bit Morton code of the AABB centre, radix sort
+//   3 karras_node      LBVH hierarchy (Karras 2012), one thread / inner node
+//   4 refit_leaf       bottom-up AABB + leaf-count refit (atomic arrival flags)
+//   5 treelet_sah      binned-SAH rebuild of every maximal subtree with
+//                      <= PT_TREELET leaves, in place (subtrees are contiguous
+//                      in Morton order, so node storage is reused)
+//   6 collapse_node    BVH2 -> 8-wide: greedy surface-area expansion, octant
+//                      slot assignment, child-box quantisation, leaf records
+#pragma once
+#include "scene_dev.h"
+
+#define PT_TREELET 64
+#define PT_SAH_BINS 8
+
+struct BuildIn {  // device copies of the flat scene arrays
+  const pt_prim_ref* prim_ref;
+  const pt_sphere* spheres;
+  const pt_rect* rects;
+  const pt_box* boxes;
+  const float* tri_v;
+  const pt_xform* xforms;
+  const pt_material* materials;
+  int n;
+};
+
+struct Bvh2 {  // LBVH / refined binary BVH over Morton-sorted primitives
+  Bvh2Node* nodes;    // n-1 inner nodes
+  int* parent;        // parent of inner node (root: -1)
+  int* leaf_parent;   // parent of sorted leaf j
+  int* count;         // leaves under inner node
+  int* flag;          // refit arrival counters
+  const uint64_t* keys;     // sorted Morton codes
+  const uint32_t* sorted;   // sorted position -> primitive id
+  const float4* plo;        // per primitive id: padded AABB (xyz)
+  const float4* phi;
+  int n;
+};
+
+// ---- 1: primitive bounds ---------------------------------------------------------
+PT_HD void prim_bounds(const BuildIn& in, int id, float3& lo, float3& hi) {
+  const pt_prim_ref p = in.prim_ref[id];
+  if (p.type == PT_PRIM_TRIANGLE) {  // programs/hitables/triangle.cu:61-83
+    const float* v = in.tri_v + 9 * (size_t)p.index;
+    float3 a = f3(v[0], v[1], v[2]), b = f3(v[3], v[4], v[5]), c = f3(v[6], v[7], v[8]);
+    lo = fmin3(fmin3(a, b), c);
+    hi = fmax3(fmax3(a, b), c);
+  } else if (p.type == PT_PRIM_SPHERE) {  // programs/hitables/sphere.cu:96-100
+    const pt_sphere s = in.spheres[p.index];
+    float3 c = f3(s.center[0], s.center[1], s.center[2]);
+    lo = c - s.radius;
+    hi = c + s.radius;
+  } else if (p.type == PT_PRIM_RECT) {  // programs/hitables/aarect.cu:117-136
+    const pt_rect q = in.rects[p.index];
+    if (q.axis == PT_X_AXIS) {
+      lo = f3(q.k, q.a0, q.b0);
+      hi = f3(q.k, q.a1, q.b1);
+    } else if (q.axis == PT_Y_AXIS) {
+      lo = f3(q.a0, q.k, q.b0);
+      hi = f3(q.a1, q.k, q.b1);
+    } else {
+      lo = f3(q.a0, q.b0, q.k);
+      hi = f3(q.a1, q.b1, q.k);
+    }
+  } else {  // programs/hitables/box.cu:84-88
+    const pt_box q = in.boxes[p.index];
+    lo = f3(q.bmin[0], q.bmin[1], q.bmin[2]);
+    hi = f3(q.bmax[0], q.bmax[1], q.bmax[2]);
+    float3 l2 = fmin3(lo, hi), h2 = fmax3(lo, hi);
+    lo = l2;
+    hi = h2;
+  }
+  if (p.xform >= 0) {  // Transform node: bound the 8 transformed corners
+    const float* m = in.xforms[p.xform].o2w;
+    float3 nlo = f3(INFINITY), nhi = f3(-INFINITY);
+    for (int c = 0; c < 8; c++) {
+      float3 q = xf_point(m, f3((c & 1) ? hi.x : lo.x, (c & 2) ? hi.y : lo.y, (c & 4) ? hi.z : lo.z));
+      nlo = fmin3(nlo, q);
+      nhi = fmax3(nhi, q);
+    }
+    lo = nlo;
+    hi = nhi;
+  }
+  // The reference pads 1e-4 (rect/triangle) .. 1e-3 (box).  Pad every axis by
+  // an absolute + relative margin so the (FMA, quantised) box test can never
+  // cull a primitive the exact intersection test would accept.
+  float3 m = fmax3(f3(fabsf(lo.x), fabsf(lo.y), fabsf(lo.z)), f3(fabsf(hi.x), fabsf(hi.y), fabsf(hi.z)));
+  float3 pad = f3(1e-3f) + m * 1e-5f;
+  lo = lo - pad;
+  hi = hi + pad;
+}
+
+// ---- 2: Morton code ---------------------------------------------------------------------
+PT_HD uint64_t expand_bits21(uint64_t x) {
+  x &= 0x1fffffull;
+  x = (x | x << 32) & 0x1f00000000ffffull;
+  x = (x | x << 16) & 0x1f0000ff0000ffull;
+  x = (x | x << 8) & 0x100f00f00f00f00full;
+  x = (x | x << 4) & 0x10c30c30c30c30c3ull;
+  x = (x | x << 2) & 0x1249249249249249ull;
+  return x;
+}
+PT_HD uint64_t morton63(float3 c, float3 smin, float3 sinv) {
+  float x = fminf(fmaxf((c.x - smin.x) * sinv.x * 2097152.0f, 0.0f), 2097151.0f);
+  float y = fminf(fmaxf((c.y - smin.y) * sinv.y * 2097152.0f, 0.0f), 2097151.0f);
+  float z = fminf(fmaxf((c.z - smin.z) * sinv.z * 2097152.0f, 0.0f), 2097151.0f);
+  if (!(x == x)) x = 0.f;
+  if (!(y == y)) y = 0.f;
+  if (!(z == z)) z = 0.f;
+  return (expand_bits21((uint64_t)x) << 2) | (expand_bits21((uint64_t)y) << 1) | expand_bits21((uint64_t)z);
+}
+
+// ---- 3: Karras LBVH hierarchy --------------------------------------------------------
+PT_HD int lbvh_delta(const uint64_t* keys, int n, int i, int j) {
+  if (j < 0 || j >= n) return -1;
+  uint64_t a = keys[i], b = keys[j];
+  if (a == b) return 64 + pt_clz32((uint32_t)i ^ (uint32_t)j);
+  return pt_clz64(a ^ b);
+}
+// child refs: >= 0 inner node, < 0 sorted leaf ~ref
+PT_HD void karras_node(const Bvh2& t, int i) {
+  const int n = t.n;
+  const uint64_t* k = t.keys;
+  int d = (lbvh_delta(k, n, i, i + 1) - lbvh_delta(k, n, i, i - 1)) >= 0 ? 1 : -1;
+  int dmin = lbvh_delta(k, n, i, i - d);
+  int lmax = 2;
+  while (lbvh_delta(k, n, i, i + lmax * d) > dmin) lmax *= 2;
+  int l = 0;
+  for (int s = lmax / 2; s >= 1; s /= 2)
+    if (lbvh_delta(k, n, i, i + (l + s) * d) > dmin) l += s;
+  int j = i + l * d;
+  int dnode = lbvh_delta(k, n, i, j);
+  int s = 0;
+  int tt = l;
+  do {
+    tt = (tt + 1) >> 1;
+    if (lbvh_delta(k, n, i, i + (s + tt) * d) > dnode) s += tt;
+  } while (tt > 1);
+  int gamma = i + s * d + (d < 0 ? d : 0);
+  int lo = i < j ? i : j, hi = i < j ? j : i;
+  int left = (lo == gamma) ? ~gamma : gamma;
+  int right = (hi == gamma + 1) ? ~(gamma + 1) : (gamma + 1);
+  t.nodes[i].left = left;
+  t.nodes[i].right = right;
+  if (left >= 0) t.parent[left] = i; else t.leaf_parent[~left] = i;
+  if (right >= 0) t.parent[right] = i; else t.leaf_parent[~right] = i;
+  if (i == 0) t.parent[0] = -1;
+}
+
+PT_HD void bvh2_child_box(const Bvh2& t, int ref, float3& lo, float3& hi, int& cnt) {
+  if (ref >= 0) {
+    const Bvh2Node& c = t.nodes[ref];
+    lo = f3(c.lo[0], c.lo[1], c.lo[2]);
+    hi = f3(c.hi[0], c.hi[1], c.hi[2]);
+    cnt = t.count[ref];
+  } else {
+    uint32_t id = t.sorted[~ref];
+    lo = xyz(t.plo[id]);
+    hi = xyz(t.phi[id]);
+    cnt = 1;
+  }
+}
+PT_HD void bvh2_set_box(Bvh2Node& nd, float3 lo, float3 hi) {
+  nd.lo[0] = lo.x; nd.lo[1] = lo.y; nd.lo[2] = lo.z;
+  nd.hi[0] = hi.x; nd.hi[1] = hi.y; nd.hi[2] = hi.z;
+}
+PT_HD float box_half_area(float3 lo, float3 hi) {
+  float3 e = hi - lo;
+  return e.x * e.y + e.y * e.z + e.z * e.x;
+}
+
+// ---- 5: binned-SAH treelet rebuild -----------------------------------------------------
+// One thread rebuilds the subtree rooted at inner node r (<= PT_TREELET leaves)
+// top-down with binned SAH over the leaves' AABB centres, reusing the subtree's
+// own inner-node slots.  Boxes and counts are written as part of the rebuild.
+PT_HD bool treelet_is_root(const Bvh2& t, int r) {
+  int c = t.count[r];
+  if (c < 3 || c > PT_TREELET) return false;
+  int p = t.parent[r];
+  return p < 0 || t.count[p] > PT_TREELET;
+}
+
+PT_HD void treelet_sah(const Bvh2& t, int r) {
+  int items[PT_TREELET];      // sorted leaf positions
+  int slots[PT_TREELET];      // inner node indices owned by this subtree
+  int m = 0, ns = 0;
+  {
+    int st[PT_TREELET];
+    int sp = 0;
+    st[sp++] = r;
+    while (sp) {
+      int nd = st[--sp];
+      slots[ns++] = nd;
+      int l = t.nodes[nd].left, rr = t.nodes[nd].right;
+      if (rr >= 0) st[sp++] = rr; else items[m++] = ~rr;
+      if (l >= 0) st[sp++] = l; else items[m++] = ~l;
+    }
+  }
+  // work stack of ranges: node slot, [lo,hi)
+  int wnode[PT_TREELET], wlo[PT_TREELET], whi[PT_TREELET];
+  int wp = 0, next_slot = 1;
+  wnode[0] = slots[0];
+  wlo[0] = 0;
+  whi[0] = m;
+  wp = 1;
+  while (wp) {
+    --wp;
+    const int node = wnode[wp], lo = wlo[wp], hi = whi[wp];
+    // bounds of the range + centroid bounds
+    float3 blo = f3(INFINITY), bhi = f3(-INFINITY), clo = blo, chi = bhi;
+    for (int i = lo; i < hi; i++) {
+      uint32_t id = t.sorted[items[i]];
+      float3 a = xyz(t.plo[id]), b = xyz(t.phi[id]);
+      blo = fmin3(blo, a);
+      bhi = fmax3(bhi, b);
+      float3 c = (a + b) * 0.5f;
+      clo = fmin3(clo, c);
+      chi = fmax3(chi, c);
+    }
+    bvh2_set_box(t.nodes[node], blo, bhi);
+    t.count[node] = hi - lo;
+    int mid = -1;
+    if (hi - lo > 2) {
+      float best = INFINITY;
+      int bestAxis = -1, bestBin = -1;
+      for (int ax = 0; ax < 3; ax++) {
+        float cmin = comp(clo, ax), cmax = comp(chi, ax);
+        if (!(cmax > cmin)) continue;
+        float scale = (float)PT_SAH_BINS / (cmax - cmin);
+        float3 binlo[PT_SAH_BINS], binhi[PT_SAH_BINS];
+        int bincnt[PT_SAH_BINS];
+        for (int b = 0; b < PT_SAH_BINS; b++) {
+          binlo[b] = f3(INFINITY);
+          binhi[b] = f3(-INFINITY);
+          bincnt[b] = 0;
+        }
+        for (int i = lo; i < hi; i++) {
+          uint32_t id = t.sorted[items[i]];
+          float3 a = xyz(t.plo[id]), b = xyz(t.phi[id]);
+          float c = (comp(a, ax) + comp(b, ax)) * 0.5f;
+          int bi = (int)((c - cmin) * scale);
+          bi = bi < 0 ? 0 : (bi > PT_SAH_BINS - 1 ? PT_SAH_BINS - 1 : bi);
+          binlo[bi] = fmin3(binlo[bi], a);
+          binhi[bi] = fmax3(binhi[bi], b);
+          bincnt[bi]++;
+        }
+        float rarea[PT_SAH_BINS];
+        int rcnt[PT_SAH_BINS];
+        float3 alo = f3(INFINITY), ahi = f3(-INFINITY);
+        int c = 0;
+        for (int b = PT_SAH_BINS - 1; b > 0; b--) {
+          alo = fmin3(alo, binlo[b]);
+          ahi = fmax3(ahi, binhi[b]);
+          c += bincnt[b];
+          rarea[b] = c ? box_half_area(alo, ahi) : 0.f;
+          rcnt[b] = c;
+        }
+        alo = f3(INFINITY);
+        ahi = f3(-INFINITY);
+        c = 0;
+        for (int b = 0; b < PT_SAH_BINS - 1; b++) {
+          alo = fmin3(alo, binlo[b]);
+          ahi = fmax3(ahi, binhi[b]);
+          c += bincnt[b];
+          if (c == 0 || rcnt[b + 1] == 0) continue;
+          float cost = box_half_area(alo, ahi) * (float)c + rarea[b + 1] * (float)rcnt[b + 1];
+          if (cost < best) {
+            best = cost;
+            bestAxis = ax;
+            bestBin = b;
+          }
+        }
+      }
+      if (bestAxis >= 0) {
+        float cmin = comp(clo, bestAxis), cmax = comp(chi, bestAxis);
+        float scale = (float)PT_SAH_BINS / (cmax - cmin);
+        int i = lo, j = hi - 1;
+        while (i <= j) {
+          uint32_t id = t.sorted[items[i]];
+          float c = (comp(xyz(t.plo[id]), bestAxis) + comp(xyz(t.phi[id]), bestAxis)) * 0.5f;
+          int bi = (int)((c - cmin) * scale);
+          bi = bi < 0 ? 0 : (bi > PT_SAH_BINS - 1 ? PT_SAH_BINS - 1 : bi);
+          if (bi <= bestBin) {
+            i++;
+          } else {
+            int tmp = items[i];
+            items[i] = items[j];
+            items[j] = tmp;
+            j--;
+          }
+        }
+        mid = i;
+      }
+    }
+    if (mid <= lo || mid >= hi) mid = (lo + hi) >> 1;  // degenerate: keep Morton order, halve
+    int refs[2];
+    for (int side = 0; side < 2; side++) {
+      int a = side ? mid : lo, b = side ? hi : mid;
+      if (b - a == 1) {
+        refs[side] = ~items[a];
+        t.leaf_parent[items[a]] = node;
+      } else {
+        int child = slots[next_slot++];
+        refs[side] = child;
+        t.parent[child] = node;
+        wnode[wp] = child;
+        wlo[wp] = a;
+        whi[wp] = b;
+        wp++;
+      }
+    }
+    t.nodes[node].left = refs[0];
+    t.nodes[node].right = refs[1];
+  }
+}
+
+// ---- 6: collapse to the compressed 8-wide BVH ----------------------------------------------
+struct Collapse {
+  Bvh2 t;
+  BuildIn in;
+  uint4* nodes8;
+  LeafRec* leaves;
+  int* prim_leaf;
+  int* node_counter;   // next free BVH8 node
+  int* leaf_counter;   // next free leaf record
+};
+
+PT_HD LeafRec make_leaf_rec(const BuildIn& in, int id) {
+  const pt_prim_ref p = in.prim_ref[id];
+  LeafRec L;
+  uint32_t kindw = (uint32_t)p.type | ((uint32_t)(p.xform + 1) << 8);
+  L.a = make_float4(0.f, 0.f, 0.f, pt_u2f((uint32_t)id));
+  L.b = make_float4(0.f, 0.f, 0.f, pt_u2f(kindw));
+  // material id in the low 24 bits, its PT_MAT_* type in the top 8 (lets the
+  // trace kernel bin a path by material without touching the material table)
+  L.c = make_float4(0.f, 0.f, 0.f,
+                    pt_u2f(((uint32_t)p.material & 0xffffffu) | ((uint32_t)in.materials[p.material].type << 24)));
+  if (p.type == PT_PRIM_TRIANGLE) {
+    const float* v = in.tri_v + 9 * (size_t)p.index;
+    L.a.x = v[0]; L.a.y = v[1]; L.a.z = v[2];
+    L.b.x = v[3]; L.b.y = v[4]; L.b.z = v[5];
+    L.c.x = v[6]; L.c.y = v[7]; L.c.z = v[8];
+  } else if (p.type == PT_PRIM_SPHERE) {
+    const pt_sphere s = in.spheres[p.index];
+    L.a.x = s.center[0]; L.a.y = s.center[1]; L.a.z = s.center[2];
+    L.b.x = s.radius;
+  } else if (p.type == PT_PRIM_RECT) {
+    const pt_rect q = in.rects[p.index];
+    L.a.x = q.a0; L.a.y = q.a1; L.a.z = q.b0;
+    L.b.x = q.b1; L.b.y = q.k;
+    L.b.z = pt_u2f((uint32_t)(q.axis & 3) | (q.flip ? 4u : 0u));
+  } else {
+    const pt_box q = in.boxes[p.index];
+    L.a.x = q.bmin[0]; L.a.y = q.bmin[1]; L.a.z = q.bmin[2];
+    L.b.x = q.bmax[0]; L.b.y = q.bmax[1]; L.b.z = q.bmax[2];
+  }
+  return L;
+}
+
+PT_HD uint32_t quant_exp(float ext) {  // biased exponent byte: 2^(eb-127)*255 >= ext
+  float s = ext / 255.0f;
+  uint32_t bits = pt_f2u(s);
+  uint32_t eb = (bits >> 23) & 0xffu;
+  if (bits & 0x7fffffu) eb += 1;
+  if (eb < 1) eb = 1;
+  if (eb > 254) eb = 254;
+  while (eb < 254 && ceilf(ext / pt_u2f(eb << 23)) > 255.0f) eb++;
+  return eb;
+}
+
+#ifdef __CUDA_ARCH__
+#define PT_ATOMIC_ADD(p, v) atomicAdd((p), (v))
+#else
+PT_HD int pt_host_atomic_add(int* p, int v) { int o = *p; *p += v; return o; }
+#define PT_ATOMIC_ADD(p, v) pt_host_atomic_add((p), (v))
+#endif
+
+// Builds BVH8 node `dst` from BVH2 subtree `ref`; appends inner children to the
+// next-level work list (pairs ref, dst) via out_count.
+PT_HD void collapse_node(const Collapse& c, int ref, int dst, uint2* out_work, int* out_count) {
+  const Bvh2& t = c.t;
+  int cref[8], ccnt[8];
+  float3 clo[8], chi[8];
+  int n = 0;
+  if (ref >= 0) {
+    cref[0] = t.nodes[ref].left;
+    cref[1] = t.nodes[ref].right;
+    n = 2;
+  } else {
+    cref[0] = ref;
+    n = 1;
+  }
+  for (int i = 0; i < n; i++) bvh2_child_box(t, cref[i], clo[i], chi[i], ccnt[i]);
+  // greedy expansion by surface area: first only subtrees too big for a leaf
+  // (> 3 primitives), then any inner node while slots remain
+  for (int pass = 0; pass < 2; pass++) {
+    const int minc = pass == 0 ? 4 : 2;
+    while (n < 8) {
+      int bi = -1;
+      float ba = -1.f;
+      for (int i = 0; i < n; i++)
+        if (cref[i] >= 0 && ccnt[i] >= minc) {
+          float a = box_half_area(clo[i], chi[i]);
+          if (a > ba) {
+            ba = a;
+            bi = i;
+          }
+        }
+      if (bi < 0) break;
+      int l = t.nodes[cref[bi]].left, r = t.nodes[cref[bi]].right;
+      cref[bi] = l;
+      bvh2_child_box(t, l, clo[bi], chi[bi], ccnt[bi]);
+      cref[n] = r;
+      bvh2_child_box(t, r, clo[n], chi[n], ccnt[n]);
+      n++;
+    }
+  }
+  // node frame
+  float3 nlo = clo[0], nhi = chi[0];
+  for (int i = 1; i < n; i++) {
+    nlo = fmin3(nlo, clo[i]);
+    nhi = fmax3(nhi, chi[i]);
+  }
+  const uint32_t ex = quant_exp(nhi.x - nlo.x), ey = quant_exp(nhi.y - nlo.y), ez = quant_exp(nhi.z - nlo.z);
+  const float sx = pt_u2f(ex << 23), sy = pt_u2f(ey << 23), sz = pt_u2f(ez << 23);
+  // octant slot assignment (greedy max of dot(child centre - node centre, slot dir))
+  int slot_of[8], child_in[8];
+  for (int i = 0; i < 8; i++) {
+    slot_of[i] = -1;
+    child_in[i] = -1;
+  }
+  float3 nc = (nlo + nhi) * 0.5f;
+  for (int k = 0; k < n; k++) {
+    float best = -INFINITY;
+    int bc = -1, bs = -1;
+    for (int i = 0; i < n; i++) {
+      if (slot_of[i] >= 0) continue;
+      float3 dc = (clo[i] + chi[i]) * 0.5f - nc;
+      for (int s = 0; s < 8; s++) {
+        if (child_in[s] >= 0) continue;
+        float cost = ((s & 4) ? dc.x : -dc.x) + ((s & 2) ? dc.y : -dc.y) + ((s & 1) ? dc.z : -dc.z);
+        if (cost > best) {
+          best = cost;
+          bc = i;
+          bs = s;
+        }
+      }
+    }
+    slot_of[bc] = bs;
+    child_in[bs] = bc;
+  }
+  int n_inner = 0, n_leafprims = 0;
+  for (int i = 0; i < n; i++) {
+    if (cref[i] >= 0 && ccnt[i] > 3) n_inner++;
+    else n_leafprims += ccnt[i];
+  }
+  const int child_base = n_inner ? PT_ATOMIC_ADD(c.node_counter, n_inner) : 0;
+  const int leaf_base = n_leafprims ? PT_ATOMIC_ADD(c.leaf_counter, n_leafprims) : 0;
+  uint32_t imask = 0;
+  uint32_t meta[8], qlo[3][8], qhi[3][8];
+  int inner_seen = 0, leaf_off = 0;
+  for (int s = 0; s < 8; s++) {
+    meta[s] = 0;
+    for (int a = 0; a < 3; a++) {
+      qlo[a][s] = 255;
+      qhi[a][s] = 0;
+    }
+    const int i = child_in[s];
+    if (i < 0) continue;
+    float q;
+    q = floorf((clo[i].x - nlo.x) / sx); qlo[0][s] = (uint32_t)fminf(fmaxf(q, 0.f), 255.f);
+    q = floorf((clo[i].y - nlo.y) / sy); qlo[1][s] = (uint32_t)fminf(fmaxf(q, 0.f), 255.f);
+    q = floorf((clo[i].z - nlo.z) / sz); qlo[2][s] = (uint32_t)fminf(fmaxf(q, 0.f), 255.f);
+    q = ceilf((chi[i].x - nlo.x) / sx); qhi[0][s] = (uint32_t)fminf(fmaxf(q, 0.f), 255.f);
+    q = ceilf((chi[i].y - nlo.y) / sy); qhi[1][s] = (uint32_t)fminf(fmaxf(q, 0.f), 255.f);
+    q = ceilf((chi[i].z - nlo.z) / sz); qhi[2][s] = (uint32_t)fminf(fmaxf(q, 0.f), 255.f);
+    if (cref[i] >= 0 && ccnt[i] > 3) {
+      meta[s] = (1u << 5) | (24u + (uint32_t)s);
+      imask |= 1u << s;
+      int w = PT_ATOMIC_ADD(out_count, 1);
+      out_work[w] = make_uint2((uint32_t)cref[i], (uint32_t)(child_base + inner_seen));
+      inner_seen++;
+    } else {
+      // leaf child: 1..3 primitives, enumerate the tiny subtree
+      int prims[3], np = 0;
+      int st[4], sp = 0;
+      st[sp++] = cref[i];
+      while (sp) {
+        int rf = st[--sp];
+        if (rf < 0) prims[np++] = (int)t.sorted[~rf];
+        else {
+          st[sp++] = t.nodes[rf].right;
+          st[sp++] = t.nodes[rf].left;
+        }
+      }
+      const uint32_t unary = np == 1 ? 1u : (np == 2 ? 3u : 7u);
+      meta[s] = (unary << 5) | (uint32_t)leaf_off;
+      for (int k = 0; k < np; k++) {
+        c.leaves[leaf_base + leaf_off + k] = make_leaf_rec(c.in, prims[k]);
+        c.prim_leaf[prims[k]] = leaf_base + leaf_off + k;
+      }
+      leaf_off += np;
+    }
+  }
+  auto pack4 = [](const uint32_t* v) { return v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24); };
+  uint4* out = c.nodes8 + (size_t)dst * 5;
+  out[0] = make_uint4(pt_f2u(nlo.x), pt_f2u(nlo.y), pt_f2u(nlo.z), ex | (ey << 8) | (ez << 16) | (imask << 24));
+  out[1] = make_uint4((uint32_t)child_base, (uint32_t)leaf_base, pack4(meta), pack4(meta + 4));
+  out[2] = make_uint4(pack4(qlo[0]), pack4(qlo[0] + 4), pack4(qlo[1]), pack4(qlo[1] + 4));
+  out[3] = make_uint4(pack4(qlo[2]), pack4(qlo[2] + 4), pack4(qhi[0]), pack4(qhi[0] + 4));
+  out[4] = make_uint4(pack4(qhi[1]), pack4(qhi[1] + 4), pack4(qhi[2]), pack4(qhi[2] + 4));
+}

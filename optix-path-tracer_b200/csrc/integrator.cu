@@ -1,0 +1,631 @@
+// integrator.cu — wavefront path integrator with path regeneration.
+//
+// Replaces the reference's megakernel launch loop (main.cpp:264-293 calling
+// context->launch once per sample; programs/raygen.cu:66-167) with a pool of
+// paths that is kept full: every iteration runs
+//   k_iter_begin   1 thread: queue bookkeeping (counts stay on the device)
+//   k_generate     pinhole/thin-lens camera rays for the free slots
+//   k_trace        closest-hit BVH8 traversal, bins paths by material type
+//   k_shade<MAT>   one kernel per material type present (+ k_miss); writes
+//                  compacted continuing paths (warp-aggregated atomics) or a
+//                  shadow request with both continuations (see shading.h)
+//   k_shadow       shadow traversal + resolve + Russian roulette
+// Path state moves with the queue (double-buffered SoA of float4), so every
+// kernel reads coalesced 128-bit words; only the material-sorted shade kernels
+// gather.  No host synchronisation inside an iteration; the host polls the
+// control block every few iterations to detect completion.
+#include <cooperative_groups.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <vector>
+
+#include "scene_host.h"
+#include "shading.h"
+#include "traverse.h"
+
+namespace cg = cooperative_groups;
+
+namespace {
+
+constexpr int NBINS = 9;  // PT_MAT_* (8) + miss
+constexpr int BIN_MISS = 8;
+
+struct PathBuf {  // 64 B / path
+  float4* o_seed;  // origin.xyz, seed
+  float4* d_pack;  // dir.xyz, pix | depth<<23 | prevSpecular<<31
+  float4* thr;     // throughput.xyz, -
+  float4* rad;     // radiance.xyz, -
+};
+struct ShadowBuf {  // 112 B / shadow request
+  float4* s[7];
+};
+
+struct Ctrl {
+  int n_cur, n_next, n_shadow;
+  int gen_base, gen_n;
+  int bin_count[NBINS];
+  unsigned long long sample_base, next_sample, total_samples;
+  unsigned long long stat_closest, stat_shadow, stat_nodes, stat_leaves, stat_iters;
+};
+
+struct Params {
+  int W, H, first_frame, max_depth, russian, pool;
+  float4* accum;
+};
+
+__device__ __forceinline__ uint32_t pack_state(uint32_t pix, int depth, bool spec) {
+  return pix | ((uint32_t)depth << 23) | (spec ? 0x80000000u : 0u);
+}
+
+__device__ __forceinline__ void accumulate(const Params& p, uint32_t pix, float3 col) {
+  col = pt_de_nan(col);
+  int x = pix % p.W, y = pix / p.W;
+  float4* dst = p.accum + (size_t)(p.H - 1 - y) * p.W + x;  // raygen.cu:153
+  atomicAdd(dst, make_float4(col.x, col.y, col.z, 1.f));
+}
+
+// warp-aggregated append: one atomic per converged group
+__device__ __forceinline__ int push_slot(int* counter) {
+  auto g = cg::coalesced_threads();
+  int base = 0;
+  if (g.thread_rank() == 0) base = atomicAdd(counter, (int)g.size());
+  base = g.shfl(base, 0);
+  return base + (int)g.thread_rank();
+}
+
+// raygen.cu:97-118 tail of one loop iteration: Russian roulette, depth cut-off,
+// then either accumulate or append the path to the next wavefront
+__device__ __forceinline__ void finish_bounce(const Params& p, Ctrl* c, const PathBuf& next, uint32_t pix,
+                                              int depth, float3 o, float3 d, float3 thr, float3 rad,
+                                              uint32_t seed, bool specular) {
+  if (p.russian) {
+    float prob = pt_ffmax(pt_ffmax(thr.x, thr.y), thr.z);
+    if (depth > 10) {
+      if (pt_rnd(seed) >= prob) {
+        accumulate(p, pix, rad + thr);
+        return;
+      }
+      thr *= 1.f / prob;
+    }
+  }
+  depth++;
+  if (depth >= p.max_depth) {  // raygen.cu:122: recursion did not terminate -> black
+    accumulate(p, pix, f3(0.f));
+    return;
+  }
+  int slot = push_slot(&c->n_next);
+  next.o_seed[slot] = make_float4(o.x, o.y, o.z, __uint_as_float(seed));
+  next.d_pack[slot] = make_float4(d.x, d.y, d.z, __uint_as_float(pack_state(pix, depth, specular)));
+  next.thr[slot] = make_float4(thr.x, thr.y, thr.z, 0.f);
+  next.rad[slot] = make_float4(rad.x, rad.y, rad.z, 0.f);
+}
+
+__global__ void k_iter_begin(Ctrl* c, int pool) {
+  c->stat_shadow += (unsigned long long)c->n_shadow;
+  int n = c->n_next;  // survivors of the previous iteration (buffers were swapped by the host)
+  unsigned long long remaining = c->total_samples - c->next_sample;
+  int room = pool - n;
+  int g = (int)(remaining < (unsigned long long)room ? remaining : (unsigned long long)room);
+  c->gen_base = n;
+  c->gen_n = g;
+  c->sample_base = c->next_sample;
+  c->next_sample += (unsigned long long)g;
+  c->n_cur = n + g;
+  c->n_next = 0;
+  c->n_shadow = 0;
+  for (int i = 0; i < NBINS; i++) c->bin_count[i] = 0;
+  c->stat_closest += (unsigned long long)c->n_cur;
+  c->stat_iters += 1;
+}
+
+__global__ void k_generate(SceneDev sc, Params p, const Ctrl* c, PathBuf cur) {
+  const int n = c->gen_n, base = c->gen_base;
+  const unsigned long long sbase = c->sample_base;
+  const unsigned long long npix = (unsigned long long)p.W * p.H;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    unsigned long long sid = sbase + (unsigned long long)i;
+    int frame = p.first_frame + (int)(sid / npix);
+    uint32_t pix = (uint32_t)(sid % npix);
+    int x = pix % p.W, y = pix / p.W;
+    uint32_t seed;
+    float3 o, d;
+    camera_ray(sc.camera, p.W, p.H, x, y, frame, seed, o, d);
+    (void)pt_rnd(seed);  // prd.time draw, raygen.cu:69 (motion blur is out of scope; the draw is not)
+    int s = base + i;
+    cur.o_seed[s] = make_float4(o.x, o.y, o.z, __uint_as_float(seed));
+    cur.d_pack[s] = make_float4(d.x, d.y, d.z, __uint_as_float(pack_state(pix, 0, false)));
+    cur.thr[s] = make_float4(1.f, 1.f, 1.f, 0.f);
+    cur.rad[s] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(128) k_trace(SceneDev sc, Ctrl* c, PathBuf cur, float4* hits, uint32_t* bin_q, int pool) {
+  const int n = c->n_cur;
+  uint32_t cn = 0, cl = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    float4 o4 = cur.o_seed[i], d4 = cur.d_pack[i];
+    uint32_t pk = __float_as_uint(d4.w);
+    int depth = (pk >> 23) & 0xff;
+    TraceHit h;
+    bvh8_closest<COUNT>(sc, f3(o4.x, o4.y, o4.z), f3(d4.x, d4.y, d4.z), depth == 0 ? 1e-6f : 1e-3f, PT_RAY_MAX, h,
+                        cn, cl);
+    hits[i] = make_float4(h.t, __int_as_float(h.leaf), h.u, h.v);
+    int key = BIN_MISS;
+    if (h.leaf >= 0) {
+      uint32_t matw = __float_as_uint(__ldg(&sc.leaves[h.leaf].c.w));
+      key = (int)(matw >> 24);
+    }
+    // material binning: lanes with the same key share one atomic
+    unsigned active = __activemask();
+    unsigned peers = __match_any_sync(active, key);
+    int leader = __ffs(peers) - 1;
+    int lane = threadIdx.x & 31;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(&c->bin_count[key], __popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    int pos = base + __popc(peers & ((1u << lane) - 1));
+    bin_q[(size_t)key * pool + pos] = (uint32_t)i;
+  }
+  if (COUNT) {
+    for (int o = 16; o > 0; o >>= 1) {
+      cn += __shfl_xor_sync(0xffffffffu, cn, o);
+      cl += __shfl_xor_sync(0xffffffffu, cl, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+      atomicAdd(&c->stat_nodes, (unsigned long long)cn);
+      atomicAdd(&c->stat_leaves, (unsigned long long)cl);
+    }
+  }
+}
+
+template <int MAT>
+__global__ void __launch_bounds__(128) k_shade(SceneDev sc, Params p, Ctrl* c, PathBuf cur, PathBuf next, ShadowBuf sb,
+                                               const float4* hits, const uint32_t* bin_q) {
+  const int n = c->bin_count[MAT];
+  const uint32_t* q = bin_q + (size_t)MAT * p.pool;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+    const int i = (int)q[j];
+    float4 o4 = cur.o_seed[i], d4 = cur.d_pack[i], t4 = cur.thr[i], r4 = cur.rad[i], h4 = hits[i];
+    uint32_t pk = __float_as_uint(d4.w);
+    PathIn in;
+    in.o = f3(o4.x, o4.y, o4.z);
+    in.d = f3(d4.x, d4.y, d4.z);
+    in.thr = f3(t4.x, t4.y, t4.z);
+    in.rad = f3(r4.x, r4.y, r4.z);
+    in.seed = __float_as_uint(o4.w);
+    in.depth = (pk >> 23) & 0xff;
+    in.prev_specular = (pk >> 31) != 0;
+    const uint32_t pix = pk & 0x7fffffu;
+    ShadeOut out;
+    shade_hit<MAT>(sc, in, h4.x, __float_as_int(h4.y), h4.z, h4.w, out);
+    if (out.kind == SH_TERMINATE) {
+      accumulate(p, pix, out.col);
+    } else if (out.kind == SH_BOUNCE) {
+      finish_bounce(p, c, next, pix, in.depth, out.P, out.dir, out.thr, out.rad, out.seed, out.specular);
+    } else {
+      int s = push_slot(&c->n_shadow);
+      uint32_t pk2 = pack_state(pix, in.depth, out.terminal);
+      sb.s[0][s] = make_float4(out.P.x, out.P.y, out.P.z, __uint_as_float(out.seed));
+      sb.s[1][s] = make_float4(out.WiL.x, out.WiL.y, out.WiL.z, __uint_as_float(out.seedS));
+      sb.s[2][s] = make_float4(out.dir.x, out.dir.y, out.dir.z, __uint_as_float(pk2));
+      sb.s[3][s] = make_float4(out.dirS.x, out.dirS.y, out.dirS.z, out.thr.x);
+      sb.s[4][s] = make_float4(out.thr.y, out.thr.z, out.rad.x, out.rad.y);
+      sb.s[5][s] = make_float4(out.rad.z, out.thrS.x, out.thrS.y, out.thrS.z);
+      sb.s[6][s] = make_float4(out.radS.x, out.radS.y, out.radS.z, 0.f);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128) k_miss(SceneDev sc, Params p, Ctrl* c, PathBuf cur, const uint32_t* bin_q) {
+  const int n = c->bin_count[BIN_MISS];
+  const uint32_t* q = bin_q + (size_t)BIN_MISS * p.pool;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+    const int i = (int)q[j];
+    float4 d4 = cur.d_pack[i], t4 = cur.thr[i], r4 = cur.rad[i];
+    PathIn in;
+    in.d = f3(d4.x, d4.y, d4.z);
+    in.thr = f3(t4.x, t4.y, t4.z);
+    in.rad = f3(r4.x, r4.y, r4.z);
+    accumulate(p, __float_as_uint(d4.w) & 0x7fffffu, shade_miss(sc, in));
+  }
+}
+
+// shadow ray: light_sample.cuh:62-72 + hit.cu:16-24 under the pinned semantics
+// (visible <=> closest hit in (1e-3, inf) is a Diffuse_Light)
+template <bool COUNT>
+__global__ void __launch_bounds__(128) k_shadow(SceneDev sc, Params p, Ctrl* c, PathBuf next, ShadowBuf sb) {
+  const int n = c->n_shadow;
+  uint32_t cn = 0, cl = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    float4 s0 = sb.s[0][i], s1 = sb.s[1][i];
+    float3 P = f3(s0.x, s0.y, s0.z);
+    TraceHit h;
+    bvh8_closest<COUNT>(sc, P, f3(s1.x, s1.y, s1.z), 1e-3f, PT_RAY_MAX, h, cn, cl);
+    bool visible = false;
+    if (h.leaf >= 0) {
+      uint32_t matw = __float_as_uint(__ldg(&sc.leaves[h.leaf].c.w));
+      visible = (matw >> 24) == PT_MAT_DIFFUSE_LIGHT;
+    }
+    float4 s2 = sb.s[2][i], s3 = sb.s[3][i], s4 = sb.s[4][i], s5 = sb.s[5][i], s6 = sb.s[6][i];
+    uint32_t pk = __float_as_uint(s2.w);
+    uint32_t pix = pk & 0x7fffffu;
+    int depth = (pk >> 23) & 0xff;
+    bool terminal = (pk >> 31) != 0;
+    float3 dir, thr, rad;
+    uint32_t seed;
+    if (visible) {
+      dir = f3(s2.x, s2.y, s2.z);
+      thr = f3(s3.w, s4.x, s4.y);
+      rad = f3(s4.z, s4.w, s5.x);
+      seed = __float_as_uint(s0.w);
+    } else {
+      dir = f3(s3.x, s3.y, s3.z);
+      thr = f3(s5.y, s5.z, s5.w);
+      rad = f3(s6.x, s6.y, s6.z);
+      seed = __float_as_uint(s1.w);
+    }
+    if (terminal) accumulate(p, pix, rad);
+    else finish_bounce(p, c, next, pix, depth, P, dir, thr, rad, seed, false);
+  }
+  if (COUNT) {
+    for (int o = 16; o > 0; o >>= 1) {
+      cn += __shfl_xor_sync(0xffffffffu, cn, o);
+      cl += __shfl_xor_sync(0xffffffffu, cl, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+      atomicAdd(&c->stat_nodes, (unsigned long long)cn);
+      atomicAdd(&c->stat_leaves, (unsigned long long)cl);
+    }
+  }
+}
+
+// standalone traversal of a ray set (pt_trace_rays)
+template <bool COUNT>
+__global__ void __launch_bounds__(128) k_trace_rays(SceneDev sc, const pt_ray* rays, long long n, pt_hit* hits,
+                                                    unsigned long long* counters) {
+  uint32_t cn = 0, cl = 0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float4* rp = (const float4*)(rays + i);
+    float4 a = __ldg(rp), b = __ldg(rp + 1);
+    TraceHit h;
+    if (b.w > a.w) {
+      bvh8_closest<COUNT>(sc, f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), a.w, b.w, h, cn, cl);
+    } else {
+      h.t = b.w;
+      h.prim = -1;
+      h.u = h.v = 0.f;
+    }
+    pt_hit o;
+    o.t = h.t;
+    o.prim = h.prim;
+    o.u = h.u;
+    o.v = h.v;
+    hits[i] = o;
+  }
+  if (COUNT) {
+    for (int o = 16; o > 0; o >>= 1) {
+      cn += __shfl_xor_sync(0xffffffffu, cn, o);
+      cl += __shfl_xor_sync(0xffffffffu, cl, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+      atomicAdd(counters, (unsigned long long)cn);
+      atomicAdd(counters + 1, (unsigned long long)cl);
+    }
+  }
+}
+
+int g_sm_count = 0;
+int sm_count() {
+  if (!g_sm_count) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
+    if (g_sm_count <= 0) g_sm_count = 148;
+  }
+  return g_sm_count;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+struct pt_renderer {
+  pt_scene* scene = nullptr;
+  int W = 0, H = 0;
+  int flags = 0;
+  long long pool_req = 0;
+  int pool = 0;
+  DevBuf accum_own;
+  float4* accum = nullptr;
+  DevBuf pathA[4], pathB[4], shadow[7], hits, bin_q, ctrl;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool started = false;
+  pt_stats stats{};
+  Ctrl* h_ctrl = nullptr;  // pinned
+};
+
+static int ensure_pool(pt_renderer* r, long long want) {
+  long long npix = (long long)r->W * r->H;
+  long long pool = r->pool_req > 0 ? r->pool_req : std::min<long long>(std::max<long long>(npix, 1 << 16), 1 << 22);
+  pool = std::min<long long>(pool, std::max<long long>(want, 1024));
+  pool = std::min<long long>(pool, 1 << 23);  // pix field is 23 bits wide; pool is independent but keep it bounded
+  if (pool <= r->pool) return PT_OK;
+  r->pool = (int)pool;
+  for (int k = 0; k < 4; k++) {
+    PT_CUDA(r->pathA[k].alloc((size_t)pool * 16));
+    PT_CUDA(r->pathB[k].alloc((size_t)pool * 16));
+  }
+  for (int k = 0; k < 7; k++) PT_CUDA(r->shadow[k].alloc((size_t)pool * 16));
+  PT_CUDA(r->hits.alloc((size_t)pool * 16));
+  PT_CUDA(r->bin_q.alloc((size_t)pool * 4 * NBINS));
+  return PT_OK;
+}
+
+extern "C" {
+
+int pt_renderer_create(pt_scene* scene, int32_t width, int32_t height, void* d_accum, pt_renderer** out) {
+  if (!scene || !out || width <= 0 || height <= 0) {
+    pt_set_error("pt_renderer_create: bad arguments");
+    return PT_ERR_INVALID;
+  }
+  if (!scene->committed) {
+    pt_set_error("pt_renderer_create: scene not committed");
+    return PT_ERR_STATE;
+  }
+  if ((long long)width * height > (1ll << 23)) {
+    pt_set_error("pt_renderer_create: more than 2^23 pixels");
+    return PT_ERR_INVALID;
+  }
+  pt_renderer* r = new pt_renderer();
+  r->scene = scene;
+  r->W = width;
+  r->H = height;
+  if (d_accum) {
+    r->accum = (float4*)d_accum;
+  } else {
+    if (r->accum_own.alloc((size_t)width * height * 16) != cudaSuccess) {
+      pt_set_error("accumulation buffer allocation failed");
+      delete r;
+      return PT_ERR_OOM;
+    }
+    r->accum = r->accum_own.as<float4>();
+  }
+  if (cudaMemset(r->accum, 0, (size_t)width * height * 16) != cudaSuccess ||
+      r->ctrl.alloc(sizeof(Ctrl)) != cudaSuccess || cudaStreamCreate(&r->stream) != cudaSuccess ||
+      cudaEventCreate(&r->ev0) != cudaSuccess || cudaEventCreate(&r->ev1) != cudaSuccess ||
+      cudaMallocHost((void**)&r->h_ctrl, sizeof(Ctrl)) != cudaSuccess) {
+    pt_set_error("renderer setup failed: %s", cudaGetErrorString(cudaGetLastError()));
+    delete r;
+    return PT_ERR_CUDA;
+  }
+  *out = r;
+  return PT_OK;
+}
+
+int pt_renderer_destroy(pt_renderer* r) {
+  if (!r) return PT_OK;
+  if (r->stream) cudaStreamDestroy(r->stream);
+  if (r->ev0) cudaEventDestroy(r->ev0);
+  if (r->ev1) cudaEventDestroy(r->ev1);
+  if (r->h_ctrl) cudaFreeHost(r->h_ctrl);
+  delete r;
+  return PT_OK;
+}
+
+int pt_renderer_set_flags(pt_renderer* r, int32_t flags) {
+  if (!r) return PT_ERR_INVALID;
+  r->flags = flags;
+  return PT_OK;
+}
+int pt_renderer_set_pool(pt_renderer* r, int64_t paths) {
+  if (!r || paths < 0) return PT_ERR_INVALID;
+  r->pool_req = paths;
+  return PT_OK;
+}
+
+int pt_render(pt_renderer* r, int32_t first_frame, int32_t nframes, int32_t max_depth, int32_t russian,
+              int32_t clear_accum) {
+  if (!r || nframes < 0 || max_depth < 0 || max_depth > 255) {
+    pt_set_error("pt_render: bad arguments (max_depth must be 0..255)");
+    return PT_ERR_INVALID;
+  }
+  pt_scene* s = r->scene;
+  const long long total = (long long)r->W * r->H * nframes;
+  int rc = ensure_pool(r, total);
+  if (rc) return rc;
+  cudaStream_t st = r->stream;
+  if (clear_accum || (first_frame == 0 && !r->started))
+    PT_CUDA(cudaMemsetAsync(r->accum, 0, (size_t)r->W * r->H * 16, st));
+  r->started = true;
+  if (total == 0 || max_depth == 0) {
+    // raygen.cu:76,122: the loop body never runs, every sample is black
+    if (total) {
+      std::vector<float> tmp((size_t)r->W * r->H * 4);
+      PT_CUDA(cudaMemcpyAsync(tmp.data(), r->accum, tmp.size() * 4, cudaMemcpyDeviceToHost, st));
+      PT_CUDA(cudaStreamSynchronize(st));
+      for (size_t i = 0; i < (size_t)r->W * r->H; i++) tmp[4 * i + 3] += (float)nframes;
+      PT_CUDA(cudaMemcpyAsync(r->accum, tmp.data(), tmp.size() * 4, cudaMemcpyHostToDevice, st));
+      PT_CUDA(cudaStreamSynchronize(st));
+    }
+    return PT_OK;
+  }
+
+  Ctrl init{};
+  init.total_samples = (unsigned long long)total;
+  PT_CUDA(cudaMemcpyAsync(r->ctrl.p, &init, sizeof(init), cudaMemcpyHostToDevice, st));
+
+  Params p;
+  p.W = r->W;
+  p.H = r->H;
+  p.first_frame = first_frame;
+  p.max_depth = max_depth;
+  p.russian = russian;
+  p.pool = r->pool;
+  p.accum = r->accum;
+  PathBuf A, B;
+  A.o_seed = r->pathA[0].as<float4>(); A.d_pack = r->pathA[1].as<float4>();
+  A.thr = r->pathA[2].as<float4>(); A.rad = r->pathA[3].as<float4>();
+  B.o_seed = r->pathB[0].as<float4>(); B.d_pack = r->pathB[1].as<float4>();
+  B.thr = r->pathB[2].as<float4>(); B.rad = r->pathB[3].as<float4>();
+  ShadowBuf sb;
+  for (int k = 0; k < 7; k++) sb.s[k] = r->shadow[k].as<float4>();
+  Ctrl* c = r->ctrl.as<Ctrl>();
+  float4* hits = r->hits.as<float4>();
+  uint32_t* bq = r->bin_q.as<uint32_t>();
+  const SceneDev& sc = s->dev;
+  const bool count = (r->flags & 1) != 0;
+  const bool timing = (r->flags & 2) != 0;
+  const int sms = sm_count();
+  const int g_trace = sms * 8, g_shade = sms * 8, g_gen = sms * 4;
+  const uint32_t mask = s->material_type_mask;
+
+  cudaEvent_t e[6] = {};
+  float ms_gen = 0, ms_trace = 0, ms_shade = 0, ms_shadow = 0;
+  if (timing)
+    for (auto& ev : e) PT_CUDA(cudaEventCreate(&ev));
+
+  PT_CUDA(cudaEventRecord(r->ev0, st));
+  unsigned long long launches = 0;
+  bool done = false;
+  long long iter = 0;
+  const int poll_every = 4;
+  while (!done) {
+    for (int k = 0; k < poll_every; k++, iter++) {
+      k_iter_begin<<<1, 1, 0, st>>>(c, r->pool);
+      if (timing) cudaEventRecord(e[0], st);
+      k_generate<<<g_gen, 256, 0, st>>>(sc, p, c, A);
+      if (timing) cudaEventRecord(e[1], st);
+      if (count) k_trace<true><<<g_trace, 128, 0, st>>>(sc, c, A, hits, bq, r->pool);
+      else k_trace<false><<<g_trace, 128, 0, st>>>(sc, c, A, hits, bq, r->pool);
+      if (timing) cudaEventRecord(e[2], st);
+      launches += 3;
+#define LAUNCH_SHADE(M)                                                       \
+  if (mask & (1u << M)) {                                                     \
+    k_shade<M><<<g_shade, 128, 0, st>>>(sc, p, c, A, B, sb, hits, bq);        \
+    launches++;                                                               \
+  }
+      LAUNCH_SHADE(PT_MAT_LAMBERTIAN)
+      LAUNCH_SHADE(PT_MAT_METAL)
+      LAUNCH_SHADE(PT_MAT_DIELECTRIC)
+      LAUNCH_SHADE(PT_MAT_DIFFUSE_LIGHT)
+      LAUNCH_SHADE(PT_MAT_OREN_NAYAR)
+      LAUNCH_SHADE(PT_MAT_TORRANCE_SPARROW)
+      LAUNCH_SHADE(PT_MAT_ASHIKHMIN_SHIRLEY)
+      LAUNCH_SHADE(PT_MAT_NORMAL)
+#undef LAUNCH_SHADE
+      k_miss<<<g_shade, 128, 0, st>>>(sc, p, c, A, bq);
+      if (timing) cudaEventRecord(e[3], st);
+      launches++;
+      if (mask & ((1u << PT_MAT_LAMBERTIAN) | (1u << PT_MAT_OREN_NAYAR) | (1u << PT_MAT_DIFFUSE_LIGHT))) {
+        if (s->lights.size() > 0) {
+          if (count) k_shadow<true><<<g_trace, 128, 0, st>>>(sc, p, c, B, sb);
+          else k_shadow<false><<<g_trace, 128, 0, st>>>(sc, p, c, B, sb);
+          launches++;
+        }
+      }
+      if (timing) {
+        cudaEventRecord(e[4], st);
+        cudaEventSynchronize(e[4]);
+        float t;
+        cudaEventElapsedTime(&t, e[0], e[1]); ms_gen += t;
+        cudaEventElapsedTime(&t, e[1], e[2]); ms_trace += t;
+        cudaEventElapsedTime(&t, e[2], e[3]); ms_shade += t;
+        cudaEventElapsedTime(&t, e[3], e[4]); ms_shadow += t;
+      }
+      std::swap(A, B);
+    }
+    PT_CUDA(cudaGetLastError());
+    PT_CUDA(cudaMemcpyAsync(r->h_ctrl, c, sizeof(Ctrl), cudaMemcpyDeviceToHost, st));
+    PT_CUDA(cudaStreamSynchronize(st));
+    done = r->h_ctrl->next_sample >= r->h_ctrl->total_samples && r->h_ctrl->n_next == 0;
+    if (iter > 100000000ll) {
+      pt_set_error("pt_render: did not converge");
+      return PT_ERR_INVALID;
+    }
+  }
+  PT_CUDA(cudaEventRecord(r->ev1, st));
+  PT_CUDA(cudaEventSynchronize(r->ev1));
+  float ms = 0.f;
+  PT_CUDA(cudaEventElapsedTime(&ms, r->ev0, r->ev1));
+  if (timing)
+    for (auto& ev : e) cudaEventDestroy(ev);
+  const Ctrl& hc = *r->h_ctrl;
+  r->stats.samples = (uint64_t)total;
+  r->stats.closest_rays = hc.stat_closest;
+  r->stats.shadow_rays = hc.stat_shadow + (uint64_t)hc.n_shadow;
+  r->stats.nodes_fetched = hc.stat_nodes;
+  r->stats.leaves_fetched = hc.stat_leaves;
+  r->stats.iterations = hc.stat_iters;
+  r->stats.kernel_launches = launches;
+  r->stats.ms_total = ms;
+  r->stats.ms_generate = ms_gen;
+  r->stats.ms_trace_closest = ms_trace;
+  r->stats.ms_shade = ms_shade;
+  r->stats.ms_trace_shadow = ms_shadow;
+  return PT_OK;
+}
+
+int pt_renderer_sync(pt_renderer* r) {
+  if (!r) return PT_ERR_INVALID;
+  PT_CUDA(cudaStreamSynchronize(r->stream));
+  return PT_OK;
+}
+
+int pt_read_accum(pt_renderer* r, float* host_rgba) {
+  if (!r || !host_rgba) return PT_ERR_INVALID;
+  PT_CUDA(cudaMemcpyAsync(host_rgba, r->accum, (size_t)r->W * r->H * 16, cudaMemcpyDeviceToHost, r->stream));
+  PT_CUDA(cudaStreamSynchronize(r->stream));
+  return PT_OK;
+}
+
+int pt_accum_device_ptr(pt_renderer* r, void** d_ptr) {
+  if (!r || !d_ptr) return PT_ERR_INVALID;
+  *d_ptr = r->accum;
+  return PT_OK;
+}
+
+int pt_get_stats(pt_renderer* r, pt_stats* out) {
+  if (!r || !out) return PT_ERR_INVALID;
+  *out = r->stats;
+  return PT_OK;
+}
+
+int pt_trace_rays_device(pt_scene* scene, const void* d_rays, int64_t n, void* d_hits, void* cuda_stream) {
+  if (!scene || !scene->committed) {
+    pt_set_error("pt_trace_rays: scene not committed");
+    return PT_ERR_STATE;
+  }
+  if (n <= 0) return PT_OK;
+  k_trace_rays<false><<<sm_count() * 8, 128, 0, (cudaStream_t)cuda_stream>>>(scene->dev, (const pt_ray*)d_rays, n,
+                                                                             (pt_hit*)d_hits, nullptr);
+  PT_CUDA(cudaGetLastError());
+  return PT_OK;
+}
+
+int pt_trace_rays(pt_scene* scene, const pt_ray* rays, int64_t n, pt_hit* hits, uint64_t* counters) {
+  if (!scene || !scene->committed) {
+    pt_set_error("pt_trace_rays: scene not committed");
+    return PT_ERR_STATE;
+  }
+  if (n <= 0) return PT_OK;
+  if (!rays || !hits) return PT_ERR_INVALID;
+  DevBuf dr, dh, dc;
+  PT_CUDA(dr.alloc((size_t)n * sizeof(pt_ray)));
+  PT_CUDA(dh.alloc((size_t)n * sizeof(pt_hit)));
+  PT_CUDA(dc.alloc(16));
+  PT_CUDA(cudaMemset(dc.p, 0, 16));
+  PT_CUDA(cudaMemcpy(dr.p, rays, (size_t)n * sizeof(pt_ray), cudaMemcpyHostToDevice));
+  if (counters)
+    k_trace_rays<true><<<sm_count() * 8, 128>>>(scene->dev, dr.as<pt_ray>(), n, dh.as<pt_hit>(),
+                                                dc.as<unsigned long long>());
+  else
+    k_trace_rays<false><<<sm_count() * 8, 128>>>(scene->dev, dr.as<pt_ray>(), n, dh.as<pt_hit>(), nullptr);
+  PT_CUDA(cudaGetLastError());
+  PT_CUDA(cudaMemcpy(hits, dh.p, (size_t)n * sizeof(pt_hit), cudaMemcpyDeviceToHost));
+  if (counters) PT_CUDA(cudaMemcpy(counters, dc.p, 16, cudaMemcpyDeviceToHost));
+  return PT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,262 @@
+// traverse.h — primitive intersection + compressed-BVH8 traversal core.
+//
+// Replaces OptiX's rtTrace / intersection-program dispatch
+// (programs/raygen.cu:77, programs/hitables/{sphere,aarect,box,triangle}.cu).
+// Semantics (pinned with the oracle): closest hit with t in the OPEN interval
+// (tmin, tmax); equal-t hits resolve to the lowest primitive id.
+//
+// All hit-deciding arithmetic uses the X* exact ops from hd.h so hit ids are
+// bit-identical to the CPU oracle.  The node (box) tests are allowed to use
+// FMA: boxes are padded (bvh_build) so the test only has to be conservative.
+#pragma once
+#include "scene_dev.h"
+
+struct TraceHit {
+  float t;
+  int leaf;  // leaf record index, -1 = miss
+  int prim;  // primitive id
+  float u, v;
+};
+
+// ---- per-primitive tests: candidate t in (tmin,tmax) of the ray -----------------
+// programs/hitables/triangle.cu:26-58
+PT_HD bool isect_triangle(float3 a, float3 b, float3 c, float3 o, float3 d, float tmin, float tmax,
+                          float& t, float& bu, float& bv) {
+  float3 e1 = xsub(b, a);
+  float3 e2 = xsub(c, a);
+  float3 P = xcross(d, e2);
+  float A = xdot(P, e1);
+  if ((double)fabsf(A) < 1E-8) return false;
+  float3 R = xsub(o, a);
+  float u = XDIV(xdot(P, R), A);
+  if (u < 0.0f || u > 1.0f) return false;
+  float3 Q = xcross(R, e1);
+  float v = XDIV(xdot(Q, d), A);
+  if (v < 0.0f || XADD(u, v) > 1.0f) return false;
+  float tt = XDIV(xdot(Q, e2), A);
+  if (tt > tmin && tt < tmax) {
+    t = tt;
+    bu = u;
+    bv = v;
+    return true;
+  }
+  return false;
+}
+// programs/hitables/sphere.cu:32-62
+PT_HD bool isect_sphere(float3 center, float radius, float3 o, float3 d, float tmin, float tmax,
+                        float& t) {
+  float3 oc = xsub(o, center);
+  float a = xdot(d, d);
+  float b = xdot(oc, d);
+  float c = XSUB(xdot(oc, oc), XMUL(radius, radius));
+  float disc = XSUB(XMUL(b, b), XMUL(a, c));
+  if (disc < 0.f) return false;
+  float sq = XSQRT(disc);
+  float t0 = XDIV(XSUB(-b, sq), a);
+  if (t0 > tmin && t0 < tmax) {
+    t = t0;
+    return true;
+  }
+  float t1 = XDIV(XADD(-b, sq), a);
+  if (t1 > tmin && t1 < tmax) {
+    t = t1;
+    return true;
+  }
+  return false;
+}
+// programs/hitables/aarect.cu:20-69 ; params: a0,a1,b0,b1,k ; axis
+PT_HD bool isect_rect(float a0, float a1, float b0, float b1, float k, int axis, float3 o, float3 d,
+                      float tmin, float tmax, float& t) {
+  float oa, ob, ok, da, db, dk;
+  if (axis == PT_X_AXIS) {
+    ok = o.x; dk = d.x; oa = o.y; da = d.y; ob = o.z; db = d.z;
+  } else if (axis == PT_Y_AXIS) {
+    ok = o.y; dk = d.y; oa = o.x; da = d.x; ob = o.z; db = d.z;
+  } else {
+    ok = o.z; dk = d.z; oa = o.x; da = d.x; ob = o.y; db = d.y;
+  }
+  float tt = XDIV(XSUB(k, ok), dk);
+  float a = XADD(oa, XMUL(tt, da));
+  float b = XADD(ob, XMUL(tt, db));
+  if (a < a0 || a > a1 || b < b0 || b > b1) return false;
+  if (tt > tmin && tt < tmax) {
+    t = tt;
+    return true;
+  }
+  return false;
+}
+// programs/hitables/box.cu:36-53 (ffmin/ffmax semantics of programs/vec.hpp:57-84)
+PT_HD float pt_ffmin(float a, float b) { return a < b ? a : b; }
+PT_HD float pt_ffmax(float a, float b) { return a > b ? a : b; }
+PT_HD bool isect_box(float3 bmin, float3 bmax, float3 o, float3 d, float tmin, float tmax, float& t) {
+  float3 t0 = f3(XDIV(XSUB(bmin.x, o.x), d.x), XDIV(XSUB(bmin.y, o.y), d.y), XDIV(XSUB(bmin.z, o.z), d.z));
+  float3 t1 = f3(XDIV(XSUB(bmax.x, o.x), d.x), XDIV(XSUB(bmax.y, o.y), d.y), XDIV(XSUB(bmax.z, o.z), d.z));
+  float tn = pt_ffmax(pt_ffmax(pt_ffmin(t0.x, t1.x), pt_ffmin(t0.y, t1.y)), pt_ffmin(t0.z, t1.z));
+  float tf = pt_ffmin(pt_ffmin(pt_ffmax(t0.x, t1.x), pt_ffmax(t0.y, t1.y)), pt_ffmax(t0.z, t1.z));
+  if (tn <= tf) {
+    if (tn > tmin && tn < tmax) {
+      t = tn;
+      return true;
+    } else if (tf > tmin && tf < tmax) {
+      t = tf;
+      return true;
+    }
+  }
+  return false;
+}
+
+// one leaf record against the (world) ray
+PT_HD bool isect_leaf(const SceneDev& sc, const LeafRec& L, float3 o, float3 d, float tmin, float tmax,
+                      float& t, float& u, float& v) {
+  uint32_t w = pt_f2u(L.b.w);
+  int kind = PT_LEAF_KIND(w);
+  u = 0.f;
+  v = 0.f;
+  if (kind == PT_PRIM_TRIANGLE) return isect_triangle(xyz(L.a), xyz(L.b), xyz(L.c), o, d, tmin, tmax, t, u, v);
+  int xf = PT_LEAF_XFORM(w);
+  if (xf >= 0) {  // Transform node: ray to object space, t is shared
+    const float* m = sc.xforms[xf].w2o;
+    o = xf_point(m, o);
+    d = xf_vector(m, d);
+  }
+  if (kind == PT_PRIM_SPHERE) return isect_sphere(xyz(L.a), L.b.x, o, d, tmin, tmax, t);
+  if (kind == PT_PRIM_RECT) {
+    int ax = (int)pt_f2u(L.b.z);
+    return isect_rect(L.a.x, L.a.y, L.a.z, L.b.x, L.b.y, ax & 3, o, d, tmin, tmax, t);
+  }
+  return isect_box(xyz(L.a), xyz(L.b), o, d, tmin, tmax, t);
+}
+
+// ---- BVH8 traversal ------------------------------------------------------------------
+#ifdef __CUDA_ARCH__
+#define PT_LDG4(p) __ldg(p)
+#define PT_LDGF4(p) __ldg(p)
+#else
+#define PT_LDG4(p) (*(p))
+#define PT_LDGF4(p) (*(p))
+#endif
+
+PT_HD uint32_t pt_sign_extend_s8x4(uint32_t v) {
+  // each byte with bit7 set -> 0xff, else 0x00
+  return ((v >> 7) & 0x01010101u) * 0xffu;
+}
+PT_HD uint32_t pt_byte(uint32_t v, int i) { return (v >> (8 * i)) & 0xffu; }
+
+#define PT_STACK 40
+
+template <bool COUNT>
+PT_HD void bvh8_closest(const SceneDev& sc, float3 o, float3 d, float tmin, float tmax,
+                        TraceHit& hit, uint32_t& n_nodes, uint32_t& n_leaves) {
+  hit.t = tmax;
+  hit.leaf = -1;
+  hit.prim = -1;
+  hit.u = hit.v = 0.f;
+  const float ray_tmax = tmax;  // candidate selection uses the ray's own interval
+
+  const float ooeps = 8.2718061e-25f;  // 2^-80
+  float idx = 1.0f / (fabsf(d.x) > ooeps ? d.x : copysignf(ooeps, d.x));
+  float idy = 1.0f / (fabsf(d.y) > ooeps ? d.y : copysignf(ooeps, d.y));
+  float idz = 1.0f / (fabsf(d.z) > ooeps ? d.z : copysignf(ooeps, d.z));
+  const uint32_t oct = (d.x < 0.f ? 4u : 0u) | (d.y < 0.f ? 2u : 0u) | (d.z < 0.f ? 1u : 0u);
+  const uint32_t octinv = 7u - oct;
+  const uint32_t octinv4 = octinv * 0x01010101u;
+
+  uint2 stack[PT_STACK];
+  int sp = 0;
+  uint2 ngroup = make_uint2(0u, 0x80000000u);  // root
+  uint2 lgroup = make_uint2(0u, 0u);
+
+  for (;;) {
+    if (ngroup.y & 0xff000000u) {
+      // pop the nearest child (highest priority bit) of the current node group
+      const uint32_t bit = (uint32_t)pt_bfind(ngroup.y);
+      ngroup.y &= ~(1u << bit);
+      const uint32_t base = ngroup.x;
+      const uint32_t imask = ngroup.y & 0xffu;
+      if (ngroup.y & 0xff000000u) {
+        if (sp < PT_STACK) stack[sp++] = ngroup;
+      }
+      const uint32_t slot = (bit - 24u) ^ octinv;
+      const uint32_t rel = (uint32_t)pt_popc(imask & ~(0xffffffffu << slot));
+      const uint32_t ni = base + rel;
+
+      const uint4* np = sc.nodes8 + (size_t)ni * 5;
+      const uint4 n0 = PT_LDG4(np + 0);
+      const uint4 n1 = PT_LDG4(np + 1);
+      const uint4 n2 = PT_LDG4(np + 2);
+      const uint4 n3 = PT_LDG4(np + 3);
+      const uint4 n4 = PT_LDG4(np + 4);
+      if (COUNT) n_nodes++;
+
+      const float px = pt_u2f(n0.x), py = pt_u2f(n0.y), pz = pt_u2f(n0.z);
+      const float sx = pt_u2f((n0.w & 0xffu) << 23) * idx;
+      const float sy = pt_u2f(((n0.w >> 8) & 0xffu) << 23) * idy;
+      const float sz = pt_u2f(((n0.w >> 16) & 0xffu) << 23) * idz;
+      const float bx = (px - o.x) * idx, by = (py - o.y) * idy, bz = (pz - o.z) * idz;
+
+      uint32_t hitmask = 0;
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        const uint32_t meta4 = h ? n1.w : n1.z;
+        const uint32_t is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
+        const uint32_t inner_mask4 = pt_sign_extend_s8x4(is_inner4 << 3);
+        const uint32_t bit_index4 = (meta4 ^ (octinv4 & inner_mask4)) & 0x1f1f1f1fu;
+        const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
+        const uint32_t qlox = h ? n2.y : n2.x, qloy = h ? n2.w : n2.z, qloz = h ? n3.y : n3.x;
+        const uint32_t qhix = h ? n3.w : n3.z, qhiy = h ? n4.y : n4.x, qhiz = h ? n4.w : n4.z;
+        const uint32_t nx = idx < 0.f ? qhix : qlox, fx = idx < 0.f ? qlox : qhix;
+        const uint32_t ny = idy < 0.f ? qhiy : qloy, fy = idy < 0.f ? qloy : qhiy;
+        const uint32_t nz = idz < 0.f ? qhiz : qloz, fz = idz < 0.f ? qloz : qhiz;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const float t0x = XFMA((float)pt_byte(nx, j), sx, bx);
+          const float t0y = XFMA((float)pt_byte(ny, j), sy, by);
+          const float t0z = XFMA((float)pt_byte(nz, j), sz, bz);
+          const float t1x = XFMA((float)pt_byte(fx, j), sx, bx);
+          const float t1y = XFMA((float)pt_byte(fy, j), sy, by);
+          const float t1z = XFMA((float)pt_byte(fz, j), sz, bz);
+          const float cmin = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, tmin));
+          const float cmax = fminf(fminf(t1x, t1y), fminf(t1z, hit.t));
+          if (cmin <= cmax) {
+            hitmask |= pt_byte(child_bits4, j) << pt_byte(bit_index4, j);
+          }
+        }
+      }
+      ngroup.x = n1.x;
+      ngroup.y = (hitmask & 0xff000000u) | (n0.w >> 24);
+      lgroup.x = n1.y;
+      lgroup.y = hitmask & 0x00ffffffu;
+    } else {
+      lgroup = ngroup;
+      ngroup = make_uint2(0u, 0u);
+    }
+
+    while (lgroup.y) {
+      const uint32_t b = (uint32_t)pt_bfind(lgroup.y);
+      lgroup.y &= ~(1u << b);
+      const uint32_t li = lgroup.x + b;
+      const float4* lp = (const float4*)(sc.leaves + li);
+      LeafRec L;
+      L.a = PT_LDGF4(lp + 0);
+      L.b = PT_LDGF4(lp + 1);
+      L.c = PT_LDGF4(lp + 2);
+      if (COUNT) n_leaves++;
+      float t, u, v;
+      if (isect_leaf(sc, L, o, d, tmin, ray_tmax, t, u, v)) {
+        const int prim = (int)pt_f2u(L.a.w);
+        if (t < hit.t || (t == hit.t && (hit.prim < 0 || prim < hit.prim))) {
+          hit.t = t;
+          hit.leaf = (int)li;
+          hit.prim = prim;
+          hit.u = u;
+          hit.v = v;
+        }
+      }
+    }
+
+    if ((ngroup.y & 0xff000000u) == 0) {
+      if (sp == 0) break;
+      ngroup = stack[--sp];
+    }
+  }
+}

@@ -1,0 +1,102 @@
+/*
+ * oracle.h — C API of the CPU oracle (liboracle.so).
+ *
+ * TEST INFRASTRUCTURE ONLY.  The oracle is a from-scratch host C++/OpenMP
+ * restatement of the reference's device programs
+ * (/root/reference/OptiX-Path-Tracer/programs/, cited per function in
+ * oracle.cpp).  Only tests/, __graft_entry__.smoke() and bench.py's
+ * cpu_baseline / --impl reference legs may load it.  The product
+ * (optix-path-tracer_b200/, libptb200.so) never links, imports or calls it.
+ *
+ * Parity pinning: the reference has no tests and cannot run here (needs the
+ * proprietary OptiX 6 SDK + a GPU).  What IS pinned against the real
+ * reference: RNG, sampling, BSDF Sample/Evaluate/PDF, microfacet helpers and
+ * Fresnel/refraction helpers — the reference's own header code
+ * (programs/ .cuh headers) is compiled unmodified into oracle/_ref/libref_probe.so by
+ * oracle/Makefile and compared with this restatement (tests/test_oracle_ref.py,
+ * golden vectors in tests/golden/).  The .cu glue (intersection programs,
+ * closest-hit programs, raygen loop, miss programs) cannot be compiled without
+ * OptiX and is restated only: for those parts parity is UNPINNED by reference
+ * outputs and the oracle defines it.
+ *
+ * It consumes the same flat scene description as the product
+ * (include/ptb200.h: pt_scene_desc), so both sides see identical inputs.
+ */
+#ifndef ORACLE_H
+#define ORACLE_H
+
+#include "../include/ptb200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct orc_stats {
+  uint64_t samples;
+  uint64_t closest_rays;
+  uint64_t shadow_rays;
+  uint64_t bounces; /* sum over samples of path length (closest-hit events) */
+  uint64_t node_tests;
+  uint64_t prim_tests;
+  double seconds;
+  int32_t threads;
+} orc_stats;
+
+/* acceleration handle: brute force for tiny scenes, BVH2 otherwise */
+typedef struct orc_scene orc_scene;
+/* mode: 0 = auto (brute force when n_prims <= 64), 1 = brute force, 2 = BVH2 */
+orc_scene* orc_scene_create(const pt_scene_desc* desc, int mode);
+void orc_scene_destroy(orc_scene* s);
+
+/* closest hit in (tmin,tmax), ties -> lowest primitive id */
+int orc_trace(const orc_scene* s, const pt_ray* rays, int64_t n, pt_hit* hits, orc_stats* stats);
+
+/* camera rays of frame `frame` (programs/raygen.cu:148-162), one per pixel,
+ * index = y*W + x with y = pixelID.y (0 = bottom image row). */
+int orc_camera_rays(const orc_scene* s, int W, int H, int frame, pt_ray* out);
+/* incoherent secondary rays: for each input ray that hits, a cosine-sampled
+ * bounce about the shading normal (origin P, tmin 1e-3); misses get tmax<0 */
+int orc_bounce_rays(const orc_scene* s, const pt_ray* in, int64_t n, uint32_t seed, pt_ray* out);
+
+/* frames [first_frame, first_frame+nframes) ADDED into accum (W*H float4,
+ * row 0 = top image row, .w += 1 per sample), programs/raygen.cu:148-167 */
+int orc_render(const orc_scene* s, int W, int H, int first_frame, int nframes, int max_depth,
+               int russian, float* accum, orc_stats* stats);
+
+/* single pixel-sample with a trace of the path for debugging/parity */
+int orc_render_pixel(const orc_scene* s, int W, int H, int x, int y, int frame, int max_depth,
+                     int russian, float* rgb);
+
+/* host_includes/image_save.hpp:13-29: 8-bit RGB, W*H*3 */
+int orc_tonemap_png8(const float* accum, int W, int H, int samples, uint8_t* rgb);
+
+/* ---- unit entry points (golden vectors / reference-header probes) -------- */
+uint32_t orc_tea64(uint32_t v0, uint32_t v1);            /* programs/random.cuh:33-47 */
+float orc_rnd(uint32_t* seed);                           /* programs/random.cuh:63-65 */
+void orc_random_in_unit_disk(uint32_t* seed, float* out3);   /* sampling.cuh:22-29 */
+void orc_random_in_unit_sphere(uint32_t* seed, float* out3); /* sampling.cuh:31-44 */
+void orc_random_on_unit_sphere(uint32_t* seed, float* out3); /* sampling.cuh:46-59 */
+
+/* BSDF probes.  mat: PT_MAT_*; color/color2: texture values; p0,p1 as pt_material.
+ * u1,u2 are the two uniform draws in DEVICE order (u1 drawn first). */
+void orc_bsdf_sample(int mat, const float* color, const float* color2, float p0, float p1,
+                     const float* P, const float* Wo, const float* N, float u1, float u2,
+                     float* Wi_out);
+void orc_bsdf_eval(int mat, const float* color, const float* color2, float p0, float p1,
+                   const float* P, const float* Wo, const float* Wi, const float* N, float* f_out,
+                   float* pdf_out);
+float orc_schlick(float cosine, float ref_idx);          /* material.cuh:30-34 */
+int orc_refract(const float* v, const float* n, float ni_over_nt, float* out3); /* :50-63 */
+void orc_ggx_sample(const float* origin, float u1, float u2, float nu, float nv, float* out3);
+float orc_ggx_d(const float* H, float nu, float nv);
+float orc_ggx_g(const float* Wo, const float* Wi, float nu, float nv);
+/* rect light: programs/pdfs/rect_pdf.cu */
+void orc_rect_sample(const pt_light* l, const float* P, float u1, float u2, float* Wi_out);
+float orc_rect_pdf(const pt_light* l, const float* P, const float* Wi);
+/* single primitive intersection: returns 1 and *t when hit in (tmin,tmax) */
+int orc_intersect_prim(const orc_scene* s, int prim, const pt_ray* ray, float* t, float* u, float* v);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

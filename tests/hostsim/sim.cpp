@@ -1,0 +1,337 @@
+// tests/hostsim/sim.cpp — TEST-ONLY host simulation of the kernel cores.
+//
+// Compiles optix-path-tracer_b200/csrc/{bvh_core,traverse,shading}.h with g++
+// (the PT_HD bodies are written to be host-compilable) and drives them with
+// serial loops that mirror the CUDA drivers (bvh_build.cu, integrator.cu).
+// Purpose: check the builder / traversal / shading LOGIC against the oracle on
+// a machine without a GPU.  This is not a product path: nothing in the package
+// loads it, and the shipped library has no CPU execution mode.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+#include <vector>
+
+#include "../../optix-path-tracer_b200/csrc/bvh_core.h"
+#include "../../optix-path-tracer_b200/csrc/shading.h"
+#include "../../optix-path-tracer_b200/csrc/traverse.h"
+
+struct Sim {
+  pt_scene_desc d;
+  std::vector<uint4> nodes8;
+  std::vector<LeafRec> leaves;
+  std::vector<int> prim_leaf;
+  std::vector<ImageDev> images;
+  SceneDev sc;
+  int n_nodes8 = 0;
+  double sah_before = 0, sah_after = 0;
+  int n_treelets = 0;
+};
+
+static double sah_sum(const Bvh2& t) {
+  double a = 0;
+  for (int i = 0; i < t.n - 1; i++) {
+    const Bvh2Node& nd = t.nodes[i];
+    a += box_half_area(f3(nd.lo[0], nd.lo[1], nd.lo[2]), f3(nd.hi[0], nd.hi[1], nd.hi[2]));
+  }
+  const Bvh2Node& r = t.nodes[0];
+  double ra = box_half_area(f3(r.lo[0], r.lo[1], r.lo[2]), f3(r.hi[0], r.hi[1], r.hi[2]));
+  return ra > 0 ? a / ra : 0;
+}
+
+extern "C" {
+
+Sim* sim_create(const pt_scene_desc* desc, int refine) {
+  Sim* s = new Sim();
+  s->d = *desc;
+  const int n = desc->n_prims;
+  BuildIn in;
+  in.prim_ref = desc->prims;
+  in.spheres = desc->spheres;
+  in.rects = desc->rects;
+  in.boxes = desc->boxes;
+  in.tri_v = desc->tri_v;
+  in.xforms = desc->xforms;
+  in.materials = desc->materials;
+  in.n = n;
+  std::vector<float4> plo(n), phi(n);
+  float3 cmin = f3(INFINITY), cmax = f3(-INFINITY);
+  for (int i = 0; i < n; i++) {
+    float3 lo, hi;
+    prim_bounds(in, i, lo, hi);
+    plo[i] = make_float4(lo.x, lo.y, lo.z, 0.f);
+    phi[i] = make_float4(hi.x, hi.y, hi.z, 0.f);
+    float3 c = (lo + hi) * 0.5f;
+    cmin = fmin3(cmin, c);
+    cmax = fmax3(cmax, c);
+  }
+  float3 ext = cmax - cmin;
+  float3 sinv = f3(ext.x > 0 ? 1.f / ext.x : 0.f, ext.y > 0 ? 1.f / ext.y : 0.f, ext.z > 0 ? 1.f / ext.z : 0.f);
+  std::vector<uint64_t> keys(n);
+  std::vector<uint32_t> order(n);
+  for (int i = 0; i < n; i++) keys[i] = morton63((xyz(plo[i]) + xyz(phi[i])) * 0.5f, cmin, sinv);
+  std::iota(order.begin(), order.end(), 0u);
+  std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return keys[a] < keys[b]; });
+  std::vector<uint64_t> skeys(n);
+  for (int i = 0; i < n; i++) skeys[i] = keys[order[i]];
+
+  const int ni = n > 1 ? n - 1 : 1;
+  std::vector<Bvh2Node> nodes2(ni);
+  std::vector<int> parent(ni, -1), leaf_parent(n, -1), count(ni, 0), flag(ni, 0);
+  Bvh2 t;
+  t.nodes = nodes2.data();
+  t.parent = parent.data();
+  t.leaf_parent = leaf_parent.data();
+  t.count = count.data();
+  t.flag = flag.data();
+  t.keys = skeys.data();
+  t.sorted = order.data();
+  t.plo = plo.data();
+  t.phi = phi.data();
+  t.n = n;
+  if (n > 1) {
+    for (int i = 0; i < n - 1; i++) karras_node(t, i);
+    // refit (mirrors k_refit: second arrival computes the node)
+    for (int j = 0; j < n; j++) {
+      int cur = t.leaf_parent[j];
+      while (cur >= 0) {
+        if (t.flag[cur]++ == 0) break;
+        Bvh2Node& nd = t.nodes[cur];
+        float3 llo, lhi, rlo, rhi;
+        int lc, rc;
+        bvh2_child_box(t, nd.left, llo, lhi, lc);
+        bvh2_child_box(t, nd.right, rlo, rhi, rc);
+        bvh2_set_box(nd, fmin3(llo, rlo), fmax3(lhi, rhi));
+        t.count[cur] = lc + rc;
+        cur = t.parent[cur];
+      }
+    }
+    s->sah_before = sah_sum(t);
+    if (refine) {
+      std::vector<int> roots;
+      for (int i = 0; i < n - 1; i++)
+        if (treelet_is_root(t, i)) roots.push_back(i);
+      for (int r : roots) treelet_sah(t, r);
+      s->n_treelets = (int)roots.size();
+    }
+    s->sah_after = sah_sum(t);
+  }
+  s->nodes8.resize((size_t)(n > 1 ? n : 2) * 5);
+  s->leaves.resize(n);
+  s->prim_leaf.assign(n, -1);
+  int counters[2] = {1, 0};
+  Collapse c;
+  c.t = t;
+  c.in = in;
+  c.nodes8 = s->nodes8.data();
+  c.leaves = s->leaves.data();
+  c.prim_leaf = s->prim_leaf.data();
+  c.node_counter = &counters[0];
+  c.leaf_counter = &counters[1];
+  std::vector<uint2> wa(n + 1), wb(n + 1);
+  wa[0] = make_uint2(n > 1 ? 0u : (uint32_t)~0, 0u);
+  int nw = 1;
+  while (nw > 0) {
+    int out = 0;
+    for (int i = 0; i < nw; i++) collapse_node(c, (int)wa[i].x, (int)wa[i].y, wb.data(), &out);
+    std::swap(wa, wb);
+    nw = out;
+  }
+  s->n_nodes8 = counters[0];
+  if (counters[1] != n) fprintf(stderr, "hostsim: leaf count %d != %d\n", counters[1], n);
+
+  for (int i = 0; i < desc->n_images; i++) {
+    ImageDev im;
+    im.texels = (const float4*)desc->images[i].rgba;
+    im.width = desc->images[i].width;
+    im.height = desc->images[i].height;
+    s->images.push_back(im);
+  }
+  SceneDev& d = s->sc;
+  d.nodes8 = s->nodes8.data();
+  d.leaves = s->leaves.data();
+  d.prim_ref = desc->prims;
+  d.prim_leaf = s->prim_leaf.data();
+  d.xforms = desc->xforms;
+  d.tri_n = desc->tri_n;
+  d.tri_uv = desc->tri_uv;
+  d.tri_tex = desc->tri_tex;
+  d.materials = desc->materials;
+  d.textures = desc->textures;
+  d.texvec = desc->texvec;
+  d.images = s->images.data();
+  d.lights = desc->lights;
+  d.n_prims = n;
+  d.n_materials = desc->n_materials;
+  d.n_textures = desc->n_textures;
+  d.n_texvec = desc->n_texvec;
+  d.n_images = desc->n_images;
+  d.n_lights = desc->n_lights;
+  d.camera = desc->camera;
+  d.miss = desc->miss;
+  return s;
+}
+
+void sim_destroy(Sim* s) { delete s; }
+
+void sim_info(const Sim* s, int* n_nodes8, double* sah_before, double* sah_after, int* n_treelets) {
+  *n_nodes8 = s->n_nodes8;
+  *sah_before = s->sah_before;
+  *sah_after = s->sah_after;
+  *n_treelets = s->n_treelets;
+}
+
+// every primitive must be referenced by exactly one leaf slot reachable from the root,
+// and every child box must contain its subtree's primitive boxes (checked via leaves)
+int sim_validate(const Sim* s) {
+  const int n = s->d.n_prims;
+  std::vector<int> seen(n, 0);
+  std::vector<int> stack = {0};
+  int visited = 0;
+  while (!stack.empty()) {
+    int ni = stack.back();
+    stack.pop_back();
+    visited++;
+    const uint4* np = s->nodes8.data() + (size_t)ni * 5;
+    uint32_t imask = np[0].w >> 24;
+    uint32_t meta[8];
+    for (int k = 0; k < 4; k++) {
+      meta[k] = (np[1].z >> (8 * k)) & 0xff;
+      meta[4 + k] = (np[1].w >> (8 * k)) & 0xff;
+    }
+    int rel = 0;
+    for (int slot = 0; slot < 8; slot++) {
+      uint32_t m = meta[slot];
+      if (!m) continue;
+      if (imask & (1u << slot)) {
+        if ((m >> 5) != 1 || (m & 31) != 24u + slot) return -2;
+        stack.push_back((int)np[1].x + rel);
+        rel++;
+      } else {
+        int cnt = pt_popc(m >> 5);
+        int off = m & 31;
+        for (int k = 0; k < cnt; k++) {
+          int li = (int)np[1].y + off + k;
+          if (li < 0 || li >= n) return -3;
+          int prim = (int)pt_f2u(s->leaves[li].a.w);
+          if (prim < 0 || prim >= n) return -4;
+          seen[prim]++;
+          if (s->prim_leaf[prim] != li) return -5;
+        }
+      }
+    }
+  }
+  for (int i = 0; i < n; i++)
+    if (seen[i] != 1) return -1;
+  if (visited != s->n_nodes8) return -6;
+  return 0;
+}
+
+int sim_trace(const Sim* s, const pt_ray* rays, long long n, pt_hit* hits, unsigned long long* counters) {
+  unsigned long long cn = 0, cl = 0;
+#pragma omp parallel for schedule(dynamic, 256) reduction(+ : cn, cl)
+  for (long long i = 0; i < n; i++) {
+    const pt_ray& r = rays[i];
+    TraceHit h;
+    uint32_t a = 0, b = 0;
+    if (r.tmax > r.tmin) {
+      bvh8_closest<true>(s->sc, f3(r.origin[0], r.origin[1], r.origin[2]), f3(r.dir[0], r.dir[1], r.dir[2]), r.tmin,
+                         r.tmax, h, a, b);
+    } else {
+      h.t = r.tmax;
+      h.prim = -1;
+      h.u = h.v = 0.f;
+    }
+    hits[i].t = h.t;
+    hits[i].prim = h.prim;
+    hits[i].u = h.u;
+    hits[i].v = h.v;
+    cn += a;
+    cl += b;
+  }
+  if (counters) {
+    counters[0] = cn;
+    counters[1] = cl;
+  }
+  return 0;
+}
+
+// serial mirror of the wavefront loop (integrator.cu) for one path at a time
+int sim_render(const Sim* s, int W, int H, int first_frame, int nframes, int max_depth, int russian, float* accum) {
+  const SceneDev& sc = s->sc;
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int y = 0; y < H; y++)
+    for (int f = first_frame; f < first_frame + nframes; f++)
+      for (int x = 0; x < W; x++) {
+        uint32_t seed;
+        float3 o, d;
+        camera_ray(sc.camera, W, H, x, y, f, seed, o, d);
+        (void)pt_rnd(seed);
+        float3 thr = f3(1.f), rad = f3(0.f);
+        bool spec = false;
+        int depth = 0;
+        float3 col = f3(0.f);
+        bool alive = max_depth > 0;
+        while (alive) {
+          TraceHit h;
+          uint32_t a = 0, b = 0;
+          bvh8_closest<false>(sc, o, d, depth == 0 ? 1e-6f : 1e-3f, PT_RAY_MAX, h, a, b);
+          PathIn in;
+          in.o = o; in.d = d; in.thr = thr; in.rad = rad; in.seed = seed; in.depth = depth; in.prev_specular = spec;
+          if (h.leaf < 0) {
+            col = shade_miss(sc, in);
+            break;
+          }
+          int mt = (int)(pt_f2u(sc.leaves[h.leaf].c.w) >> 24);
+          ShadeOut out;
+          shade_hit_any(sc, mt, in, h.t, h.leaf, h.u, h.v, out);
+          if (out.kind == SH_TERMINATE) {
+            col = out.col;
+            break;
+          }
+          float3 nd, nthr, nrad;
+          uint32_t nseed;
+          bool nspec = out.specular;
+          if (out.kind == SH_SHADOW) {
+            TraceHit sh;
+            bvh8_closest<false>(sc, out.P, out.WiL, 1e-3f, PT_RAY_MAX, sh, a, b);
+            bool vis = sh.leaf >= 0 && (pt_f2u(sc.leaves[sh.leaf].c.w) >> 24) == PT_MAT_DIFFUSE_LIGHT;
+            if (vis) { nd = out.dir; nthr = out.thr; nrad = out.rad; nseed = out.seed; }
+            else { nd = out.dirS; nthr = out.thrS; nrad = out.radS; nseed = out.seedS; }
+            nspec = false;
+            if (out.terminal) {
+              col = nrad;
+              break;
+            }
+          } else {
+            nd = out.dir; nthr = out.thr; nrad = out.rad; nseed = out.seed;
+          }
+          // finish_bounce
+          if (russian) {
+            float prob = pt_ffmax(pt_ffmax(nthr.x, nthr.y), nthr.z);
+            if (depth > 10) {
+              if (pt_rnd(nseed) >= prob) {
+                col = nrad + nthr;
+                break;
+              }
+              nthr *= 1.f / prob;
+            }
+          }
+          depth++;
+          if (depth >= max_depth) {
+            col = f3(0.f);
+            break;
+          }
+          o = out.P; d = nd; thr = nthr; rad = nrad; seed = nseed; spec = nspec;
+        }
+        col = pt_de_nan(col);
+        float* px = accum + 4 * ((size_t)(H - 1 - y) * W + x);
+        px[0] += col.x;
+        px[1] += col.y;
+        px[2] += col.z;
+        px[3] += 1.f;
+      }
+  return 0;
+}
+
+}  // extern "C"
