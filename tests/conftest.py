@@ -1,0 +1,23 @@
+import os
+import sys
+
+import pytest
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+@pytest.fixture(scope="session")
+def lib():
+    import helpers
+    helpers.build_product()
+    return helpers.pt.load()
+
+
+@pytest.fixture(scope="session")
+def orc():
+    import helpers
+    return helpers.oracle()

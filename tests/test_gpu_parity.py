@@ -1,0 +1,264 @@
+"""GPU parity tests (run on the B200 box): the CUDA path, called through the C ABI
+(include/ptb200.h via the ctypes binding), against the CPU oracle on the same inputs.
+
+Bars (BASELINE.json north_star):
+  1. first-hit primitive ids / t / barycentrics: BIT-EXACT on fixed ray sets;
+  2. per-pixel radiance at fixed seed for non-stochastic passes (Normal_Shader, depth-1):
+     |diff| <= 2e-5 absolute (libm sinf/atan2f/... differ by <= 2 ulp between glibc and CUDA);
+  3. stochastic passes at fixed seed: identical RNG streams, so images agree except where a
+     1-ulp libm difference flips a branch: <= 1.5 % of pixels may differ by > 1e-3, and the
+     image means agree to 1 %;
+  4. converged images: RMSE on the gamma-encoded [0,1] image <= 0.02 against the oracle
+     rendered with DIFFERENT frame indices (independent samples).
+"""
+import numpy as np
+import pytest
+
+import helpers as h
+
+pt = h.pt
+pytestmark = pytest.mark.gpu
+
+
+def same_hits(a, b):
+    return ((a["prim"] == b["prim"]) & (a["t"].view(np.uint32) == b["t"].view(np.uint32)) &
+            (a["u"].view(np.uint32) == b["u"].view(np.uint32)) & (a["v"].view(np.uint32) == b["v"].view(np.uint32)))
+
+
+def ray_set(orc, W, H, extra=4000, seed=3):
+    rays = np.concatenate([orc.camera_rays(W, H, 0), h.random_rays(extra, seed)])
+    b1 = orc.bounce_rays(rays, 7)
+    b2 = orc.bounce_rays(b1, 8)
+    return np.concatenate([rays, b1, b2])
+
+
+SCENES = {
+    "cornell": lambda lib: h.build_cornell(64, 64, lib),
+    "zoo": lambda lib: h.build_material_zoo(64, 64, lib),
+    "spheres488": lambda lib: h.build_spheres(22, W=64, H=64, lib=lib),
+    "soup": lambda lib: h.build_random_prims(3, lib=lib),
+    "soup_big": lambda lib: h.build_random_prims(8, n_sph=600, n_rect=500, n_box=500, n_tri=5000, lib=lib),
+    "mesh8k": lambda lib: h.build_mesh_scene(64, 64, 64, lib),
+    "single": lambda lib: h.build_random_prims(5, n_sph=1, n_rect=0, n_box=0, n_tri=0, lib=lib),
+}
+
+
+@pytest.mark.parametrize("name", list(SCENES))
+def test_hit_ids_bit_exact(lib, name):
+    sc = SCENES[name](lib)
+    sc.commit()
+    orc = h.OracleScene(sc, mode=1 if sc.desc().n_prims <= 1000 else 2)
+    rays = ray_set(orc, 64, 64)
+    ho, _ = orc.trace(rays)
+    hg = sc.trace(rays)
+    ok = same_hits(ho, hg)
+    assert ok.all(), f"{(~ok).sum()} of {len(rays)} rays differ"
+    assert (ho["prim"] >= 0).mean() > 0.1
+
+
+def test_hit_ids_bit_exact_mesh_250k_incoherent(lib):
+    """>= 1 M rays on a 250k-triangle mesh, mostly incoherent secondary rays."""
+    sc = h.build_mesh_scene(354, 512, 512, lib)
+    sc.commit()
+    info = sc.bvh_info()
+    assert info.n_prims == 2 * 354 * 354 and info.n_leaf_records == info.n_prims
+    assert info.sah_cost_refined <= info.sah_cost_lbvh
+    orc = h.OracleScene(sc, mode=2)
+    cam = orc.camera_rays(512, 512, 0)
+    b1 = orc.bounce_rays(cam, 1)
+    b2 = orc.bounce_rays(b1, 2)
+    b3 = orc.bounce_rays(b2, 3)
+    rays = np.concatenate([cam, b1, b2, b3])
+    assert len(rays) >= 1_000_000
+    ho, _ = orc.trace(rays)
+    hg, cnt = sc.trace(rays, count_fetches=True)
+    ok = same_hits(ho, hg)
+    assert ok.all(), f"{(~ok).sum()} of {len(rays)} rays differ"
+    assert cnt[0] > 0 and cnt[1] > 0
+
+
+def test_trace_edge_cases(lib):
+    sc = h.build_cornell(16, 16, lib)
+    sc.commit()
+    assert len(sc.trace(np.zeros(0, dtype=pt.RAY_DTYPE))) == 0          # empty ray set
+    rays = np.zeros(4, dtype=pt.RAY_DTYPE)
+    rays["origin"] = [[278, 278, -800]] * 4
+    rays["dir"] = [[0, 0, 1], [0, 0, 1], [0, 0, -1], [0, 1e-30, 1]]
+    rays["tmin"] = [1e-6, 10.0, 1e-6, 1e-6]
+    rays["tmax"] = [1e27, 1.0, 1e27, 1e27]
+    hg = sc.trace(rays)
+    ho, _ = h.OracleScene(sc, mode=1).trace(rays)
+    assert same_hits(ho, hg).all()
+    assert hg["prim"][0] == 5 and hg["prim"][1] == -1 and hg["prim"][2] == -1  # back wall, empty, miss
+
+
+def test_normal_shader_radiance_tolerance(lib):
+    """Non-stochastic pass (programs/materials/normal_shader.cu): radiance = N*0.5+0.5."""
+    sc = h.build_random_prims(3, lib=lib, W=96, H=96)
+    sc.commit()
+    r = pt.Renderer(sc, 96, 96)
+    r.render(0, 1)
+    g = r.read_accum()
+    a, st = h.OracleScene(sc).render(96, 96, 0, 1)
+    assert np.array_equal(g[..., 3], a[..., 3])
+    assert np.abs(g - a).max() <= 2e-5
+    s = r.stats()
+    assert s.closest_rays == st.closest_rays == 96 * 96 and s.shadow_rays == 0
+
+
+@pytest.mark.parametrize("name", ["cornell", "zoo", "spheres488", "mesh8k"])
+def test_fixed_seed_radiance(lib, name):
+    sc = SCENES[name](lib)
+    sc.commit()
+    W = H = 64
+    r = pt.Renderer(sc, W, H)
+    r.render(0, 4)
+    g = r.read_accum()
+    a, st = h.OracleScene(sc).render(W, H, 0, 4)
+    assert (g[..., 3] == 4).all()
+    d = np.abs(g[..., :3] - a[..., :3]).max(axis=-1)
+    frac = float((d > 1e-3).mean())
+    assert frac <= 0.015, f"{frac:.4f} of pixels differ"
+    assert abs(g[..., :3].mean() - a[..., :3].mean()) <= 0.01 * a[..., :3].mean()
+    s = r.stats()
+    assert abs(int(s.closest_rays) - int(st.closest_rays)) <= 0.01 * st.closest_rays
+    assert abs(int(s.shadow_rays) - int(st.shadow_rays)) <= 0.01 * st.shadow_rays + 8
+
+
+def test_depth1_is_deterministic_and_exact(lib):
+    """max_depth=1: only camera rays that hit the light contribute (raygen.cu:85-90,122)."""
+    sc = h.build_cornell(64, 64, lib)
+    sc.commit()
+    r = pt.Renderer(sc, 64, 64)
+    r.render(0, 2, max_depth=1)
+    g = r.read_accum()
+    a, _ = h.OracleScene(sc).render(64, 64, 0, 2, max_depth=1)
+    assert np.abs(g - a).max() <= 2e-5
+
+
+def test_converged_rmse(lib):
+    sc = h.build_cornell(64, 64, lib)
+    sc.commit()
+    n = 256
+    r = pt.Renderer(sc, 64, 64)
+    r.render(0, n)
+    g = r.read_accum()
+    a, _ = h.OracleScene(sc).render(64, 64, 1000, n)  # independent samples
+    gi = np.sqrt(np.clip(g[..., :3] / n, 0, 1))
+    ai = np.sqrt(np.clip(a[..., :3] / n, 0, 1))
+    assert h.rmse(gi, ai) <= 0.02
+    assert (g[..., 3] == n).all()
+    # same seeds: the 8-bit images agree almost everywhere
+    b, _ = h.OracleScene(sc).render(64, 64, 0, n)
+    p1, p2 = pt.tonemap_png8(g, n).astype(int), pt.tonemap_png8(b, n).astype(int)
+    assert np.abs(p1 - p2).mean() <= 0.25
+
+
+def test_material_zoo_converged_rmse(lib):
+    sc = h.build_material_zoo(48, 48, lib)
+    sc.commit()
+    n = 192
+    r = pt.Renderer(sc, 48, 48)
+    r.render(0, n)
+    g = r.read_accum()
+    a, _ = h.OracleScene(sc).render(48, 48, 5000, n)
+    gi = np.sqrt(np.clip(g[..., :3] / n, 0, 1))
+    ai = np.sqrt(np.clip(a[..., :3] / n, 0, 1))
+    assert h.rmse(gi, ai) <= 0.03
+
+
+def test_accumulation_properties(lib):
+    """Size-independent properties: .w == samples, frame-range additivity, determinism,
+    pool-size independence."""
+    sc = h.build_spheres(22, W=160, H=96, lib=lib)
+    sc.commit()
+    W, H = 160, 96
+    r = pt.Renderer(sc, W, H)
+    r.render(0, 8)
+    full = r.read_accum()
+    assert (full[..., 3] == 8).all()
+    r.render(0, 4, clear=True)
+    r.render(4, 4)
+    two = r.read_accum()
+    assert (two[..., 3] == 8).all()
+    assert np.allclose(full, two, rtol=1e-5, atol=1e-5)   # fp32 summation order only
+    # one frame: every pixel receives exactly one sample -> bit-reproducible, pool independent
+    r.render(3, 1, clear=True)
+    a = r.read_accum()
+    r2 = pt.Renderer(sc, W, H)
+    r2.set_pool(2048)
+    r2.render(3, 1)
+    b = r2.read_accum()
+    assert np.array_equal(a, b)
+    assert r2.stats().iterations > r.stats().iterations
+
+
+def test_russian_roulette_and_depth_variants(lib):
+    sc = h.build_cornell(32, 32, lib)
+    sc.commit()
+    o = h.OracleScene(sc)
+    r = pt.Renderer(sc, 32, 32)
+    for depth, rr in [(3, False), (14, True), (50, False)]:
+        r.render(0, 3, max_depth=depth, russian=rr, clear=True)
+        g = r.read_accum()
+        a, _ = o.render(32, 32, 0, 3, max_depth=depth, russian=rr)
+        d = np.abs(g[..., :3] - a[..., :3]).max(axis=-1)
+        assert (d > 1e-3).mean() <= 0.02, (depth, rr)
+
+
+def test_textures_and_env_map(lib):
+    """checker (programs/textures/checkered_texture.cu), image (image_texture.cu), vector
+    (vector.cu) textures and the HDR environment miss program (miss.cu:64-95)."""
+    s = pt.Scene(lib)
+    img = np.random.default_rng(5).uniform(0, 1, (32, 64, 4)).astype(np.float32)
+    iid = s.add_image(img)
+    env = s.add_image(h.synthetic_hdri())
+    texs = [h.tex_const(0.2, 0.3, 0.1), h.tex_const(0.9, 0.9, 0.9), pt.Texture(pt.TEX_CHECKER, pt.F3(0, 0, 0), 0, 1),
+            pt.Texture(pt.TEX_IMAGE, pt.F3(0, 0, 0), iid, 0), pt.Texture(pt.TEX_VECTOR, pt.F3(0, 0, 0), 0, 3)]
+    s.set_textures(texs)
+    s.set_texture_vector([0, 1, 3])
+    s.set_materials([h.material(pt.MAT_LAMBERTIAN, 2), h.material(pt.MAT_LAMBERTIAN, 3),
+                     h.material(pt.MAT_LAMBERTIAN, 4)])
+    s.add_spheres([pt.Sphere(pt.F3(0, -100.5, -1), 100), pt.Sphere(pt.F3(0, 0, -1), 0.5)], [0, 1])
+    tris, _ = h.heightfield_mesh(8, size=2.0, amp=0.1)
+    tris = tris + np.array([1.5, 0.2, -1.0] * 3, dtype=np.float32)
+    uv = np.tile(np.array([0, 0, 1, 0, 1, 1], dtype=np.float32), (len(tris), 1))
+    s.add_mesh(tris, 2, uv=uv, tex_index=np.arange(len(tris)) % 4)   # index 3 is out of range -> black
+    s.set_camera(h.make_camera([0, 1, 3], [0.5, 0, -1], [0, 1, 0], 50, 1.0, 0.0, 1.0))
+    s.set_miss(pt.Miss(pt.MISS_HDR, pt.F3(0, 0, 0), pt.F3(0, 0, 0), env, 1, 0))
+    s.commit()
+    r = pt.Renderer(s, 64, 64)
+    r.render(0, 4)
+    g = r.read_accum()
+    a, _ = h.OracleScene(s).render(64, 64, 0, 4)
+    d = np.abs(g[..., :3] - a[..., :3]).max(axis=-1)
+    assert (d > 1e-3).mean() <= 0.015
+    assert g[..., :3].mean() > 0.05
+
+
+def test_caller_owned_accum_buffer(lib):
+    """pt_renderer_create(d_accum): a torch tensor serves as the accumulation / NCCL buffer."""
+    import torch
+    sc = h.build_cornell(32, 32, lib)
+    sc.commit()
+    t = torch.zeros(32, 32, 4, device="cuda", dtype=torch.float32)
+    r = pt.Renderer(sc, 32, 32, d_accum=t.data_ptr())
+    r.render(0, 2)
+    assert r.accum_device_ptr() == t.data_ptr()
+    assert np.array_equal(t.cpu().numpy(), r.read_accum())
+    assert float(t[..., 3].min()) == 2.0
+
+
+def test_instrumented_counters(lib):
+    sc = h.build_mesh_scene(64, 64, 64, lib)
+    sc.commit()
+    r = pt.Renderer(sc, 64, 64)
+    r.set_flags(pt.FLAG_COUNT_FETCHES | pt.FLAG_TIME_KERNELS)
+    r.render(0, 2)
+    s = r.stats()
+    assert s.nodes_fetched >= s.closest_rays and s.leaves_fetched > 0
+    assert s.ms_trace_closest > 0 and s.ms_total > 0
+    base = r.read_accum()
+    r.set_flags(0)
+    r.render(0, 2, clear=True)
+    assert np.allclose(base, r.read_accum(), rtol=1e-5, atol=1e-6)

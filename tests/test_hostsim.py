@@ -1,0 +1,102 @@
+"""CPU logic tests of the kernel cores (builder, BVH8 traversal, shading) by host
+simulation (tests/hostsim/sim.cpp) against the oracle.  The GPU parity tests proper
+are in test_gpu_parity.py; these catch logic errors without a GPU."""
+import numpy as np
+import pytest
+
+import helpers as h
+
+pt = h.pt
+
+
+def same_hits(a, b):
+    return ((a["prim"] == b["prim"]) & (a["t"].view(np.uint32) == b["t"].view(np.uint32)) &
+            (a["u"].view(np.uint32) == b["u"].view(np.uint32)) & (a["v"].view(np.uint32) == b["v"].view(np.uint32)))
+
+
+SCENES = {
+    "cornell": lambda: h.build_cornell(32, 32),
+    "zoo": lambda: h.build_material_zoo(32, 32),
+    "spheres": lambda: h.build_spheres(12, W=32, H=32),
+    "soup": lambda: h.build_random_prims(3),
+    "soup_noxf": lambda: h.build_random_prims(4, xforms=False),
+    "mesh": lambda: h.build_mesh_scene(40, 32, 32),
+    "single": lambda: h.build_random_prims(5, n_sph=1, n_rect=0, n_box=0, n_tri=0),
+    "two": lambda: h.build_random_prims(6, n_sph=0, n_rect=0, n_box=0, n_tri=2),
+}
+
+
+@pytest.mark.parametrize("name", list(SCENES))
+def test_bvh8_structure_and_hit_ids(name):
+    sc = SCENES[name]()
+    sim = h.SimScene(sc)
+    assert sim.validate() == 0
+    orc = h.OracleScene(sc, mode=1)  # brute force: the definition of a hit
+    rays = np.concatenate([orc.camera_rays(32, 32, 0), h.random_rays(3000, 11)])
+    rays = np.concatenate([rays, orc.bounce_rays(rays, 5)])
+    ho, _ = orc.trace(rays)
+    hs, _ = sim.trace(rays)
+    assert same_hits(ho, hs).all()
+
+
+def test_oracle_bvh_equals_bruteforce():
+    sc = h.build_mesh_scene(48, 32, 32)
+    a, b = h.OracleScene(sc, mode=1), h.OracleScene(sc, mode=2)
+    rays = np.concatenate([a.camera_rays(64, 64, 1), h.random_rays(5000, 2)])
+    rays = np.concatenate([rays, a.bounce_rays(rays, 9)])
+    ha, _ = a.trace(rays)
+    hb, _ = b.trace(rays)
+    assert same_hits(ha, hb).all()
+
+
+def test_refinement_lowers_sah():
+    sc = h.build_mesh_scene(64, 32, 32)
+    info = h.SimScene(sc).info()
+    assert info["n_treelets"] > 0 and info["sah_after"] < info["sah_before"]
+
+
+def test_degenerate_inputs():
+    # coincident primitives (equal Morton codes, equal t): ties resolve to the lowest id
+    s = pt.Scene()
+    s.set_textures([h.tex_const(0.5)])
+    s.set_materials([h.material(pt.MAT_NORMAL)])
+    s.add_spheres([pt.Sphere(pt.F3(0, 0, 0), 1.0)] * 9, [0] * 9)
+    sim, orc = h.SimScene(s), h.OracleScene(s, mode=1)
+    assert sim.validate() == 0
+    rays = h.random_rays(500, 4, extent=3.0)
+    hs, _ = sim.trace(rays)
+    ho, _ = orc.trace(rays)
+    assert same_hits(ho, hs).all()
+    assert set(np.unique(hs["prim"])) <= {-1, 0}
+    # empty interval / zero direction components
+    rays = np.zeros(3, dtype=pt.RAY_DTYPE)
+    rays["origin"] = [[0, 0, -5], [0, 0, -5], [0.5, 0, -5]]
+    rays["dir"] = [[0, 0, 1], [0, 0, 1], [0, 0, 1]]
+    rays["tmin"] = [1e-3, 5.0, 1e-3]
+    rays["tmax"] = [1e27, 1.0, 1e27]
+    hs, _ = sim.trace(rays)
+    assert hs["prim"][0] == 0 and abs(hs["t"][0] - 4.0) < 1e-6 and hs["prim"][1] == -1 and hs["prim"][2] == 0
+
+
+@pytest.mark.parametrize("name,frames", [("cornell", 3), ("zoo", 3), ("spheres", 3), ("mesh", 2), ("soup", 1)])
+def test_wavefront_logic_equals_reference_loop(name, frames):
+    """The speculative two-continuation NEE scheme (shading.h) must reproduce the reference's
+    per-sample RNG stream: on one CPU (same libm) the images are bit-identical."""
+    sc = SCENES[name]()
+    W = H = 24
+    a, _ = h.OracleScene(sc).render(W, H, 0, frames)
+    b = h.SimScene(sc).render(W, H, 0, frames)
+    assert (a[..., 3] == frames).all() and (b[..., 3] == frames).all()
+    assert np.array_equal(a, b)
+
+
+def test_russian_roulette_and_depth_cutoff():
+    sc = h.build_cornell(16, 16)
+    o, s = h.OracleScene(sc), h.SimScene(sc)
+    for depth, rr in [(1, True), (3, False), (12, True), (50, False)]:
+        a, _ = o.render(16, 16, 0, 2, max_depth=depth, russian=rr)
+        b = s.render(16, 16, 0, 2, max_depth=depth, russian=rr)
+        assert np.array_equal(a, b), (depth, rr)
+    # programs/raygen.cu:122: depth exhaustion returns black, so depth=1 only sees the light
+    a, _ = o.render(16, 16, 0, 1, max_depth=1)
+    assert a[..., :3].max() <= 7.0 + 1e-6
