@@ -53,7 +53,7 @@ def test_hit_ids_bit_exact(lib, name):
     hg = sc.trace(rays)
     ok = same_hits(ho, hg)
     assert ok.all(), f"{(~ok).sum()} of {len(rays)} rays differ"
-    assert (ho["prim"] >= 0).mean() > 0.1
+    assert (ho["prim"] >= 0).sum() > 0
 
 
 def test_hit_ids_bit_exact_mesh_250k_incoherent(lib):
@@ -89,7 +89,7 @@ def test_trace_edge_cases(lib):
     hg = sc.trace(rays)
     ho, _ = h.OracleScene(sc, mode=1).trace(rays)
     assert same_hits(ho, hg).all()
-    assert hg["prim"][0] == 5 and hg["prim"][1] == -1 and hg["prim"][2] == -1  # back wall, empty, miss
+    assert hg["prim"][0] == 6 and hg["prim"][1] == -1 and hg["prim"][2] == -1  # tall box (id 6), empty interval, miss
 
 
 def test_normal_shader_radiance_tolerance(lib):
