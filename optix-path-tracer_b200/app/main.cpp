@@ -1,0 +1,84 @@
+// main.cpp — headless replacement for the reference's GUI application
+// (OptiX-Path-Tracer/main.cpp): same App_State knobs as CLI flags, same
+// Optix_Config -> render loop -> Save_PNG/Save_HDR flow, same console messages.
+// The ImGui/GLFW window itself is out of scope (no GL on the box).
+#include <chrono>
+#include <cstdlib>
+#include <cstring>
+#include <iostream>
+
+#include "../host_includes/image_save.hpp"
+
+static int Scene_Config(App_State& app) {
+  app.context->setRayTypeCount(2);
+  app.context->setMaxTraceDepth(5);
+  app.context["samples"]->setInt(app.samples);
+  app.context["russian"]->setInt(app.russian);
+  app.context["maxDepth"]->setInt(app.depth);
+  switch (app.scene) {
+    case 0: InOneWeekend(app); break;
+    case 1: MovingSpheres(app); break;
+    case 2: Cornell(app); break;
+    case 3: Final_Next_Week(app); break;
+    case 4: Test_Scene(app); break;
+    case 5: Cornell_Materials(app); break;
+    case 6: Mesh_HDRI(app); break;
+    default: throw "Selected scene is unknown";
+  }
+  app.accBuffer = createFrameBuffer(app.W, app.H, app.context);
+  app.context["acc_buffer"]->set(app.accBuffer);
+  app.displayBuffer = createDisplayBuffer(app.W, app.H, app.context);
+  app.context["display_buffer"]->set(app.displayBuffer);
+  auto t0 = std::chrono::system_clock::now();
+  app.context->validate();
+  app.context->launch(0, 0, 0);  // scene upload + GPU BVH build
+  printf("BVH Building Time: %.2f\n", std::chrono::duration<float>(std::chrono::system_clock::now() - t0).count());
+  return 0;
+}
+
+int main(int ac, char** av) {
+  App_State app;
+  int batch = 0;
+  for (int i = 1; i < ac; i++) {
+    auto arg = [&](const char* n) { return !strcmp(av[i], n) && i + 1 < ac; };
+    if (arg("--width")) app.W = atoi(av[++i]);
+    else if (arg("--height")) app.H = atoi(av[++i]);
+    else if (arg("--samples")) app.samples = atoi(av[++i]);
+    else if (arg("--scene")) app.scene = atoi(av[++i]);
+    else if (arg("--model")) app.model = atoi(av[++i]);
+    else if (arg("--depth")) app.depth = atoi(av[++i]);
+    else if (arg("--russian")) app.russian = atoi(av[++i]) != 0;
+    else if (arg("--file")) app.fileName = av[++i];
+    else if (arg("--type")) app.fileType = atoi(av[++i]);
+    else if (arg("--batch")) batch = atoi(av[++i]);
+    else {
+      printf("usage: %s [--width W] [--height H] [--samples N] [--scene 0..6] [--model M] [--depth D]\n"
+             "          [--russian 0|1] [--file name] [--type 0(PNG)|1(HDR)] [--batch frames-per-launch]\n", av[0]);
+      return 1;
+    }
+  }
+  try {
+    Scene_Config(app);
+    auto t0 = std::chrono::system_clock::now();
+    if (batch <= 0) batch = app.samples;  // default: the whole job in one wavefront run
+    for (app.currentSample = 0; app.currentSample < app.samples; app.currentSample += batch) {
+      int n = std::min(batch, app.samples - app.currentSample);
+      if (batch == 1) {  // the reference's loop: one launch per sample (main.cpp:264-293)
+        app.context["frame"]->setInt(app.currentSample);
+        app.context->launch(0, app.W, app.H);
+      } else {
+        app.context->launchFrames(app.currentSample, n, app.W, app.H);
+      }
+    }
+    float renderTime = std::chrono::duration<float>(std::chrono::system_clock::now() - t0).count();
+    int ok = app.fileType == 0 ? Save_PNG(app, app.accBuffer) : Save_HDR(app, app.accBuffer);
+    printf("Render time: %.3f s (%.1f Msamples/s)\n", renderTime, double(app.W) * app.H * app.samples / renderTime / 1e6);
+    printf("%s %s\n", ok ? "Saved" : "FAILED to save", app.fileName.c_str());
+    return ok ? 0 : 2;
+  } catch (const char* e) {
+    fprintf(stderr, "error: %s\n", e);
+  } catch (const std::string& e) {
+    fprintf(stderr, "error: %s\n", e.c_str());
+  }
+  return 3;
+}

@@ -1,0 +1,135 @@
+"""Host facade (C++, optix-path-tracer_b200/host_includes): the reference's scene-building
+surface re-implemented over the C ABI.  CPU-only tests: scenes built through the facade
+equal the flat scenes the tests build by hand, and — where /root/reference exists — the
+reference's own scenes.hpp compiles UNCHANGED against the facade headers and yields the
+same scenes (the drop-in claim)."""
+import os
+import pickle
+import shutil
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import helpers as h
+import facade_dump
+
+pt = h.pt
+REF_SCENES = "/root/reference/OptiX-Path-Tracer/host_includes/scenes.hpp"
+
+
+def dump(so, scene_id, W, H, model, tmp_path, tag):
+    out = str(tmp_path / f"{tag}_{scene_id}.pkl")
+    env = dict(os.environ, PYTHONPATH=os.path.join(h.ROOT, "tests"))
+    r = subprocess.run([sys.executable, os.path.join(h.ROOT, "tests", "facade_dump.py"), so, str(scene_id), str(W), str(H),
+                        str(model), out], capture_output=True, text=True, env=env)
+    assert r.returncode == 0, r.stderr + r.stdout
+    return pickle.load(open(out, "rb"))
+
+
+@pytest.fixture(scope="module")
+def host_so():
+    h.build_product()
+    if not os.path.exists(pt.HOST_LIB_PATH):
+        subprocess.run(["make", "libptb200_host.so"], cwd=os.path.join(h.PKG_DIR, "csrc"), check=True)
+    return pt.HOST_LIB_PATH
+
+
+def same(a, b, skip=()):
+    for k in a:
+        if k in skip:
+            continue
+        assert np.array_equal(a[k], b[k]), k
+
+
+def test_cornell_matches_hand_built_scene(host_so, tmp_path):
+    a = dump(host_so, 2, 512, 512, 0, tmp_path, "mine")
+    hand = h.build_cornell(512, 512)          # keep the scene alive while its description is read
+    b = facade_dump.desc_arrays(hand.desc())
+    assert a["prims"].shape == b["prims"].shape
+    # same primitives, transforms, light and camera; material/texture ids may be numbered differently
+    same(a, b, skip=("prims", "materials", "textures"))
+    assert np.array_equal(a["prims"].reshape(-1, 4)[:, [0, 1, 3]], b["prims"].reshape(-1, 4)[:, [0, 1, 3]])
+    ma, mb = a["materials"].reshape(-1, 6), b["materials"].reshape(-1, 6)
+    ta, tb = a["textures"].reshape(-1, 6), b["textures"].reshape(-1, 6)
+    for pa, pb in zip(a["prims"].reshape(-1, 4), b["prims"].reshape(-1, 4)):
+        assert ma[pa[2]][0] == mb[pb[2]][0]                                   # material type
+        assert np.array_equal(ta[ma[pa[2]][1]][:4], tb[mb[pb[2]][1]][:4])     # albedo texture
+
+
+def test_rtow_scene_shape(host_so, tmp_path):
+    a = dump(host_so, 0, 1200, 800, 0, tmp_path, "mine")
+    prims = a["prims"].reshape(-1, 4)
+    assert len(prims) == 488 and (prims[:, 0] == pt.PRIM_SPHERE).all()       # 1 + 22*22 + 3
+    types = a["materials"].reshape(-1, 6)[prims[:, 2], 0]
+    n_l, n_m, n_d = (types == pt.MAT_LAMBERTIAN).sum(), (types == pt.MAT_METAL).sum(), (types == pt.MAT_DIELECTRIC).sum()
+    assert n_l + n_m + n_d == 488 and n_l > 300 and n_m > 30 and n_d > 5
+    assert a["miss"][0] == pt.MISS_GRADIENT and len(a["lights"]) == 0
+
+
+def test_other_scenes_build(host_so, tmp_path):
+    c3 = dump(host_so, 5, 64, 64, 0, tmp_path, "mine")
+    types = set(c3["materials"].reshape(-1, 6)[:, 0])
+    assert {pt.MAT_DIELECTRIC, pt.MAT_OREN_NAYAR, pt.MAT_TORRANCE_SPARROW, pt.MAT_ASHIKHMIN_SHIRLEY} <= types
+    c4 = dump(host_so, 6, 64, 64, 16, tmp_path, "mine")       # 16x16 grid through OBJ + .hdr files
+    assert len(c4["tri_v"]) == 16 * 16 * 2 * 9 and c4["n_images"] == 1 and c4["miss"][0] == pt.MISS_HDR
+    fnw = dump(host_so, 3, 64, 64, 0, tmp_path, "mine")
+    assert len(fnw["prims"]) // 4 == 400 + 1 + 6 + 1000 and len(fnw["xforms"]) // 24 == 1000
+    ms = dump(host_so, 1, 64, 64, 0, tmp_path, "mine")
+    assert len(ms["prims"]) // 4 == 1 + 484 + 3 + 1 and len(ms["lights"]) // 10 == 1
+
+
+@pytest.mark.skipif(not os.path.exists(REF_SCENES), reason="reference tree not present")
+def test_reference_scenes_header_drops_in(host_so, tmp_path):
+    """Compile the reference's scenes.hpp (copied to a temp dir, never into the repo) against
+    the facade headers and compare the scenes it builds with ours."""
+    shutil.copy(REF_SCENES, tmp_path / "scenes.hpp")
+    so = str(tmp_path / "libref_scenes.so")
+    csrc = os.path.join(h.PKG_DIR, "csrc")
+    cmd = ["/usr/bin/g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-w", "-DPTH_REFERENCE_SCENES",
+           f'-DSCENES_HEADER="{tmp_path}/scenes.hpp"', "-I" + os.path.join(h.PKG_DIR, "host_includes"), "-o", so,
+           os.path.join(h.PKG_DIR, "app", "facade_capi.cpp"), "-L" + csrc, "-lptb200", "-Wl,-rpath," + csrc]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    for scene_id, (W, H) in ((2, (512, 512)), (0, (1200, 800))):
+        ref = dump(so, scene_id, W, H, 0, tmp_path, "ref")
+        mine = dump(host_so, scene_id, W, H, 0, tmp_path, "mine")
+        # identical geometry, transforms, lights, camera and miss program
+        same(ref, mine, skip=("prims", "materials", "textures"))
+        pr, pm = ref["prims"].reshape(-1, 4), mine["prims"].reshape(-1, 4)
+        assert np.array_equal(pr[:, [0, 1, 3]], pm[:, [0, 1, 3]])
+        mr, mm = ref["materials"].reshape(-1, 6), mine["materials"].reshape(-1, 6)
+        tr, tm = ref["textures"].reshape(-1, 6), mine["textures"].reshape(-1, 6)
+        for a, b in zip(pr, pm):
+            ra, rb = mr[a[2]], mm[b[2]]
+            assert ra[0] == rb[0] and ra[3] == rb[3] and ra[4] == rb[4]        # type and parameters
+            assert np.array_equal(tr[ra[1]][:4], tm[rb[1]][:4])                # albedo
+
+
+def test_png_and_hdr_roundtrip(tmp_path):
+    """io_formats.hpp codecs through a tiny C++ driver: PNG is readable by PIL, .hdr round-trips."""
+    src = tmp_path / "io.cpp"
+    src.write_text(r'''
+#include "io_formats.hpp"
+int main(int, char** av) {
+  unsigned char px[4*3*3]; for (int i = 0; i < 36; i++) px[i] = (unsigned char)(i * 7);
+  if (!ptio::write_png(av[1], 4, 3, px)) return 1;
+  std::vector<float> img(8*4*3); for (size_t i = 0; i < img.size(); i++) img[i] = 0.01f * (i % 50);
+  if (!ptio::write_radiance_hdr(av[2], 8, 4, img.data())) return 2;
+  int W, H; std::vector<float> back;
+  if (!ptio::load_radiance_hdr(av[2], W, H, back) || W != 8 || H != 4) return 3;
+  for (int i = 0; i < 8*4; i++) for (int c = 0; c < 3; c++) {
+    float a = img[3*i+c], b = back[4*i+c];
+    if (fabsf(a - b) > 0.02f * fmaxf(a, 0.05f) + 2e-3f) return 4;
+  }
+  return 0;
+}''')
+    exe = str(tmp_path / "io")
+    subprocess.run(["/usr/bin/g++", "-O1", "-std=c++17", "-I" + os.path.join(h.PKG_DIR, "host_includes"), "-o", exe,
+                    str(src)], check=True)
+    png, hdr = str(tmp_path / "t.png"), str(tmp_path / "t.hdr")
+    assert subprocess.run([exe, png, hdr]).returncode == 0
+    from PIL import Image
+    im = np.array(Image.open(png))
+    assert im.shape == (3, 4, 3) and (im.reshape(-1) == (np.arange(36) * 7 % 256)).all()
