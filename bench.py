@@ -162,6 +162,7 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--spp", type=int, default=0, help="override samples per pixel (dev only; invalidates the metric)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--pool", type=int, default=0, help="path-pool size (dev only; 0 = library default)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -193,6 +194,8 @@ def main():
     info = sc.bvh_info()
     accum = torch.zeros(H, W, 4, device="cuda", dtype=torch.float32)
     r = pt.Renderer(sc, W, H, d_accum=accum.data_ptr())
+    if args.pool:
+        r.set_pool(args.pool)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
     from optix_path_tracer_b200 import multigpu
     first, _ = multigpu.frame_range(rank, world, spp)

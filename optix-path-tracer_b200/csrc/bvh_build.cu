@@ -8,6 +8,7 @@
 
 #include <cfloat>
 #include <cstdio>
+#include <cstdlib>
 
 #include "scene_host.h"
 
@@ -26,10 +27,11 @@ __device__ __forceinline__ void atomic_max_f(float* addr, float v) {
   else atomicMin((unsigned*)addr, __float_as_uint(v));
 }
 
-// scene_bounds: [0..2] centroid min, [3..5] centroid max
+// scene_bounds: [0..2] centroid min, [3..5] centroid max, [6] largest |coordinate|
 __global__ void k_prim_bounds(BuildIn in, float4* plo, float4* phi, float* scene_bounds) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   float3 c = f3(0.f);
+  float amax = 0.f;
   bool ok = i < in.n;
   if (ok) {
     float3 lo, hi;
@@ -37,6 +39,8 @@ __global__ void k_prim_bounds(BuildIn in, float4* plo, float4* phi, float* scene
     plo[i] = make_float4(lo.x, lo.y, lo.z, 0.f);
     phi[i] = make_float4(hi.x, hi.y, hi.z, 0.f);
     c = (lo + hi) * 0.5f;
+    amax = fmaxf(fmaxf(fmaxf(fabsf(lo.x), fabsf(lo.y)), fabsf(lo.z)), fmaxf(fmaxf(fabsf(hi.x), fabsf(hi.y)), fabsf(hi.z)));
+    if (!(amax < 3.0e38f)) amax = 0.f;
   }
   // warp reduce then one atomic per warp
   float mn[3] = {ok ? c.x : FLT_MAX, ok ? c.y : FLT_MAX, ok ? c.z : FLT_MAX};
@@ -46,11 +50,23 @@ __global__ void k_prim_bounds(BuildIn in, float4* plo, float4* phi, float* scene
       mn[a] = fminf(mn[a], __shfl_xor_sync(0xffffffffu, mn[a], o));
       mx[a] = fmaxf(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], o));
     }
-  if ((threadIdx.x & 31) == 0)
+  for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+  if ((threadIdx.x & 31) == 0) {
     for (int a = 0; a < 3; a++) {
       if (mn[a] != FLT_MAX) atomic_min_f(scene_bounds + a, mn[a]);
       if (mx[a] != -FLT_MAX) atomic_max_f(scene_bounds + 3 + a, mx[a]);
     }
+    atomic_max_f(scene_bounds + 6, amax);
+  }
+}
+
+__global__ void k_pad_bounds(int n, float4* plo, float4* phi, const float* scene_bounds) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float3 lo = xyz(plo[i]), hi = xyz(phi[i]);
+  pad_bounds(lo, hi, scene_bounds[6]);
+  plo[i] = make_float4(lo.x, lo.y, lo.z, 0.f);
+  phi[i] = make_float4(hi.x, hi.y, hi.z, 0.f);
 }
 
 __global__ void k_morton(int n, const float4* plo, const float4* phi, const float* sb, uint64_t* keys,
@@ -143,8 +159,34 @@ int upload(DevBuf& b, const std::vector<T>& v) {
 
 }  // namespace
 
+namespace {
+struct StageTimer {  // PTB200_BUILD_TIMING=1 prints per-stage GPU time of the build
+  bool on;
+  cudaEvent_t last{};
+  explicit StageTimer() : on(getenv("PTB200_BUILD_TIMING") != nullptr) {
+    if (on) {
+      cudaEventCreate(&last);
+      cudaEventRecord(last);
+    }
+  }
+  void mark(const char* name) {
+    if (!on) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e);
+    cudaEventSynchronize(e);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, last, e);
+    fprintf(stderr, "[bvh build] %-16s %8.3f ms\n", name, ms);
+    cudaEventDestroy(last);
+    last = e;
+  }
+};
+}  // namespace
+
 int pt_bvh_build(pt_scene* s) {
   const int n = (int)s->prims.size();
+  StageTimer tm;
   if (n <= 0) {
     pt_set_error("scene has no primitives");
     return PT_ERR_INVALID;
@@ -168,14 +210,17 @@ int pt_bvh_build(pt_scene* s) {
   DevBuf nodes2, parent, leaf_parent, count, flag, roots, counters, cost;
   PT_CUDA(plo.alloc((size_t)n * 16));
   PT_CUDA(phi.alloc((size_t)n * 16));
-  PT_CUDA(sbounds.alloc(6 * 4));
+  PT_CUDA(sbounds.alloc(8 * 4));
   {
-    float init[6] = {FLT_MAX, FLT_MAX, FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX};
+    float init[8] = {FLT_MAX, FLT_MAX, FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX, 0.f, 0.f};
     PT_CUDA(cudaMemcpy(sbounds.p, init, sizeof(init), cudaMemcpyHostToDevice));
   }
   k_prim_bounds<<<nblk(n), TB>>>(in, plo.as<float4>(), phi.as<float4>(), sbounds.as<float>());
   PT_CUDA(cudaGetLastError());
+  k_pad_bounds<<<nblk(n), TB>>>(n, plo.as<float4>(), phi.as<float4>(), sbounds.as<float>());
+  PT_CUDA(cudaGetLastError());
 
+  tm.mark("bounds");
   PT_CUDA(keys.alloc((size_t)n * 8));
   PT_CUDA(keys2.alloc((size_t)n * 8));
   PT_CUDA(vals.alloc((size_t)n * 4));
@@ -192,6 +237,7 @@ int pt_bvh_build(pt_scene* s) {
                                             vals.as<uint32_t>(), vals2.as<uint32_t>(), n, 0, 63));
   }
 
+  tm.mark("morton+sort");
   const int ni = n > 1 ? n - 1 : 1;
   PT_CUDA(nodes2.alloc((size_t)ni * sizeof(Bvh2Node)));
   PT_CUDA(parent.alloc((size_t)ni * 4));
@@ -221,8 +267,10 @@ int pt_bvh_build(pt_scene* s) {
   if (n > 1) {
     k_karras<<<nblk(n - 1), TB>>>(t);
     PT_CUDA(cudaGetLastError());
+    tm.mark("karras");
     k_refit<<<nblk(n), TB>>>(t);
     PT_CUDA(cudaGetLastError());
+    tm.mark("refit");
 
     PT_CUDA(cudaMemset(cost.p, 0, 16));
     k_sah_cost<<<nblk(n - 1), TB>>>(t, cost.as<double>());
@@ -237,6 +285,7 @@ int pt_bvh_build(pt_scene* s) {
       k_treelet_sah<<<nblk(n_roots, 64), 64>>>(t, roots.as<int>(), n_roots);
       PT_CUDA(cudaGetLastError());
     }
+    tm.mark("treelet sah");
     k_sah_cost<<<nblk(n - 1), TB>>>(t, cost.as<double>() + 1);
     double hc[2];
     PT_CUDA(cudaMemcpy(hc, cost.p, 16, cudaMemcpyDeviceToHost));
@@ -286,6 +335,7 @@ int pt_bvh_build(pt_scene* s) {
       return PT_ERR_INVALID;
     }
   }
+  tm.mark("collapse");
   int hcnt[2];
   PT_CUDA(cudaMemcpy(hcnt, d_cnt, 8, cudaMemcpyDeviceToHost));
   PT_CUDA(cudaEventRecord(ev1));

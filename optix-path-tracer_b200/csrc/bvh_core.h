@@ -87,11 +87,16 @@ PT_HD void prim_bounds(const BuildIn& in, int id, float3& lo, float3& hi) {
     lo = nlo;
     hi = nhi;
   }
-  // The reference pads 1e-4 (rect/triangle) .. 1e-3 (box).  Pad every axis by
-  // an absolute + relative margin so the (FMA, quantised) box test can never
-  // cull a primitive the exact intersection test would accept.
+}
+
+// Padding.  The reference pads 1e-4 (rect/triangle) .. 1e-3 (box) on selected axes.  Here every
+// axis gets a margin proportional to the primitive's own coordinates and to the scene scale S
+// (largest |coordinate| in the scene), so the (FMA, quantised) box test can never cull a
+// primitive the exact intersection test would accept: box-test rounding error grows with
+// |coordinate| * 2^-23 and with the distance a ray travels (~S).
+PT_HD void pad_bounds(float3& lo, float3& hi, float S) {
   float3 m = fmax3(f3(fabsf(lo.x), fabsf(lo.y), fabsf(lo.z)), f3(fabsf(hi.x), fabsf(hi.y), fabsf(hi.z)));
-  float3 pad = f3(1e-3f) + m * 1e-5f;
+  float3 pad = m * 2e-5f + f3(2e-6f * S + 1e-7f);
   lo = lo - pad;
   hi = hi + pad;
 }

@@ -18,10 +18,12 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 #include "scene_host.h"
 #include "shading.h"
+#include "trace_sched.cuh"
 #include "traverse.h"
 
 namespace cg = cooperative_groups;
@@ -43,6 +45,7 @@ struct ShadowBuf {  // 112 B / shadow request
 
 struct Ctrl {
   int n_cur, n_next, n_shadow;
+  int fetch_closest, fetch_shadow;  // ray cursors of the persistent traversal kernels
   int gen_base, gen_n;
   int bin_count[NBINS];
   unsigned long long sample_base, next_sample, total_samples;
@@ -114,6 +117,8 @@ __global__ void k_iter_begin(Ctrl* c, int pool) {
   c->n_cur = n + g;
   c->n_next = 0;
   c->n_shadow = 0;
+  c->fetch_closest = 0;
+  c->fetch_shadow = 0;
   for (int i = 0; i < NBINS; i++) c->bin_count[i] = 0;
   c->stat_closest += (unsigned long long)c->n_cur;
   c->stat_iters += 1;
@@ -140,34 +145,45 @@ __global__ void k_generate(SceneDev sc, Params p, const Ctrl* c, PathBuf cur) {
   }
 }
 
-template <bool COUNT>
-__global__ void __launch_bounds__(128) k_trace(SceneDev sc, Ctrl* c, PathBuf cur, float4* hits, uint32_t* bin_q, int pool) {
-  const int n = c->n_cur;
-  uint32_t cn = 0, cl = 0;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+// closest-hit traversal of the current wavefront: persistent warps, vote-scheduled (trace_sched.cuh)
+struct ClosestPolicy {
+  const SceneDev& sc;
+  Ctrl* c;
+  PathBuf cur;
+  float4* hits;
+  uint32_t* bin_q;
+  int pool;
+  __device__ __forceinline__ bool load(int i, float3& o, float3& d, float& tmin, float& tmax) const {
     float4 o4 = cur.o_seed[i], d4 = cur.d_pack[i];
-    uint32_t pk = __float_as_uint(d4.w);
-    int depth = (pk >> 23) & 0xff;
-    TraceHit h;
-    bvh8_closest<COUNT>(sc, f3(o4.x, o4.y, o4.z), f3(d4.x, d4.y, d4.z), depth == 0 ? 1e-6f : 1e-3f, PT_RAY_MAX, h,
-                        cn, cl);
+    int depth = (__float_as_uint(d4.w) >> 23) & 0xff;
+    o = f3(o4.x, o4.y, o4.z);
+    d = f3(d4.x, d4.y, d4.z);
+    tmin = depth == 0 ? 1e-6f : 1e-3f;  // raygen.cu:61 camera rays, :102 bounced rays
+    tmax = PT_RAY_MAX;
+    return true;
+  }
+  __device__ __forceinline__ void emit(int i, const TraceHit& h, unsigned fin) const {
     hits[i] = make_float4(h.t, __int_as_float(h.leaf), h.u, h.v);
     int key = BIN_MISS;
-    if (h.leaf >= 0) {
-      uint32_t matw = __float_as_uint(__ldg(&sc.leaves[h.leaf].c.w));
-      key = (int)(matw >> 24);
-    }
-    // material binning: lanes with the same key share one atomic
-    unsigned active = __activemask();
-    unsigned peers = __match_any_sync(active, key);
+    if (h.leaf >= 0) key = (int)(__float_as_uint(__ldg(&sc.leaves[h.leaf].c.w)) >> 24);
+    // material binning: finished lanes with the same key share one atomic
+    unsigned peers = __match_any_sync(fin, key);
     int leader = __ffs(peers) - 1;
     int lane = threadIdx.x & 31;
     int base = 0;
     if (lane == leader) base = atomicAdd(&c->bin_count[key], __popc(peers));
     base = __shfl_sync(peers, base, leader);
-    int pos = base + __popc(peers & ((1u << lane) - 1));
-    bin_q[(size_t)key * pool + pos] = (uint32_t)i;
+    bin_q[(size_t)key * pool + base + __popc(peers & ((1u << lane) - 1))] = (uint32_t)i;
   }
+};
+
+template <bool COUNT>
+__global__ void __launch_bounds__(PT_TRACE_THREADS) k_trace(SceneDev sc, Ctrl* c, PathBuf cur, float4* hits,
+                                                            uint32_t* bin_q, int pool, SchedParams sched) {
+  __shared__ uint2 s_stack[PT_SMEM_STACK * PT_TRACE_THREADS];
+  ClosestPolicy pol{sc, c, cur, hits, bin_q, pool};
+  uint32_t cn = 0, cl = 0;
+  trace_persistent<COUNT>(sc, c->n_cur, &c->fetch_closest, pol, s_stack, sched, cn, cl);
   if (COUNT) {
     for (int o = 16; o > 0; o >>= 1) {
       cn += __shfl_xor_sync(0xffffffffu, cn, o);
@@ -233,22 +249,26 @@ __global__ void __launch_bounds__(128) k_miss(SceneDev sc, Params p, Ctrl* c, Pa
 }
 
 // shadow ray: light_sample.cuh:62-72 + hit.cu:16-24 under the pinned semantics
-// (visible <=> closest hit in (1e-3, inf) is a Diffuse_Light)
-template <bool COUNT>
-__global__ void __launch_bounds__(128) k_shadow(SceneDev sc, Params p, Ctrl* c, PathBuf next, ShadowBuf sb) {
-  const int n = c->n_shadow;
-  uint32_t cn = 0, cl = 0;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+// (visible <=> closest hit in (1e-3, inf) is a Diffuse_Light); then resolve + Russian roulette
+struct ShadowPolicy {
+  const SceneDev& sc;
+  const Params& p;
+  Ctrl* c;
+  PathBuf next;
+  ShadowBuf sb;
+  __device__ __forceinline__ bool load(int i, float3& o, float3& d, float& tmin, float& tmax) const {
     float4 s0 = sb.s[0][i], s1 = sb.s[1][i];
-    float3 P = f3(s0.x, s0.y, s0.z);
-    TraceHit h;
-    bvh8_closest<COUNT>(sc, P, f3(s1.x, s1.y, s1.z), 1e-3f, PT_RAY_MAX, h, cn, cl);
+    o = f3(s0.x, s0.y, s0.z);
+    d = f3(s1.x, s1.y, s1.z);
+    tmin = 1e-3f;
+    tmax = PT_RAY_MAX;
+    return true;
+  }
+  __device__ __forceinline__ void emit(int i, const TraceHit& h, unsigned) const {
     bool visible = false;
-    if (h.leaf >= 0) {
-      uint32_t matw = __float_as_uint(__ldg(&sc.leaves[h.leaf].c.w));
-      visible = (matw >> 24) == PT_MAT_DIFFUSE_LIGHT;
-    }
-    float4 s2 = sb.s[2][i], s3 = sb.s[3][i], s4 = sb.s[4][i], s5 = sb.s[5][i], s6 = sb.s[6][i];
+    if (h.leaf >= 0) visible = (__float_as_uint(__ldg(&sc.leaves[h.leaf].c.w)) >> 24) == PT_MAT_DIFFUSE_LIGHT;
+    float4 s0 = sb.s[0][i], s1 = sb.s[1][i], s2 = sb.s[2][i], s3 = sb.s[3][i], s4 = sb.s[4][i], s5 = sb.s[5][i],
+           s6 = sb.s[6][i];
     uint32_t pk = __float_as_uint(s2.w);
     uint32_t pix = pk & 0x7fffffu;
     int depth = (pk >> 23) & 0xff;
@@ -267,8 +287,17 @@ __global__ void __launch_bounds__(128) k_shadow(SceneDev sc, Params p, Ctrl* c, 
       seed = __float_as_uint(s1.w);
     }
     if (terminal) accumulate(p, pix, rad);
-    else finish_bounce(p, c, next, pix, depth, P, dir, thr, rad, seed, false);
+    else finish_bounce(p, c, next, pix, depth, f3(s0.x, s0.y, s0.z), dir, thr, rad, seed, false);
   }
+};
+
+template <bool COUNT>
+__global__ void __launch_bounds__(PT_TRACE_THREADS) k_shadow(SceneDev sc, Params p, Ctrl* c, PathBuf next, ShadowBuf sb,
+                                                             SchedParams sched) {
+  __shared__ uint2 s_stack[PT_SMEM_STACK * PT_TRACE_THREADS];
+  ShadowPolicy pol{sc, p, c, next, sb};
+  uint32_t cn = 0, cl = 0;
+  trace_persistent<COUNT>(sc, c->n_shadow, &c->fetch_shadow, pol, s_stack, sched, cn, cl);
   if (COUNT) {
     for (int o = 16; o > 0; o >>= 1) {
       cn += __shfl_xor_sync(0xffffffffu, cn, o);
@@ -281,22 +310,20 @@ __global__ void __launch_bounds__(128) k_shadow(SceneDev sc, Params p, Ctrl* c, 
   }
 }
 
-// standalone traversal of a ray set (pt_trace_rays)
-template <bool COUNT>
-__global__ void __launch_bounds__(128) k_trace_rays(SceneDev sc, const pt_ray* rays, long long n, pt_hit* hits,
-                                                    unsigned long long* counters) {
-  uint32_t cn = 0, cl = 0;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+// standalone traversal of a ray set (pt_trace_rays); counters: [0] nodes, [1] leaves, [2] fetch cursor
+struct RaySetPolicy {
+  const pt_ray* rays;
+  pt_hit* hits;
+  __device__ __forceinline__ bool load(int i, float3& o, float3& d, float& tmin, float& tmax) const {
     const float4* rp = (const float4*)(rays + i);
     float4 a = __ldg(rp), b = __ldg(rp + 1);
-    TraceHit h;
-    if (b.w > a.w) {
-      bvh8_closest<COUNT>(sc, f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), a.w, b.w, h, cn, cl);
-    } else {
-      h.t = b.w;
-      h.prim = -1;
-      h.u = h.v = 0.f;
-    }
+    o = f3(a.x, a.y, a.z);
+    d = f3(b.x, b.y, b.z);
+    tmin = a.w;
+    tmax = b.w;
+    return b.w > a.w;
+  }
+  __device__ __forceinline__ void emit(int i, const TraceHit& h, unsigned) const {
     pt_hit o;
     o.t = h.t;
     o.prim = h.prim;
@@ -304,6 +331,15 @@ __global__ void __launch_bounds__(128) k_trace_rays(SceneDev sc, const pt_ray* r
     o.v = h.v;
     hits[i] = o;
   }
+};
+
+template <bool COUNT>
+__global__ void __launch_bounds__(PT_TRACE_THREADS) k_trace_rays(SceneDev sc, const pt_ray* rays, int n, pt_hit* hits,
+                                                                 unsigned long long* counters, SchedParams sched) {
+  __shared__ uint2 s_stack[PT_SMEM_STACK * PT_TRACE_THREADS];
+  RaySetPolicy pol{rays, hits};
+  uint32_t cn = 0, cl = 0;
+  trace_persistent<COUNT>(sc, n, (int*)(counters + 2), pol, s_stack, sched, cn, cl);
   if (COUNT) {
     for (int o = 16; o > 0; o >>= 1) {
       cn += __shfl_xor_sync(0xffffffffu, cn, o);
@@ -327,6 +363,30 @@ int sm_count() {
   return g_sm_count;
 }
 
+// scheduler knobs; PTB200_REFILL_MIN / PTB200_LEAF_THRESH override the tuned defaults (dev only)
+SchedParams sched_params() {
+  static SchedParams p = [] {
+    SchedParams q{12, 8};
+    if (const char* e = getenv("PTB200_REFILL_MIN")) q.refill_min = std::max(1, atoi(e));
+    if (const char* e = getenv("PTB200_LEAF_THRESH")) q.leaf_thresh = std::max(1, atoi(e));
+    return q;
+  }();
+  return p;
+}
+
+// resident CTAs per SM of the persistent traversal kernels (they must all be co-resident)
+int g_trace_bpm = 0;
+int trace_blocks_per_sm() {
+  if (!g_trace_bpm) {
+    int a = 0, b = 0, c = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_trace<false>, PT_TRACE_THREADS, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_shadow<false>, PT_TRACE_THREADS, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c, k_trace_rays<false>, PT_TRACE_THREADS, 0);
+    g_trace_bpm = std::max(1, std::min(a, std::min(b, c)));
+  }
+  return g_trace_bpm;
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
@@ -348,9 +408,10 @@ struct pt_renderer {
 
 static int ensure_pool(pt_renderer* r, long long want) {
   long long npix = (long long)r->W * r->H;
-  long long pool = r->pool_req > 0 ? r->pool_req : std::min<long long>(std::max<long long>(npix, 1 << 16), 1 << 22);
+  long long pool = r->pool_req > 0 ? r->pool_req : (1ll << 22);
   pool = std::min<long long>(pool, std::max<long long>(want, 1024));
-  pool = std::min<long long>(pool, 1 << 23);  // pix field is 23 bits wide; pool is independent but keep it bounded
+  (void)npix;
+  pool = std::min<long long>(pool, 1ll << 25);
   if (pool <= r->pool) return PT_OK;
   r->pool = (int)pool;
   for (int k = 0; k < 4; k++) {
@@ -478,8 +539,9 @@ int pt_render(pt_renderer* r, int32_t first_frame, int32_t nframes, int32_t max_
   const bool count = (r->flags & 1) != 0;
   const bool timing = (r->flags & 2) != 0;
   const int sms = sm_count();
-  const int g_trace = sms * 8, g_shade = sms * 8, g_gen = sms * 4;
+  const int g_trace = sms * trace_blocks_per_sm(), g_shade = sms * 8, g_gen = sms * 4;
   const uint32_t mask = s->material_type_mask;
+  const SchedParams sched = sched_params();
 
   cudaEvent_t e[6] = {};
   float ms_gen = 0, ms_trace = 0, ms_shade = 0, ms_shadow = 0;
@@ -497,8 +559,8 @@ int pt_render(pt_renderer* r, int32_t first_frame, int32_t nframes, int32_t max_
       if (timing) cudaEventRecord(e[0], st);
       k_generate<<<g_gen, 256, 0, st>>>(sc, p, c, A);
       if (timing) cudaEventRecord(e[1], st);
-      if (count) k_trace<true><<<g_trace, 128, 0, st>>>(sc, c, A, hits, bq, r->pool);
-      else k_trace<false><<<g_trace, 128, 0, st>>>(sc, c, A, hits, bq, r->pool);
+      if (count) k_trace<true><<<g_trace, PT_TRACE_THREADS, 0, st>>>(sc, c, A, hits, bq, r->pool, sched);
+      else k_trace<false><<<g_trace, PT_TRACE_THREADS, 0, st>>>(sc, c, A, hits, bq, r->pool, sched);
       if (timing) cudaEventRecord(e[2], st);
       launches += 3;
 #define LAUNCH_SHADE(M)                                                       \
@@ -520,8 +582,8 @@ int pt_render(pt_renderer* r, int32_t first_frame, int32_t nframes, int32_t max_
       launches++;
       if (mask & ((1u << PT_MAT_LAMBERTIAN) | (1u << PT_MAT_OREN_NAYAR) | (1u << PT_MAT_DIFFUSE_LIGHT))) {
         if (s->lights.size() > 0) {
-          if (count) k_shadow<true><<<g_trace, 128, 0, st>>>(sc, p, c, B, sb);
-          else k_shadow<false><<<g_trace, 128, 0, st>>>(sc, p, c, B, sb);
+          if (count) k_shadow<true><<<g_trace, PT_TRACE_THREADS, 0, st>>>(sc, p, c, B, sb, sched);
+          else k_shadow<false><<<g_trace, PT_TRACE_THREADS, 0, st>>>(sc, p, c, B, sb, sched);
           launches++;
         }
       }
@@ -598,9 +660,18 @@ int pt_trace_rays_device(pt_scene* scene, const void* d_rays, int64_t n, void* d
     return PT_ERR_STATE;
   }
   if (n <= 0) return PT_OK;
-  k_trace_rays<false><<<sm_count() * 8, 128, 0, (cudaStream_t)cuda_stream>>>(scene->dev, (const pt_ray*)d_rays, n,
-                                                                             (pt_hit*)d_hits, nullptr);
+  if (n > 0x7fffffff) {
+    pt_set_error("pt_trace_rays: at most 2^31-1 rays per call");
+    return PT_ERR_INVALID;
+  }
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  unsigned long long* dc = nullptr;
+  PT_CUDA(cudaMallocAsync((void**)&dc, 32, st));
+  PT_CUDA(cudaMemsetAsync(dc, 0, 32, st));
+  k_trace_rays<false><<<sm_count() * trace_blocks_per_sm(), PT_TRACE_THREADS, 0, st>>>(
+      scene->dev, (const pt_ray*)d_rays, (int)n, (pt_hit*)d_hits, dc, sched_params());
   PT_CUDA(cudaGetLastError());
+  PT_CUDA(cudaFreeAsync(dc, st));
   return PT_OK;
 }
 
@@ -611,17 +682,23 @@ int pt_trace_rays(pt_scene* scene, const pt_ray* rays, int64_t n, pt_hit* hits, 
   }
   if (n <= 0) return PT_OK;
   if (!rays || !hits) return PT_ERR_INVALID;
+  if (n > 0x7fffffff) {
+    pt_set_error("pt_trace_rays: at most 2^31-1 rays per call");
+    return PT_ERR_INVALID;
+  }
   DevBuf dr, dh, dc;
   PT_CUDA(dr.alloc((size_t)n * sizeof(pt_ray)));
   PT_CUDA(dh.alloc((size_t)n * sizeof(pt_hit)));
-  PT_CUDA(dc.alloc(16));
-  PT_CUDA(cudaMemset(dc.p, 0, 16));
+  PT_CUDA(dc.alloc(32));
+  PT_CUDA(cudaMemset(dc.p, 0, 32));
   PT_CUDA(cudaMemcpy(dr.p, rays, (size_t)n * sizeof(pt_ray), cudaMemcpyHostToDevice));
+  const int grid = sm_count() * trace_blocks_per_sm();
   if (counters)
-    k_trace_rays<true><<<sm_count() * 8, 128>>>(scene->dev, dr.as<pt_ray>(), n, dh.as<pt_hit>(),
-                                                dc.as<unsigned long long>());
+    k_trace_rays<true><<<grid, PT_TRACE_THREADS>>>(scene->dev, dr.as<pt_ray>(), (int)n, dh.as<pt_hit>(),
+                                                   dc.as<unsigned long long>(), sched_params());
   else
-    k_trace_rays<false><<<sm_count() * 8, 128>>>(scene->dev, dr.as<pt_ray>(), n, dh.as<pt_hit>(), nullptr);
+    k_trace_rays<false><<<grid, PT_TRACE_THREADS>>>(scene->dev, dr.as<pt_ray>(), (int)n, dh.as<pt_hit>(),
+                                                    dc.as<unsigned long long>(), sched_params());
   PT_CUDA(cudaGetLastError());
   PT_CUDA(cudaMemcpy(hits, dh.p, (size_t)n * sizeof(pt_hit), cudaMemcpyDeviceToHost));
   if (counters) PT_CUDA(cudaMemcpy(counters, dc.p, 16, cudaMemcpyDeviceToHost));

@@ -24,15 +24,29 @@ struct DevBuf {  // owning device allocation
   void* p = nullptr;
   size_t bytes = 0;
   ~DevBuf() { release(); }
+  // stream-ordered allocations from the device's default pool (kept warm: repeated scene
+  // commits reuse memory instead of paying cudaMalloc/cudaFree every time)
+  static void warm_pool() {
+    static bool done = false;
+    if (done) return;
+    done = true;
+    int dev = 0;
+    cudaMemPool_t pool;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+      unsigned long long keep = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+  }
   void release() {
-    if (p) cudaFree(p);
+    if (p) cudaFreeAsync(p, 0);
     p = nullptr;
     bytes = 0;
   }
   cudaError_t alloc(size_t n) {
     release();
+    warm_pool();
     if (n == 0) n = 16;
-    cudaError_t e = cudaMalloc(&p, n);
+    cudaError_t e = cudaMallocAsync(&p, n, 0);
     if (e == cudaSuccess) bytes = n;
     return e;
   }

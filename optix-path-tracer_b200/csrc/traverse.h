@@ -142,121 +142,155 @@ PT_HD uint32_t pt_sign_extend_s8x4(uint32_t v) {
 }
 PT_HD uint32_t pt_byte(uint32_t v, int i) { return (v >> (8 * i)) & 0xffu; }
 
-#define PT_STACK 40
+// exact float(byte j of w).  Device: one PRMT builds the float 2^23 + q, one FADD removes
+// the bias (I2F runs at 1/8 rate and dominated the node test in the round-1 profile).
+PT_HD float pt_byte_to_float(uint32_t w, int j) {
+#ifdef __CUDA_ARCH__
+  return __uint_as_float(__byte_perm(w, 0x4b000000u, 0x7440u | (uint32_t)j)) - 8388608.0f;
+#else
+  return (float)pt_byte(w, j);
+#endif
+}
 
-template <bool COUNT>
-PT_HD void bvh8_closest(const SceneDev& sc, float3 o, float3 d, float tmin, float tmax,
-                        TraceHit& hit, uint32_t& n_nodes, uint32_t& n_leaves) {
+struct RayCtx {
+  float3 o, d;
+  float idx, idy, idz;  // guarded reciprocal direction
+  float tmin, tmax;     // the ray's own interval (candidate selection)
+  uint32_t octinv;
+};
+
+PT_HD void ray_setup(RayCtx& r, float3 o, float3 d, float tmin, float tmax) {
+  const float ooeps = 8.2718061e-25f;  // 2^-80
+  r.o = o;
+  r.d = d;
+  r.tmin = tmin;
+  r.tmax = tmax;
+  r.idx = 1.0f / (fabsf(d.x) > ooeps ? d.x : copysignf(ooeps, d.x));
+  r.idy = 1.0f / (fabsf(d.y) > ooeps ? d.y : copysignf(ooeps, d.y));
+  r.idz = 1.0f / (fabsf(d.z) > ooeps ? d.z : copysignf(ooeps, d.z));
+  const uint32_t oct = (d.x < 0.f ? 4u : 0u) | (d.y < 0.f ? 2u : 0u) | (d.z < 0.f ? 1u : 0u);
+  r.octinv = 7u - oct;
+}
+
+PT_HD void hit_reset(TraceHit& hit, float tmax) {
   hit.t = tmax;
   hit.leaf = -1;
   hit.prim = -1;
   hit.u = hit.v = 0.f;
-  const float ray_tmax = tmax;  // candidate selection uses the ray's own interval
+}
 
-  const float ooeps = 8.2718061e-25f;  // 2^-80
-  float idx = 1.0f / (fabsf(d.x) > ooeps ? d.x : copysignf(ooeps, d.x));
-  float idy = 1.0f / (fabsf(d.y) > ooeps ? d.y : copysignf(ooeps, d.y));
-  float idz = 1.0f / (fabsf(d.z) > ooeps ? d.z : copysignf(ooeps, d.z));
-  const uint32_t oct = (d.x < 0.f ? 4u : 0u) | (d.y < 0.f ? 2u : 0u) | (d.z < 0.f ? 1u : 0u);
-  const uint32_t octinv = 7u - oct;
-  const uint32_t octinv4 = octinv * 0x01010101u;
+// Pops the nearest pending child of node group `ng` (which must have node bits), fetches that
+// node (5 x 128-bit), tests its 8 quantised child boxes against the ray clipped to [tmin, tbest]
+// and returns: `rest` = what is left of the popped-from group (push it if it still has node bits),
+// `ng` = hit inner children of the fetched node (octant-ordered priority bits 24..31 | imask),
+// `lg` = hit leaf slots of the fetched node (leaf base, bit per leaf record).
+PT_HD void bvh8_node_step(const SceneDev& sc, const RayCtx& r, float tbest, uint2& ng, uint2& lg, uint2& rest) {
+  const uint32_t bit = (uint32_t)pt_bfind(ng.y);
+  ng.y &= ~(1u << bit);
+  rest = ng;
+  const uint32_t imask_p = ng.y & 0xffu;
+  const uint32_t slot = (bit - 24u) ^ r.octinv;
+  const uint32_t rel = (uint32_t)pt_popc(imask_p & ~(0xffffffffu << slot));
+  const uint32_t ni = ng.x + rel;
 
+  const uint4* np = sc.nodes8 + (size_t)ni * 5;
+  const uint4 n0 = PT_LDG4(np + 0);
+  const uint4 n1 = PT_LDG4(np + 1);
+  const uint4 n2 = PT_LDG4(np + 2);
+  const uint4 n3 = PT_LDG4(np + 3);
+  const uint4 n4 = PT_LDG4(np + 4);
+
+  const float sx = pt_u2f((n0.w & 0xffu) << 23) * r.idx;
+  const float sy = pt_u2f(((n0.w >> 8) & 0xffu) << 23) * r.idy;
+  const float sz = pt_u2f(((n0.w >> 16) & 0xffu) << 23) * r.idz;
+  const float bx = (pt_u2f(n0.x) - r.o.x) * r.idx;
+  const float by = (pt_u2f(n0.y) - r.o.y) * r.idy;
+  const float bz = (pt_u2f(n0.z) - r.o.z) * r.idz;
+  const uint32_t octinv4 = r.octinv * 0x01010101u;
+
+  uint32_t hitmask = 0;
+#pragma unroll
+  for (int h = 0; h < 2; h++) {
+    const uint32_t meta4 = h ? n1.w : n1.z;
+    const uint32_t is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
+    const uint32_t inner_mask4 = pt_sign_extend_s8x4(is_inner4 << 3);
+    const uint32_t bit_index4 = (meta4 ^ (octinv4 & inner_mask4)) & 0x1f1f1f1fu;
+    const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
+    const uint32_t qlox = h ? n2.y : n2.x, qloy = h ? n2.w : n2.z, qloz = h ? n3.y : n3.x;
+    const uint32_t qhix = h ? n3.w : n3.z, qhiy = h ? n4.y : n4.x, qhiz = h ? n4.w : n4.z;
+    const uint32_t nx = r.idx < 0.f ? qhix : qlox, fx = r.idx < 0.f ? qlox : qhix;
+    const uint32_t ny = r.idy < 0.f ? qhiy : qloy, fy = r.idy < 0.f ? qloy : qhiy;
+    const uint32_t nz = r.idz < 0.f ? qhiz : qloz, fz = r.idz < 0.f ? qloz : qhiz;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const float t0x = XFMA(pt_byte_to_float(nx, j), sx, bx);
+      const float t0y = XFMA(pt_byte_to_float(ny, j), sy, by);
+      const float t0z = XFMA(pt_byte_to_float(nz, j), sz, bz);
+      const float t1x = XFMA(pt_byte_to_float(fx, j), sx, bx);
+      const float t1y = XFMA(pt_byte_to_float(fy, j), sy, by);
+      const float t1z = XFMA(pt_byte_to_float(fz, j), sz, bz);
+      const float cmin = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, r.tmin));
+      const float cmax = fminf(fminf(t1x, t1y), fminf(t1z, tbest));
+      if (cmin <= cmax) hitmask |= pt_byte(child_bits4, j) << pt_byte(bit_index4, j);
+    }
+  }
+  ng.x = n1.x;
+  ng.y = (hitmask & 0xff000000u) | (n0.w >> 24);
+  lg.x = n1.y;
+  lg.y = hitmask & 0x00ffffffu;
+}
+
+// Tests ONE pending leaf record of `lg` (highest bit) and updates the closest hit.
+PT_HD void bvh8_leaf_step(const SceneDev& sc, const RayCtx& r, uint2& lg, TraceHit& hit) {
+  const uint32_t b = (uint32_t)pt_bfind(lg.y);
+  lg.y &= ~(1u << b);
+  const uint32_t li = lg.x + b;
+  const float4* lp = (const float4*)(sc.leaves + li);
+  LeafRec L;
+  L.a = PT_LDGF4(lp + 0);
+  L.b = PT_LDGF4(lp + 1);
+  L.c = PT_LDGF4(lp + 2);
+  float t, u, v;
+  if (isect_leaf(sc, L, r.o, r.d, r.tmin, r.tmax, t, u, v)) {
+    const int prim = (int)pt_f2u(L.a.w);
+    if (t < hit.t || (t == hit.t && (hit.prim < 0 || prim < hit.prim))) {
+      hit.t = t;
+      hit.leaf = (int)li;
+      hit.prim = prim;
+      hit.u = u;
+      hit.v = v;
+    }
+  }
+}
+
+#define PT_STACK 48
+
+// Straightforward single-ray loop over the step functions (host simulation, reference for the
+// warp-scheduled GPU driver in trace_sched.cuh).
+template <bool COUNT>
+PT_HD void bvh8_closest(const SceneDev& sc, float3 o, float3 d, float tmin, float tmax,
+                        TraceHit& hit, uint32_t& n_nodes, uint32_t& n_leaves) {
+  RayCtx r;
+  ray_setup(r, o, d, tmin, tmax);
+  hit_reset(hit, tmax);
   uint2 stack[PT_STACK];
   int sp = 0;
-  uint2 ngroup = make_uint2(0u, 0x80000000u);  // root
-  uint2 lgroup = make_uint2(0u, 0u);
-
+  uint2 ng = make_uint2(0u, 0x80000000u);  // root
+  uint2 lg = make_uint2(0u, 0u);
   for (;;) {
-    if (ngroup.y & 0xff000000u) {
-      // pop the nearest child (highest priority bit) of the current node group
-      const uint32_t bit = (uint32_t)pt_bfind(ngroup.y);
-      ngroup.y &= ~(1u << bit);
-      const uint32_t base = ngroup.x;
-      const uint32_t imask = ngroup.y & 0xffu;
-      if (ngroup.y & 0xff000000u) {
-        if (sp < PT_STACK) stack[sp++] = ngroup;
-      }
-      const uint32_t slot = (bit - 24u) ^ octinv;
-      const uint32_t rel = (uint32_t)pt_popc(imask & ~(0xffffffffu << slot));
-      const uint32_t ni = base + rel;
-
-      const uint4* np = sc.nodes8 + (size_t)ni * 5;
-      const uint4 n0 = PT_LDG4(np + 0);
-      const uint4 n1 = PT_LDG4(np + 1);
-      const uint4 n2 = PT_LDG4(np + 2);
-      const uint4 n3 = PT_LDG4(np + 3);
-      const uint4 n4 = PT_LDG4(np + 4);
+    if (ng.y & 0xff000000u) {
+      uint2 rest;
+      bvh8_node_step(sc, r, hit.t, ng, lg, rest);
       if (COUNT) n_nodes++;
-
-      const float px = pt_u2f(n0.x), py = pt_u2f(n0.y), pz = pt_u2f(n0.z);
-      const float sx = pt_u2f((n0.w & 0xffu) << 23) * idx;
-      const float sy = pt_u2f(((n0.w >> 8) & 0xffu) << 23) * idy;
-      const float sz = pt_u2f(((n0.w >> 16) & 0xffu) << 23) * idz;
-      const float bx = (px - o.x) * idx, by = (py - o.y) * idy, bz = (pz - o.z) * idz;
-
-      uint32_t hitmask = 0;
-#pragma unroll
-      for (int h = 0; h < 2; h++) {
-        const uint32_t meta4 = h ? n1.w : n1.z;
-        const uint32_t is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
-        const uint32_t inner_mask4 = pt_sign_extend_s8x4(is_inner4 << 3);
-        const uint32_t bit_index4 = (meta4 ^ (octinv4 & inner_mask4)) & 0x1f1f1f1fu;
-        const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
-        const uint32_t qlox = h ? n2.y : n2.x, qloy = h ? n2.w : n2.z, qloz = h ? n3.y : n3.x;
-        const uint32_t qhix = h ? n3.w : n3.z, qhiy = h ? n4.y : n4.x, qhiz = h ? n4.w : n4.z;
-        const uint32_t nx = idx < 0.f ? qhix : qlox, fx = idx < 0.f ? qlox : qhix;
-        const uint32_t ny = idy < 0.f ? qhiy : qloy, fy = idy < 0.f ? qloy : qhiy;
-        const uint32_t nz = idz < 0.f ? qhiz : qloz, fz = idz < 0.f ? qloz : qhiz;
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-          const float t0x = XFMA((float)pt_byte(nx, j), sx, bx);
-          const float t0y = XFMA((float)pt_byte(ny, j), sy, by);
-          const float t0z = XFMA((float)pt_byte(nz, j), sz, bz);
-          const float t1x = XFMA((float)pt_byte(fx, j), sx, bx);
-          const float t1y = XFMA((float)pt_byte(fy, j), sy, by);
-          const float t1z = XFMA((float)pt_byte(fz, j), sz, bz);
-          const float cmin = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, tmin));
-          const float cmax = fminf(fminf(t1x, t1y), fminf(t1z, hit.t));
-          if (cmin <= cmax) {
-            hitmask |= pt_byte(child_bits4, j) << pt_byte(bit_index4, j);
-          }
-        }
-      }
-      ngroup.x = n1.x;
-      ngroup.y = (hitmask & 0xff000000u) | (n0.w >> 24);
-      lgroup.x = n1.y;
-      lgroup.y = hitmask & 0x00ffffffu;
-    } else {
-      lgroup = ngroup;
-      ngroup = make_uint2(0u, 0u);
+      if ((rest.y & 0xff000000u) && sp < PT_STACK) stack[sp++] = rest;
     }
-
-    while (lgroup.y) {
-      const uint32_t b = (uint32_t)pt_bfind(lgroup.y);
-      lgroup.y &= ~(1u << b);
-      const uint32_t li = lgroup.x + b;
-      const float4* lp = (const float4*)(sc.leaves + li);
-      LeafRec L;
-      L.a = PT_LDGF4(lp + 0);
-      L.b = PT_LDGF4(lp + 1);
-      L.c = PT_LDGF4(lp + 2);
+    while (lg.y) {
+      bvh8_leaf_step(sc, r, lg, hit);
       if (COUNT) n_leaves++;
-      float t, u, v;
-      if (isect_leaf(sc, L, o, d, tmin, ray_tmax, t, u, v)) {
-        const int prim = (int)pt_f2u(L.a.w);
-        if (t < hit.t || (t == hit.t && (hit.prim < 0 || prim < hit.prim))) {
-          hit.t = t;
-          hit.leaf = (int)li;
-          hit.prim = prim;
-          hit.u = u;
-          hit.v = v;
-        }
-      }
     }
-
-    if ((ngroup.y & 0xff000000u) == 0) {
+    if ((ng.y & 0xff000000u) == 0) {
       if (sp == 0) break;
-      ngroup = stack[--sp];
+      ng = stack[--sp];
     }
   }
 }

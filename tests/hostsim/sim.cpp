@@ -56,6 +56,7 @@ Sim* sim_create(const pt_scene_desc* desc, int refine) {
   in.n = n;
   std::vector<float4> plo(n), phi(n);
   float3 cmin = f3(INFINITY), cmax = f3(-INFINITY);
+  float S = 0.f;
   for (int i = 0; i < n; i++) {
     float3 lo, hi;
     prim_bounds(in, i, lo, hi);
@@ -64,6 +65,13 @@ Sim* sim_create(const pt_scene_desc* desc, int refine) {
     float3 c = (lo + hi) * 0.5f;
     cmin = fmin3(cmin, c);
     cmax = fmax3(cmax, c);
+    S = fmaxf(S, fmaxf(fmaxf(fmaxf(fabsf(lo.x), fabsf(lo.y)), fabsf(lo.z)), fmaxf(fmaxf(fabsf(hi.x), fabsf(hi.y)), fabsf(hi.z))));
+  }
+  for (int i = 0; i < n; i++) {
+    float3 lo = xyz(plo[i]), hi = xyz(phi[i]);
+    pad_bounds(lo, hi, S);
+    plo[i] = make_float4(lo.x, lo.y, lo.z, 0.f);
+    phi[i] = make_float4(hi.x, hi.y, hi.z, 0.f);
   }
   float3 ext = cmax - cmin;
   float3 sinv = f3(ext.x > 0 ? 1.f / ext.x : 0.f, ext.y > 0 ? 1.f / ext.y : 0.f, ext.z > 0 ? 1.f / ext.z : 0.f);
