@@ -46,7 +46,7 @@ def build_scene(h, name, W, H, lib=None):
     """Scenes come from the C++ host facade's scene functions (InOneWeekend, Cornell, ... — the
     reference's scene-building surface); the numpy builders are the fallback if it is not built."""
     pt = h.pt
-    if os.path.exists(pt.HOST_LIB_PATH):
+    if os.path.exists(pt.HOST_LIB_PATH) and not os.environ.get("PTB200_NO_FACADE"):
         import facade_dump
         return facade_dump.build(pt.HOST_LIB_PATH, FACADE_IDS[name], W, H, 0)
     if name == "c1":

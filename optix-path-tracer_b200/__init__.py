@@ -156,7 +156,7 @@ def load(path: Optional[str] = None) -> C.CDLL:
     global _lib
     if _lib is not None and path is None:
         return _lib
-    p = path or LIB_PATH
+    p = path or os.environ.get("PTB200_LIB") or LIB_PATH   # PTB200_LIB: dev override (kernel variants)
     if not os.path.exists(p):
         raise PtError(f"CUDA library not built: {p} (run `python -c 'import __graft_entry__ as g; "
                       f"g.build()'` or `make -C optix-path-tracer_b200/csrc`)")

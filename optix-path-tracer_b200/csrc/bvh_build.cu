@@ -121,14 +121,14 @@ __global__ void k_refit(Bvh2 t) {
   }
 }
 
-__global__ void k_treelet_mark(Bvh2 t, int* roots, int* n_roots) {
+__global__ void k_treelet_mark(Bvh2 t, int lo, long long hi, int* roots, int* n_roots) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= t.n - 1) return;
-  if (treelet_is_root(t, i)) roots[atomicAdd(n_roots, 1)] = i;
+  if (treelet_is_root(t, i, lo, hi)) roots[atomicAdd(n_roots, 1)] = i;
 }
-__global__ void k_treelet_sah(Bvh2 t, const int* roots, int n_roots) {
+__global__ void k_treelet_sah(Bvh2 t, int lo, const int* roots, int n_roots) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n_roots) treelet_sah(t, roots[i]);
+  if (i < n_roots) treelet_sah(t, roots[i], lo);
 }
 
 // SAH cost: sum of inner-node areas (C_trav = 1) + leaf areas (C_isect = 1), over root area
@@ -276,14 +276,20 @@ int pt_bvh_build(pt_scene* s) {
     k_sah_cost<<<nblk(n - 1), TB>>>(t, cost.as<double>());
     // treelet refinement
     PT_CUDA(roots.alloc((size_t)ni * 4));
-    PT_CUDA(cudaMemset(counters.p, 0, 64));
-    k_treelet_mark<<<nblk(n - 1), TB>>>(t, roots.as<int>(), counters.as<int>());
-    PT_CUDA(cudaGetLastError());
-    int n_roots = 0;
-    PT_CUDA(cudaMemcpy(&n_roots, counters.p, 4, cudaMemcpyDeviceToHost));
-    if (n_roots > 0) {
-      k_treelet_sah<<<nblk(n_roots, 64), 64>>>(t, roots.as<int>(), n_roots);
+    // hierarchical passes: leaves -> treelets of <= 64 leaves -> treelets of <= 64 treelets -> ...
+    long long lo = 1, hi = PT_TREELET;
+    for (int pass = 0; pass < 8 && lo < (long long)n; pass++) {
+      PT_CUDA(cudaMemset(counters.p, 0, 64));
+      k_treelet_mark<<<nblk(n - 1), TB>>>(t, (int)lo, hi, roots.as<int>(), counters.as<int>());
       PT_CUDA(cudaGetLastError());
+      int n_roots = 0;
+      PT_CUDA(cudaMemcpy(&n_roots, counters.p, 4, cudaMemcpyDeviceToHost));
+      if (n_roots > 0) {
+        k_treelet_sah<<<nblk(n_roots, 64), 64>>>(t, (int)lo, roots.as<int>(), n_roots);
+        PT_CUDA(cudaGetLastError());
+      }
+      lo = hi;
+      hi *= PT_TREELET;
     }
     tm.mark("treelet sah");
     k_sah_cost<<<nblk(n - 1), TB>>>(t, cost.as<double>() + 1);

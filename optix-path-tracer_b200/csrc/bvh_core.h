@@ -180,56 +180,72 @@ PT_HD float box_half_area(float3 lo, float3 hi) {
   return e.x * e.y + e.y * e.z + e.z * e.x;
 }
 
-// ---- 5: binned-SAH treelet rebuild -----------------------------------------------------
-// One thread rebuilds the subtree rooted at inner node r (<= PT_TREELET leaves)
-// top-down with binned SAH over the leaves' AABB centres, reusing the subtree's
-// own inner-node slots.  Boxes and counts are written as part of the rebuild.
-PT_HD bool treelet_is_root(const Bvh2& t, int r) {
-  int c = t.count[r];
-  if (c < 3 || c > PT_TREELET) return false;
-  int p = t.parent[r];
-  return p < 0 || t.count[p] > PT_TREELET;
+// ---- 5: hierarchical binned-SAH treelet rebuild ------------------------------------------
+// Pass k (k = 1,2,..) uses thresholds lo_k = PT_TREELET^(k-1), hi_k = PT_TREELET^k on the leaf
+// count.  A node r is a pass-k root when count[r] <= hi_k < count[parent] (or r is the tree
+// root).  One thread rebuilds the part of r's subtree ABOVE the pass-(k-1) roots: it expands r
+// downwards (largest leaf count first) until every item has count <= lo_k or PT_TREELET items
+// are collected, then rebuilds a binary tree over those items top-down with binned SAH (cost =
+// half-area x leaf count), reusing exactly the inner-node slots it expanded.  Pass 1 therefore
+// rebuilds all subtrees of <= PT_TREELET leaves down to the leaves (they are contiguous in Morton
+// order); later passes fix the upper levels that plain LBVH leaves in Morton order.
+PT_HD bool treelet_is_root(const Bvh2& t, int r, int lo, long long hi) {
+  const int c = t.count[r];
+  if (c < 3 || c <= lo || (long long)c > hi) return false;
+  const int p = t.parent[r];
+  return p < 0 || (long long)t.count[p] > hi;
 }
 
-PT_HD void treelet_sah(const Bvh2& t, int r) {
-  int items[PT_TREELET];      // sorted leaf positions
-  int slots[PT_TREELET];      // inner node indices owned by this subtree
+PT_HD void treelet_sah(const Bvh2& t, int r, int lo_count) {
+  int items[PT_TREELET];  // child refs: >= 0 inner node, < 0 sorted leaf ~ref
+  int icnt[PT_TREELET];   // leaves below each item
+  int slots[PT_TREELET];  // inner nodes expanded (owned by this treelet)
   int m = 0, ns = 0;
-  {
-    int st[PT_TREELET];
-    int sp = 0;
-    st[sp++] = r;
-    while (sp) {
-      int nd = st[--sp];
-      slots[ns++] = nd;
-      int l = t.nodes[nd].left, rr = t.nodes[nd].right;
-      if (rr >= 0) st[sp++] = rr; else items[m++] = ~rr;
-      if (l >= 0) st[sp++] = l; else items[m++] = ~l;
-    }
+  items[0] = r;
+  icnt[0] = t.count[r];
+  m = 1;
+  while (m < PT_TREELET) {  // expand the item with the most leaves that is still above the cut
+    int bi = -1, bc = lo_count;
+    for (int i = 0; i < m; i++)
+      if (items[i] >= 0 && icnt[i] > bc) {
+        bc = icnt[i];
+        bi = i;
+      }
+    if (bi < 0) break;
+    const int nd = items[bi];
+    slots[ns++] = nd;
+    const int l = t.nodes[nd].left, rr = t.nodes[nd].right;
+    items[bi] = l;
+    icnt[bi] = l >= 0 ? t.count[l] : 1;
+    items[m] = rr;
+    icnt[m] = rr >= 0 ? t.count[rr] : 1;
+    m++;
   }
-  // work stack of ranges: node slot, [lo,hi)
+  if (ns == 0) return;
+  // slots[0] == r: the treelet root keeps its index (its parent points at it)
   int wnode[PT_TREELET], wlo[PT_TREELET], whi[PT_TREELET];
-  int wp = 0, next_slot = 1;
+  int wp = 1, next_slot = 1;
   wnode[0] = slots[0];
   wlo[0] = 0;
   whi[0] = m;
-  wp = 1;
   while (wp) {
     --wp;
     const int node = wnode[wp], lo = wlo[wp], hi = whi[wp];
-    // bounds of the range + centroid bounds
     float3 blo = f3(INFINITY), bhi = f3(-INFINITY), clo = blo, chi = bhi;
+    int total = 0;
     for (int i = lo; i < hi; i++) {
-      uint32_t id = t.sorted[items[i]];
-      float3 a = xyz(t.plo[id]), b = xyz(t.phi[id]);
+      float3 a, b;
+      int c;
+      bvh2_child_box(t, items[i], a, b, c);
       blo = fmin3(blo, a);
       bhi = fmax3(bhi, b);
-      float3 c = (a + b) * 0.5f;
-      clo = fmin3(clo, c);
-      chi = fmax3(chi, c);
+      float3 ce = (a + b) * 0.5f;
+      clo = fmin3(clo, ce);
+      chi = fmax3(chi, ce);
+      total += icnt[i];
     }
     bvh2_set_box(t.nodes[node], blo, bhi);
-    t.count[node] = hi - lo;
+    t.count[node] = total;
     int mid = -1;
     if (hi - lo > 2) {
       float best = INFINITY;
@@ -239,46 +255,53 @@ PT_HD void treelet_sah(const Bvh2& t, int r) {
         if (!(cmax > cmin)) continue;
         float scale = (float)PT_SAH_BINS / (cmax - cmin);
         float3 binlo[PT_SAH_BINS], binhi[PT_SAH_BINS];
-        int bincnt[PT_SAH_BINS];
-        for (int b = 0; b < PT_SAH_BINS; b++) {
-          binlo[b] = f3(INFINITY);
-          binhi[b] = f3(-INFINITY);
-          bincnt[b] = 0;
+        int bincnt[PT_SAH_BINS], binitems[PT_SAH_BINS];
+        for (int bq = 0; bq < PT_SAH_BINS; bq++) {
+          binlo[bq] = f3(INFINITY);
+          binhi[bq] = f3(-INFINITY);
+          bincnt[bq] = 0;
+          binitems[bq] = 0;
         }
         for (int i = lo; i < hi; i++) {
-          uint32_t id = t.sorted[items[i]];
-          float3 a = xyz(t.plo[id]), b = xyz(t.phi[id]);
-          float c = (comp(a, ax) + comp(b, ax)) * 0.5f;
-          int bi = (int)((c - cmin) * scale);
+          float3 a, b;
+          int c;
+          bvh2_child_box(t, items[i], a, b, c);
+          float ce = (comp(a, ax) + comp(b, ax)) * 0.5f;
+          int bi = (int)((ce - cmin) * scale);
           bi = bi < 0 ? 0 : (bi > PT_SAH_BINS - 1 ? PT_SAH_BINS - 1 : bi);
           binlo[bi] = fmin3(binlo[bi], a);
           binhi[bi] = fmax3(binhi[bi], b);
-          bincnt[bi]++;
+          bincnt[bi] += icnt[i];
+          binitems[bi]++;
         }
         float rarea[PT_SAH_BINS];
-        int rcnt[PT_SAH_BINS];
+        int rcnt[PT_SAH_BINS], ritems[PT_SAH_BINS];
         float3 alo = f3(INFINITY), ahi = f3(-INFINITY);
-        int c = 0;
-        for (int b = PT_SAH_BINS - 1; b > 0; b--) {
-          alo = fmin3(alo, binlo[b]);
-          ahi = fmax3(ahi, binhi[b]);
-          c += bincnt[b];
-          rarea[b] = c ? box_half_area(alo, ahi) : 0.f;
-          rcnt[b] = c;
+        int c = 0, ci = 0;
+        for (int bq = PT_SAH_BINS - 1; bq > 0; bq--) {
+          alo = fmin3(alo, binlo[bq]);
+          ahi = fmax3(ahi, binhi[bq]);
+          c += bincnt[bq];
+          ci += binitems[bq];
+          rarea[bq] = ci ? box_half_area(alo, ahi) : 0.f;
+          rcnt[bq] = c;
+          ritems[bq] = ci;
         }
         alo = f3(INFINITY);
         ahi = f3(-INFINITY);
         c = 0;
-        for (int b = 0; b < PT_SAH_BINS - 1; b++) {
-          alo = fmin3(alo, binlo[b]);
-          ahi = fmax3(ahi, binhi[b]);
-          c += bincnt[b];
-          if (c == 0 || rcnt[b + 1] == 0) continue;
-          float cost = box_half_area(alo, ahi) * (float)c + rarea[b + 1] * (float)rcnt[b + 1];
+        ci = 0;
+        for (int bq = 0; bq < PT_SAH_BINS - 1; bq++) {
+          alo = fmin3(alo, binlo[bq]);
+          ahi = fmax3(ahi, binhi[bq]);
+          c += bincnt[bq];
+          ci += binitems[bq];
+          if (ci == 0 || ritems[bq + 1] == 0) continue;
+          float cost = box_half_area(alo, ahi) * (float)c + rarea[bq + 1] * (float)rcnt[bq + 1];
           if (cost < best) {
             best = cost;
             bestAxis = ax;
-            bestBin = b;
+            bestBin = bq;
           }
         }
       }
@@ -287,29 +310,31 @@ PT_HD void treelet_sah(const Bvh2& t, int r) {
         float scale = (float)PT_SAH_BINS / (cmax - cmin);
         int i = lo, j = hi - 1;
         while (i <= j) {
-          uint32_t id = t.sorted[items[i]];
-          float c = (comp(xyz(t.plo[id]), bestAxis) + comp(xyz(t.phi[id]), bestAxis)) * 0.5f;
-          int bi = (int)((c - cmin) * scale);
+          float3 a, b;
+          int c;
+          bvh2_child_box(t, items[i], a, b, c);
+          float ce = (comp(a, bestAxis) + comp(b, bestAxis)) * 0.5f;
+          int bi = (int)((ce - cmin) * scale);
           bi = bi < 0 ? 0 : (bi > PT_SAH_BINS - 1 ? PT_SAH_BINS - 1 : bi);
           if (bi <= bestBin) {
             i++;
           } else {
-            int tmp = items[i];
-            items[i] = items[j];
-            items[j] = tmp;
+            int tmp = items[i]; items[i] = items[j]; items[j] = tmp;
+            tmp = icnt[i]; icnt[i] = icnt[j]; icnt[j] = tmp;
             j--;
           }
         }
         mid = i;
       }
     }
-    if (mid <= lo || mid >= hi) mid = (lo + hi) >> 1;  // degenerate: keep Morton order, halve
+    if (mid <= lo || mid >= hi) mid = (lo + hi) >> 1;  // degenerate: keep the current order, halve
     int refs[2];
     for (int side = 0; side < 2; side++) {
       int a = side ? mid : lo, b = side ? hi : mid;
       if (b - a == 1) {
-        refs[side] = ~items[a];
-        t.leaf_parent[items[a]] = node;
+        refs[side] = items[a];
+        if (items[a] >= 0) t.parent[items[a]] = node;
+        else t.leaf_parent[~items[a]] = node;
       } else {
         int child = slots[next_slot++];
         refs[side] = child;
@@ -426,14 +451,36 @@ PT_HD void collapse_node(const Collapse& c, int ref, int dst, uint2* out_work, i
       n++;
     }
   }
-  // node frame
+  // node frame.  Child planes are quantised to 8 bits relative to (p, 2^e) per axis with a guard
+  // band of G grid steps (covers the <= 2^-10-step rounding of the biased FMA in the box test,
+  // traverse.h) and the origin is placed 1/64 step below the node minimum so the low side never
+  // clamps: decoded boxes always contain the true boxes.
   float3 nlo = clo[0], nhi = chi[0];
   for (int i = 1; i < n; i++) {
     nlo = fmin3(nlo, clo[i]);
     nhi = fmax3(nhi, chi[i]);
   }
-  const uint32_t ex = quant_exp(nhi.x - nlo.x), ey = quant_exp(nhi.y - nlo.y), ez = quant_exp(nhi.z - nlo.z);
-  const float sx = pt_u2f(ex << 23), sy = pt_u2f(ey << 23), sz = pt_u2f(ez << 23);
+  const float G = 1.0f / 256.0f;
+  uint32_t eb[3];
+  float sc3[3], p3[3];
+  for (int a = 0; a < 3; a++) {
+    const float lo_a = comp(nlo, a), hi_a = comp(nhi, a);
+    uint32_t e = quant_exp(hi_a - lo_a);
+    for (;;) {
+      const float sca = pt_u2f(e << 23);
+      const float pa = lo_a - sca * (1.0f / 64.0f);
+      if (e >= 254 || ceilf((hi_a - pa) / sca + G) <= 255.0f) {
+        sc3[a] = sca;
+        p3[a] = pa;
+        break;
+      }
+      e++;
+    }
+    eb[a] = e;
+  }
+  const uint32_t ex = eb[0], ey = eb[1], ez = eb[2];
+  const float sx = sc3[0], sy = sc3[1], sz = sc3[2];
+  const float3 porg = f3(p3[0], p3[1], p3[2]);
   // octant slot assignment (greedy max of dot(child centre - node centre, slot dir))
   int slot_of[8], child_in[8];
   for (int i = 0; i < 8; i++) {
@@ -479,12 +526,12 @@ PT_HD void collapse_node(const Collapse& c, int ref, int dst, uint2* out_work, i
     const int i = child_in[s];
     if (i < 0) continue;
     float q;
-    q = floorf((clo[i].x - nlo.x) / sx); qlo[0][s] = (uint32_t)fminf(fmaxf(q, 0.f), 255.f);
-    q = floorf((clo[i].y - nlo.y) / sy); qlo[1][s] = (uint32_t)fminf(fmaxf(q, 0.f), 255.f);
-    q = floorf((clo[i].z - nlo.z) / sz); qlo[2][s] = (uint32_t)fminf(fmaxf(q, 0.f), 255.f);
-    q = ceilf((chi[i].x - nlo.x) / sx); qhi[0][s] = (uint32_t)fminf(fmaxf(q, 0.f), 255.f);
-    q = ceilf((chi[i].y - nlo.y) / sy); qhi[1][s] = (uint32_t)fminf(fmaxf(q, 0.f), 255.f);
-    q = ceilf((chi[i].z - nlo.z) / sz); qhi[2][s] = (uint32_t)fminf(fmaxf(q, 0.f), 255.f);
+    q = floorf((clo[i].x - porg.x) / sx - G); qlo[0][s] = (uint32_t)fminf(fmaxf(q, 0.f), 255.f);
+    q = floorf((clo[i].y - porg.y) / sy - G); qlo[1][s] = (uint32_t)fminf(fmaxf(q, 0.f), 255.f);
+    q = floorf((clo[i].z - porg.z) / sz - G); qlo[2][s] = (uint32_t)fminf(fmaxf(q, 0.f), 255.f);
+    q = ceilf((chi[i].x - porg.x) / sx + G); qhi[0][s] = (uint32_t)fminf(fmaxf(q, 0.f), 255.f);
+    q = ceilf((chi[i].y - porg.y) / sy + G); qhi[1][s] = (uint32_t)fminf(fmaxf(q, 0.f), 255.f);
+    q = ceilf((chi[i].z - porg.z) / sz + G); qhi[2][s] = (uint32_t)fminf(fmaxf(q, 0.f), 255.f);
     if (cref[i] >= 0 && ccnt[i] > 3) {
       meta[s] = (1u << 5) | (24u + (uint32_t)s);
       imask |= 1u << s;
@@ -515,7 +562,7 @@ PT_HD void collapse_node(const Collapse& c, int ref, int dst, uint2* out_work, i
   }
   auto pack4 = [](const uint32_t* v) { return v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24); };
   uint4* out = c.nodes8 + (size_t)dst * 5;
-  out[0] = make_uint4(pt_f2u(nlo.x), pt_f2u(nlo.y), pt_f2u(nlo.z), ex | (ey << 8) | (ez << 16) | (imask << 24));
+  out[0] = make_uint4(pt_f2u(porg.x), pt_f2u(porg.y), pt_f2u(porg.z), ex | (ey << 8) | (ez << 16) | (imask << 24));
   out[1] = make_uint4((uint32_t)child_base, (uint32_t)leaf_base, pack4(meta), pack4(meta + 4));
   out[2] = make_uint4(pack4(qlo[0]), pack4(qlo[0] + 4), pack4(qlo[1]), pack4(qlo[1] + 4));
   out[3] = make_uint4(pack4(qlo[2]), pack4(qlo[2] + 4), pack4(qhi[0]), pack4(qhi[0] + 4));

@@ -196,8 +196,11 @@ __global__ void __launch_bounds__(PT_TRACE_THREADS) k_trace(SceneDev sc, Ctrl* c
   }
 }
 
+#ifndef PT_SHADE_MINBLOCKS
+#define PT_SHADE_MINBLOCKS 8
+#endif
 template <int MAT>
-__global__ void __launch_bounds__(128) k_shade(SceneDev sc, Params p, Ctrl* c, PathBuf cur, PathBuf next, ShadowBuf sb,
+__global__ void __launch_bounds__(128, PT_SHADE_MINBLOCKS) k_shade(SceneDev sc, Params p, Ctrl* c, PathBuf cur, PathBuf next, ShadowBuf sb,
                                                const float4* hits, const uint32_t* bin_q) {
   const int n = c->bin_count[MAT];
   const uint32_t* q = bin_q + (size_t)MAT * p.pool;
@@ -552,9 +555,12 @@ int pt_render(pt_renderer* r, int32_t first_frame, int32_t nframes, int32_t max_
   unsigned long long launches = 0;
   bool done = false;
   long long iter = 0;
-  const int poll_every = 4;
+  // Completion is detected by polling the device control block.  While more than a pool-full of
+  // samples is still ungenerated, at least remaining/pool further iterations are certain, so the
+  // host keeps launching without synchronising; near the end it polls every 4 iterations.
+  long long poll_every = std::max<long long>(4, total / std::max(1, r->pool));
   while (!done) {
-    for (int k = 0; k < poll_every; k++, iter++) {
+    for (long long k = 0; k < poll_every; k++, iter++) {
       k_iter_begin<<<1, 1, 0, st>>>(c, r->pool);
       if (timing) cudaEventRecord(e[0], st);
       k_generate<<<g_gen, 256, 0, st>>>(sc, p, c, A);
@@ -602,6 +608,7 @@ int pt_render(pt_renderer* r, int32_t first_frame, int32_t nframes, int32_t max_
     PT_CUDA(cudaMemcpyAsync(r->h_ctrl, c, sizeof(Ctrl), cudaMemcpyDeviceToHost, st));
     PT_CUDA(cudaStreamSynchronize(st));
     done = r->h_ctrl->next_sample >= r->h_ctrl->total_samples && r->h_ctrl->n_next == 0;
+    poll_every = std::max<long long>(4, (long long)((r->h_ctrl->total_samples - r->h_ctrl->next_sample) / (unsigned)std::max(1, r->pool)));
     if (iter > 100000000ll) {
       pt_set_error("pt_render: did not converge");
       return PT_ERR_INVALID;

@@ -19,21 +19,42 @@ struct TraceHit {
 };
 
 // ---- per-primitive tests: candidate t in (tmin,tmax) of the ray -----------------
-// programs/hitables/triangle.cu:26-58
-PT_HD bool isect_triangle(float3 a, float3 b, float3 c, float3 o, float3 d, float tmin, float tmax,
+// programs/hitables/triangle.cu:26-58.  `tbest` (<= tmax) is the closest hit so far: a candidate
+// beyond it can never win.  The "certainly out" pre-tests decide from numerators and |A| alone
+// when the quotient is clearly outside its range (margins of 2^-18 >> the 2^-24 rounding of an
+// IEEE quotient); everything near a boundary falls through to the exact divisions, so the
+// accept/reject decision and the returned t,u,v are bit-identical to the reference sequence.
+PT_HD bool isect_triangle(float3 a, float3 b, float3 c, float3 o, float3 d, float tmin, float tmax, float tbest,
                           float& t, float& bu, float& bv) {
   float3 e1 = xsub(b, a);
   float3 e2 = xsub(c, a);
   float3 P = xcross(d, e2);
   float A = xdot(P, e1);
-  if ((double)fabsf(A) < 1E-8) return false;
+  const float absA = fabsf(A);
+  if ((double)absA < 1E-8) return false;
   float3 R = xsub(o, a);
-  float u = XDIV(xdot(P, R), A);
-  if (u < 0.0f || u > 1.0f) return false;
+  const float uN = xdot(P, R);
+  const float hiA = absA * 1.000004f;   // > |A| (1 + 2^-18)
+  const float tiny = absA * 1e-30f;     // quotients above this cannot underflow to zero
+  const bool opp_u = (uN < 0.f) != (A < 0.f);
+  if (fabsf(uN) > hiA) return false;                 // |u| > 1: u < 0 or u > 1
+  if (opp_u && fabsf(uN) > tiny) return false;       // u < 0
   float3 Q = xcross(R, e1);
-  float v = XDIV(xdot(Q, d), A);
+  const float vN = xdot(Q, d);
+  const bool opp_v = (vN < 0.f) != (A < 0.f);
+  if (fabsf(vN) > hiA) return false;                 // v < 0 or v > 1 >= 1 - u
+  if (opp_v && fabsf(vN) > tiny) return false;       // v < 0
+  const float tN = xdot(Q, e2);
+  if (tmin >= 0.f) {
+    const bool opp_t = (tN < 0.f) != (A < 0.f);
+    if (opp_t && fabsf(tN) > tiny) return false;     // t < 0 <= tmin
+    if (tbest < 1e30f && fabsf(tN) > hiA * tbest) return false;  // t > tbest
+  }
+  float u = XDIV(uN, A);
+  if (u < 0.0f || u > 1.0f) return false;
+  float v = XDIV(vN, A);
   if (v < 0.0f || XADD(u, v) > 1.0f) return false;
-  float tt = XDIV(xdot(Q, e2), A);
+  float tt = XDIV(tN, A);
   if (tt > tmin && tt < tmax) {
     t = tt;
     bu = u;
@@ -106,13 +127,13 @@ PT_HD bool isect_box(float3 bmin, float3 bmax, float3 o, float3 d, float tmin, f
 }
 
 // one leaf record against the (world) ray
-PT_HD bool isect_leaf(const SceneDev& sc, const LeafRec& L, float3 o, float3 d, float tmin, float tmax,
+PT_HD bool isect_leaf(const SceneDev& sc, const LeafRec& L, float3 o, float3 d, float tmin, float tmax, float tbest,
                       float& t, float& u, float& v) {
   uint32_t w = pt_f2u(L.b.w);
   int kind = PT_LEAF_KIND(w);
   u = 0.f;
   v = 0.f;
-  if (kind == PT_PRIM_TRIANGLE) return isect_triangle(xyz(L.a), xyz(L.b), xyz(L.c), o, d, tmin, tmax, t, u, v);
+  if (kind == PT_PRIM_TRIANGLE) return isect_triangle(xyz(L.a), xyz(L.b), xyz(L.c), o, d, tmin, tmax, tbest, t, u, v);
   int xf = PT_LEAF_XFORM(w);
   if (xf >= 0) {  // Transform node: ray to object space, t is shared
     const float* m = sc.xforms[xf].w2o;
@@ -142,15 +163,22 @@ PT_HD uint32_t pt_sign_extend_s8x4(uint32_t v) {
 }
 PT_HD uint32_t pt_byte(uint32_t v, int i) { return (v >> (8 * i)) & 0xffu; }
 
-// exact float(byte j of w).  Device: one PRMT builds the float 2^23 + q, one FADD removes
-// the bias (I2F runs at 1/8 rate and dominated the node test in the round-1 profile).
-PT_HD float pt_byte_to_float(uint32_t w, int j) {
+// Quantised plane byte -> float.  I2F runs at 1/8 rate and dominated the node test in the first
+// profile, so on the device one PRMT builds the float (2^15 + q) directly (q lands in mantissa
+// bits 8..15) and the 2^15 bias is folded into the FMA's addend once per node and axis:
+//   t = (2^15 + q) * s + (b - 2^15 * s).
+// Folding rounds the addend at magnitude 2^15*s, an error of at most 2^-10 quantisation steps;
+// the builder quantises child boxes with a 2^-8-step guard band (bvh_core.h), so the test stays
+// conservative.  The host build converts exactly.
 #ifdef __CUDA_ARCH__
-  return __uint_as_float(__byte_perm(w, 0x4b000000u, 0x7440u | (uint32_t)j)) - 8388608.0f;
-#else
-  return (float)pt_byte(w, j);
-#endif
+#define PT_QBIAS 32768.0f
+PT_HD float pt_byte_to_float(uint32_t w, int j) {
+  return __uint_as_float(__byte_perm(w, 0x47000000u, 0x7404u | ((uint32_t)j << 4)));
 }
+#else
+#define PT_QBIAS 0.0f
+PT_HD float pt_byte_to_float(uint32_t w, int j) { return (float)pt_byte(w, j); }
+#endif
 
 struct RayCtx {
   float3 o, d;
@@ -203,9 +231,9 @@ PT_HD void bvh8_node_step(const SceneDev& sc, const RayCtx& r, float tbest, uint
   const float sx = pt_u2f((n0.w & 0xffu) << 23) * r.idx;
   const float sy = pt_u2f(((n0.w >> 8) & 0xffu) << 23) * r.idy;
   const float sz = pt_u2f(((n0.w >> 16) & 0xffu) << 23) * r.idz;
-  const float bx = (pt_u2f(n0.x) - r.o.x) * r.idx;
-  const float by = (pt_u2f(n0.y) - r.o.y) * r.idy;
-  const float bz = (pt_u2f(n0.z) - r.o.z) * r.idz;
+  const float bx = XFMA(-PT_QBIAS, sx, (pt_u2f(n0.x) - r.o.x) * r.idx);
+  const float by = XFMA(-PT_QBIAS, sy, (pt_u2f(n0.y) - r.o.y) * r.idy);
+  const float bz = XFMA(-PT_QBIAS, sz, (pt_u2f(n0.z) - r.o.z) * r.idz);
   const uint32_t octinv4 = r.octinv * 0x01010101u;
 
   uint32_t hitmask = 0;
@@ -251,7 +279,7 @@ PT_HD void bvh8_leaf_step(const SceneDev& sc, const RayCtx& r, uint2& lg, TraceH
   L.b = PT_LDGF4(lp + 1);
   L.c = PT_LDGF4(lp + 2);
   float t, u, v;
-  if (isect_leaf(sc, L, r.o, r.d, r.tmin, r.tmax, t, u, v)) {
+  if (isect_leaf(sc, L, r.o, r.d, r.tmin, r.tmax, hit.t, t, u, v)) {
     const int prim = (int)pt_f2u(L.a.w);
     if (t < hit.t || (t == hit.t && (hit.prim < 0 || prim < hit.prim))) {
       hit.t = t;

@@ -116,11 +116,16 @@ Sim* sim_create(const pt_scene_desc* desc, int refine) {
     }
     s->sah_before = sah_sum(t);
     if (refine) {
-      std::vector<int> roots;
-      for (int i = 0; i < n - 1; i++)
-        if (treelet_is_root(t, i)) roots.push_back(i);
-      for (int r : roots) treelet_sah(t, r);
-      s->n_treelets = (int)roots.size();
+      long long lo = 1, hi = PT_TREELET;
+      for (int pass = 0; pass < 8 && lo < (long long)n; pass++) {
+        std::vector<int> roots;
+        for (int i = 0; i < n - 1; i++)
+          if (treelet_is_root(t, i, (int)lo, hi)) roots.push_back(i);
+        for (int r : roots) treelet_sah(t, r, (int)lo);
+        s->n_treelets += (int)roots.size();
+        lo = hi;
+        hi *= PT_TREELET;
+      }
     }
     s->sah_after = sah_sum(t);
   }

@@ -100,3 +100,25 @@ def test_russian_roulette_and_depth_cutoff():
     # programs/raygen.cu:122: depth exhaustion returns black, so depth=1 only sees the light
     a, _ = o.render(16, 16, 0, 1, max_depth=1)
     assert a[..., :3].max() <= 7.0 + 1e-6
+
+
+def test_triangle_boundary_rays():
+    """Rays aimed exactly at mesh vertices and edge midpoints (u=0, v=0, u+v=1 boundaries) and
+    grazing directions: the division-free pre-rejection in isect_triangle must not change any
+    accept/reject decision or value."""
+    sc = h.build_mesh_scene(12, 16, 16)
+    d = sc.desc()
+    v = np.ctypeslib.as_array(d.tri_v, shape=(d.n_tris, 3, 3)).copy()
+    targets = np.concatenate([v.reshape(-1, 3), (v[:, 0] + v[:, 1]) / 2, (v[:, 1] + v[:, 2]) / 2,
+                              (v[:, 0] + v[:, 2]) / 2]).astype(np.float32)
+    rays = np.zeros(len(targets) * 2, dtype=pt.RAY_DTYPE)
+    for k, org in enumerate(([0.25, 6.0, -0.5], [3.0, 0.3, -7.0])):
+        sl = slice(k * len(targets), (k + 1) * len(targets))
+        rays["origin"][sl] = org
+        rays["dir"][sl] = targets - np.array(org, dtype=np.float32)
+    rays["tmin"] = 1e-3
+    rays["tmax"] = 1e27
+    ho, _ = h.OracleScene(sc, mode=1).trace(rays)
+    hs, _ = h.SimScene(sc).trace(rays)
+    assert same_hits(ho, hs).all()
+    assert (ho["prim"] >= 0).mean() > 0.5
