@@ -209,6 +209,15 @@ typedef struct pt_scene_desc {
   const pt_light* lights;
   pt_camera camera;
   pt_miss miss;
+  /* environment importance sampling tables (only when miss.env_nee != 0 and miss.type ==
+   * PT_MISS_HDR with a spherical map; NEW, not in the reference): one entry per texel of the
+   * environment image, row-major.  Alias method: pick texel i uniformly, keep it with
+   * probability env_alias_prob[i], otherwise take env_alias_idx[i].  env_texel_pdf[i] is the
+   * probability of texel i (sums to 1). */
+  int32_t env_n;
+  const float* env_alias_prob;
+  const int32_t* env_alias_idx;
+  const float* env_texel_pdf;
 } pt_scene_desc;
 
 /* ---- scene construction --------------------------------------------------- */

@@ -108,6 +108,8 @@ class SceneDesc(C.Structure):
         ("n_images", C.c_int32), ("images", C.POINTER(Image)),
         ("n_lights", C.c_int32), ("lights", C.POINTER(Light)),
         ("camera", Camera), ("miss", Miss),
+        ("env_n", C.c_int32), ("env_alias_prob", C.POINTER(C.c_float)),
+        ("env_alias_idx", C.POINTER(C.c_int32)), ("env_texel_pdf", C.POINTER(C.c_float)),
     ]
 
 

@@ -90,6 +90,76 @@ int add_analytic(pt_scene* s, std::vector<T>& store, int kind, const T* prims, c
   return PT_OK;
 }
 
+// Alias table (Vose) over the texels of the environment image, weight = luminance of the
+// radiance the miss program returns (2 x texel, programs/miss.cu:93) x sin(theta) of the row,
+// plus 1 % of the mean so no direction has zero probability.  Built on the host at commit:
+// it is scene set-up, not part of the per-sample path.
+void build_env_tables(pt_scene* s) {
+  s->env_alias_prob.clear();
+  s->env_alias_idx.clear();
+  s->env_texel_pdf.clear();
+  s->env_tables_valid = true;
+  const pt_miss& m = s->miss;
+  if (!m.env_nee || m.type != PT_MISS_HDR || !m.spherical || m.image < 0 || m.image >= (int)s->images.size()) return;
+  const HostImage& im = s->images[m.image];
+  const size_t n = (size_t)im.width * im.height;
+  std::vector<double> w(n);
+  double sum = 0.0;
+  for (int y = 0; y < im.height; y++) {
+    const double st = sin(3.14159265358979323846 * (y + 0.5) / im.height);
+    for (int x = 0; x < im.width; x++) {
+      const float* t = &im.rgba[4 * ((size_t)y * im.width + x)];
+      double lum = 2.0 * (0.2126 * t[0] + 0.7152 * t[1] + 0.0722 * t[2]);
+      if (!(lum > 0.0) || !std::isfinite(lum)) lum = 0.0;
+      w[(size_t)y * im.width + x] = lum * st;
+      sum += lum * st;
+    }
+  }
+  const double floor_w = sum > 0.0 ? 0.01 * sum / (double)n : 1.0;
+  sum = 0.0;
+  for (int y = 0; y < im.height; y++) {
+    const double st = sin(3.14159265358979323846 * (y + 0.5) / im.height);
+    for (int x = 0; x < im.width; x++) {
+      double& v = w[(size_t)y * im.width + x];
+      v += floor_w * st;
+      sum += v;
+    }
+  }
+  s->env_texel_pdf.resize(n);
+  s->env_alias_prob.resize(n);
+  s->env_alias_idx.resize(n);
+  std::vector<double> q(n);
+  std::vector<int32_t> small, large;
+  small.reserve(n);
+  large.reserve(n);
+  for (size_t i = 0; i < n; i++) {
+    const double p = w[i] / sum;
+    s->env_texel_pdf[i] = (float)p;
+    q[i] = p * (double)n;
+    (q[i] < 1.0 ? small : large).push_back((int32_t)i);
+  }
+  while (!small.empty() && !large.empty()) {
+    const int32_t a = small.back();
+    small.pop_back();
+    const int32_t b = large.back();
+    s->env_alias_prob[a] = (float)q[a];
+    s->env_alias_idx[a] = b;
+    q[b] = (q[b] + q[a]) - 1.0;
+    if (q[b] < 1.0) {
+      large.pop_back();
+      small.push_back(b);
+    }
+  }
+  for (int32_t i : large) {
+    s->env_alias_prob[i] = 1.f;
+    s->env_alias_idx[i] = i;
+  }
+  for (int32_t i : small) {
+    s->env_alias_prob[i] = 1.f;
+    s->env_alias_idx[i] = i;
+  }
+}
+
 template <typename T>
 int upload_vec(DevBuf& b, const std::vector<T>& v) {
   PT_CUDA(b.alloc(v.size() * sizeof(T)));
@@ -267,6 +337,7 @@ int pt_scene_add_image(pt_scene* s, const float* rgba, int32_t w, int32_t h, int
   if (image_id) *image_id = (int32_t)s->images.size();
   s->images.push_back(std::move(im));
   s->committed = false;
+  s->env_tables_valid = false;
   return PT_OK;
 }
 int pt_scene_set_lights(pt_scene* s, const pt_light* l, int32_t n) {
@@ -292,7 +363,13 @@ int pt_scene_set_miss(pt_scene* s, const pt_miss* miss) {
     pt_set_error("Parameters invalid, miss program unknown or not yet implemented");  // programs.hpp:59,89
     return PT_ERR_INVALID;
   }
+  const bool tables_change = miss->env_nee != s->miss.env_nee || miss->image != s->miss.image ||
+                             miss->type != s->miss.type || miss->spherical != s->miss.spherical;
   s->miss = *miss;
+  if (tables_change) {
+    s->env_tables_valid = false;
+    if (miss->env_nee) s->committed = false;  // tables are uploaded by commit
+  }
   if (s->committed) s->dev.miss = *miss;
   return PT_OK;
 }
@@ -357,6 +434,10 @@ int pt_scene_commit(pt_scene* s) {
     imgs.push_back(d);
   }
   if ((rc = upload_vec(s->d_images, imgs))) return rc;
+  if (!s->env_tables_valid) build_env_tables(s);
+  if ((rc = upload_vec(s->d_env_prob, s->env_alias_prob))) return rc;
+  if ((rc = upload_vec(s->d_env_idx, s->env_alias_idx))) return rc;
+  if ((rc = upload_vec(s->d_env_pdf, s->env_texel_pdf))) return rc;
 
   if ((rc = pt_bvh_build(s))) return rc;
 
@@ -374,6 +455,12 @@ int pt_scene_commit(pt_scene* s) {
   d.texvec = s->d_texvec.as<int>();
   d.images = s->d_images.as<ImageDev>();
   d.lights = s->d_lights.as<pt_light>();
+  d.env_alias_prob = s->d_env_prob.as<float>();
+  d.env_alias_idx = s->d_env_idx.as<int>();
+  d.env_texel_pdf = s->d_env_pdf.as<float>();
+  d.env_n = (int)s->env_alias_prob.size();
+  d.env_w = d.env_n ? s->images[s->miss.image].width : 0;
+  d.env_h = d.env_n ? s->images[s->miss.image].height : 0;
   d.n_prims = (int)s->prims.size();
   d.n_materials = nm;
   d.n_textures = (int)s->textures.size();
@@ -419,6 +506,11 @@ int pt_scene_get_desc(const pt_scene* cs, pt_scene_desc* o) {
   o->lights = s->lights.data();
   o->camera = s->camera;
   o->miss = s->miss;
+  if (!s->env_tables_valid) build_env_tables(s);
+  o->env_n = (int)s->env_alias_prob.size();
+  o->env_alias_prob = s->env_alias_prob.data();
+  o->env_alias_idx = s->env_alias_idx.data();
+  o->env_texel_pdf = s->env_texel_pdf.data();
   return PT_OK;
 }
 

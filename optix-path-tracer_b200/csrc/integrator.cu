@@ -43,14 +43,29 @@ struct ShadowBuf {  // 112 B / shadow request
   float4* s[7];
 };
 
-struct Ctrl {
-  int n_cur, n_next, n_shadow;
-  int fetch_closest, fetch_shadow;  // ray cursors of the persistent traversal kernels
-  int gen_base, gen_n;
-  int bin_count[NBINS];
-  unsigned long long sample_base, next_sample, total_samples;
-  unsigned long long stat_closest, stat_shadow, stat_nodes, stat_leaves, stat_iters;
+// Device control block.  Every atomically updated counter sits on its own 128-byte line: queue
+// tails, bin counters and fetch cursors are hammered by warp-aggregated atomics from all SMs while
+// other fields are read as loop bounds, and sharing L2 lines between them (or with whatever small
+// allocation happens to be adjacent) made whole kernels up to 50 % slower depending on placement.
+struct alignas(128) PaddedInt {
+  int v;
+  int pad[31];
 };
+struct alignas(128) Ctrl {
+  // written by k_iter_begin only, read as loop bounds
+  int n_cur, gen_base, gen_n;
+  unsigned long long sample_base, next_sample, total_samples;
+  unsigned long long stat_closest, stat_shadow, stat_iters;
+  // atomics
+  PaddedInt n_next_, n_shadow_, fetch_closest_, fetch_shadow_;
+  PaddedInt bin_count[NBINS];
+  alignas(128) unsigned long long stat_nodes;
+  alignas(128) unsigned long long stat_leaves;
+};
+#define n_next n_next_.v
+#define n_shadow n_shadow_.v
+#define fetch_closest fetch_closest_.v
+#define fetch_shadow fetch_shadow_.v
 
 struct Params {
   int W, H, first_frame, max_depth, russian, pool;
@@ -81,7 +96,7 @@ __device__ __forceinline__ int push_slot(int* counter) {
 // then either accumulate or append the path to the next wavefront
 __device__ __forceinline__ void finish_bounce(const Params& p, Ctrl* c, const PathBuf& next, uint32_t pix,
                                               int depth, float3 o, float3 d, float3 thr, float3 rad,
-                                              uint32_t seed, bool specular) {
+                                              uint32_t seed, bool specular, float pdf) {
   if (p.russian) {
     float prob = pt_ffmax(pt_ffmax(thr.x, thr.y), thr.z);
     if (depth > 10) {
@@ -100,7 +115,7 @@ __device__ __forceinline__ void finish_bounce(const Params& p, Ctrl* c, const Pa
   int slot = push_slot(&c->n_next);
   next.o_seed[slot] = make_float4(o.x, o.y, o.z, __uint_as_float(seed));
   next.d_pack[slot] = make_float4(d.x, d.y, d.z, __uint_as_float(pack_state(pix, depth, specular)));
-  next.thr[slot] = make_float4(thr.x, thr.y, thr.z, 0.f);
+  next.thr[slot] = make_float4(thr.x, thr.y, thr.z, pdf);  // .w: BSDF pdf of this ray (env NEE MIS)
   next.rad[slot] = make_float4(rad.x, rad.y, rad.z, 0.f);
 }
 
@@ -119,7 +134,7 @@ __global__ void k_iter_begin(Ctrl* c, int pool) {
   c->n_shadow = 0;
   c->fetch_closest = 0;
   c->fetch_shadow = 0;
-  for (int i = 0; i < NBINS; i++) c->bin_count[i] = 0;
+  for (int i = 0; i < NBINS; i++) c->bin_count[i].v = 0;
   c->stat_closest += (unsigned long long)c->n_cur;
   c->stat_iters += 1;
 }
@@ -162,6 +177,7 @@ struct ClosestPolicy {
     tmax = PT_RAY_MAX;
     return true;
   }
+  __device__ __forceinline__ bool any_hit(int) const { return false; }
   __device__ __forceinline__ void emit(int i, const TraceHit& h, unsigned fin) const {
     hits[i] = make_float4(h.t, __int_as_float(h.leaf), h.u, h.v);
     int key = BIN_MISS;
@@ -171,7 +187,7 @@ struct ClosestPolicy {
     int leader = __ffs(peers) - 1;
     int lane = threadIdx.x & 31;
     int base = 0;
-    if (lane == leader) base = atomicAdd(&c->bin_count[key], __popc(peers));
+    if (lane == leader) base = atomicAdd(&c->bin_count[key].v, __popc(peers));
     base = __shfl_sync(peers, base, leader);
     bin_q[(size_t)key * pool + base + __popc(peers & ((1u << lane) - 1))] = (uint32_t)i;
   }
@@ -202,7 +218,7 @@ __global__ void __launch_bounds__(PT_TRACE_THREADS) k_trace(SceneDev sc, Ctrl* c
 template <int MAT>
 __global__ void __launch_bounds__(128, PT_SHADE_MINBLOCKS) k_shade(SceneDev sc, Params p, Ctrl* c, PathBuf cur, PathBuf next, ShadowBuf sb,
                                                const float4* hits, const uint32_t* bin_q) {
-  const int n = c->bin_count[MAT];
+  const int n = c->bin_count[MAT].v;
   const uint32_t* q = bin_q + (size_t)MAT * p.pool;
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
     const int i = (int)q[j];
@@ -216,13 +232,14 @@ __global__ void __launch_bounds__(128, PT_SHADE_MINBLOCKS) k_shade(SceneDev sc, 
     in.seed = __float_as_uint(o4.w);
     in.depth = (pk >> 23) & 0xff;
     in.prev_specular = (pk >> 31) != 0;
+    in.last_pdf = t4.w;
     const uint32_t pix = pk & 0x7fffffu;
     ShadeOut out;
     shade_hit<MAT>(sc, in, h4.x, __float_as_int(h4.y), h4.z, h4.w, out);
     if (out.kind == SH_TERMINATE) {
       accumulate(p, pix, out.col);
     } else if (out.kind == SH_BOUNCE) {
-      finish_bounce(p, c, next, pix, in.depth, out.P, out.dir, out.thr, out.rad, out.seed, out.specular);
+      finish_bounce(p, c, next, pix, in.depth, out.P, out.dir, out.thr, out.rad, out.seed, out.specular, out.pdf);
     } else {
       int s = push_slot(&c->n_shadow);
       uint32_t pk2 = pack_state(pix, in.depth, out.terminal);
@@ -232,13 +249,13 @@ __global__ void __launch_bounds__(128, PT_SHADE_MINBLOCKS) k_shade(SceneDev sc, 
       sb.s[3][s] = make_float4(out.dirS.x, out.dirS.y, out.dirS.z, out.thr.x);
       sb.s[4][s] = make_float4(out.thr.y, out.thr.z, out.rad.x, out.rad.y);
       sb.s[5][s] = make_float4(out.rad.z, out.thrS.x, out.thrS.y, out.thrS.z);
-      sb.s[6][s] = make_float4(out.radS.x, out.radS.y, out.radS.z, 0.f);
+      sb.s[6][s] = make_float4(out.radS.x, out.radS.y, out.radS.z, out.env_shadow ? out.pdf : -1.f);
     }
   }
 }
 
 __global__ void __launch_bounds__(128) k_miss(SceneDev sc, Params p, Ctrl* c, PathBuf cur, const uint32_t* bin_q) {
-  const int n = c->bin_count[BIN_MISS];
+  const int n = c->bin_count[BIN_MISS].v;
   const uint32_t* q = bin_q + (size_t)BIN_MISS * p.pool;
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
     const int i = (int)q[j];
@@ -247,6 +264,7 @@ __global__ void __launch_bounds__(128) k_miss(SceneDev sc, Params p, Ctrl* c, Pa
     in.d = f3(d4.x, d4.y, d4.z);
     in.thr = f3(t4.x, t4.y, t4.z);
     in.rad = f3(r4.x, r4.y, r4.z);
+    in.last_pdf = t4.w;
     accumulate(p, __float_as_uint(d4.w) & 0x7fffffu, shade_miss(sc, in));
   }
 }
@@ -267,11 +285,18 @@ struct ShadowPolicy {
     tmax = PT_RAY_MAX;
     return true;
   }
+  // environment shadow rays are occlusion queries; rect-light shadow rays need the closest hit
+#ifdef PT_NO_ANYHIT
+  __device__ __forceinline__ bool any_hit(int) const { return false; }
+#else
+  __device__ __forceinline__ bool any_hit(int i) const { return sb.s[6][i].w >= 0.f; }
+#endif
   __device__ __forceinline__ void emit(int i, const TraceHit& h, unsigned) const {
-    bool visible = false;
-    if (h.leaf >= 0) visible = (__float_as_uint(__ldg(&sc.leaves[h.leaf].c.w)) >> 24) == PT_MAT_DIFFUSE_LIGHT;
     float4 s0 = sb.s[0][i], s1 = sb.s[1][i], s2 = sb.s[2][i], s3 = sb.s[3][i], s4 = sb.s[4][i], s5 = sb.s[5][i],
            s6 = sb.s[6][i];
+    const bool env = s6.w >= 0.f;  // shadow ray towards the environment: visible <=> nothing hit
+    bool visible = env ? h.leaf < 0 : false;
+    if (!env && h.leaf >= 0) visible = (__float_as_uint(__ldg(&sc.leaves[h.leaf].c.w)) >> 24) == PT_MAT_DIFFUSE_LIGHT;
     uint32_t pk = __float_as_uint(s2.w);
     uint32_t pix = pk & 0x7fffffu;
     int depth = (pk >> 23) & 0xff;
@@ -290,7 +315,7 @@ struct ShadowPolicy {
       seed = __float_as_uint(s1.w);
     }
     if (terminal) accumulate(p, pix, rad);
-    else finish_bounce(p, c, next, pix, depth, f3(s0.x, s0.y, s0.z), dir, thr, rad, seed, false);
+    else finish_bounce(p, c, next, pix, depth, f3(s0.x, s0.y, s0.z), dir, thr, rad, seed, false, env ? s6.w : 0.f);
   }
 };
 
@@ -326,6 +351,7 @@ struct RaySetPolicy {
     tmax = b.w;
     return b.w > a.w;
   }
+  __device__ __forceinline__ bool any_hit(int) const { return false; }
   __device__ __forceinline__ void emit(int i, const TraceHit& h, unsigned) const {
     pt_hit o;
     o.t = h.t;
@@ -386,6 +412,9 @@ int trace_blocks_per_sm() {
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_shadow<false>, PT_TRACE_THREADS, 0);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c, k_trace_rays<false>, PT_TRACE_THREADS, 0);
     g_trace_bpm = std::max(1, std::min(a, std::min(b, c)));
+#ifdef PT_TRACE_BPM
+    g_trace_bpm = PT_TRACE_BPM;
+#endif
   }
   return g_trace_bpm;
 }
@@ -401,7 +430,12 @@ struct pt_renderer {
   int pool = 0;
   DevBuf accum_own;
   float4* accum = nullptr;
-  DevBuf pathA[4], pathB[4], shadow[7], hits, bin_q, ctrl;
+  // all per-path arrays live in one slab; array k starts at a skewed offset so that the same
+  // path index in different arrays never maps to the same DRAM/L2 partition (arrays of exactly
+  // 2^26 bytes allocated back to back alias badly: measured -30 % on NEE scenes)
+  DevBuf slab, ctrl;
+  float4 *pathA[4] = {}, *pathB[4] = {}, *shadow[7] = {}, *hits = nullptr;
+  uint32_t* bin_q = nullptr;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool started = false;
@@ -417,13 +451,29 @@ static int ensure_pool(pt_renderer* r, long long want) {
   pool = std::min<long long>(pool, 1ll << 25);
   if (pool <= r->pool) return PT_OK;
   r->pool = (int)pool;
-  for (int k = 0; k < 4; k++) {
-    PT_CUDA(r->pathA[k].alloc((size_t)pool * 16));
-    PT_CUDA(r->pathB[k].alloc((size_t)pool * 16));
-  }
-  for (int k = 0; k < 7; k++) PT_CUDA(r->shadow[k].alloc((size_t)pool * 16));
-  PT_CUDA(r->hits.alloc((size_t)pool * 16));
-  PT_CUDA(r->bin_q.alloc((size_t)pool * 4 * NBINS));
+  const size_t arr = (size_t)pool * 16;
+  size_t skew = 33 * 256;  // odd multiple of 256 B
+  size_t gap = 64 * 1024;
+  if (const char* e = getenv("PTB200_GAP")) gap = (size_t)atoll(e);    // dev: layout experiments
+  if (const char* e = getenv("PTB200_SKEW")) skew = (size_t)atoll(e);
+  const int n_arr = 4 + 4 + 7 + 1;
+  const size_t total = (arr + gap + 7 * skew + 256) * n_arr + (size_t)pool * 4 * NBINS + 64 * 1024;
+  PT_CUDA(r->slab.alloc(total));
+  char* base = r->slab.as<char>();
+  size_t off = 0;
+  int k = 0;
+  auto carve = [&](size_t bytes) {
+    char* p = base + off + (size_t)(k % 7) * skew;
+    off += bytes + gap + 7 * skew;
+    off = (off + 255) & ~(size_t)255;
+    k++;
+    return p;
+  };
+  for (int i = 0; i < 4; i++) r->pathA[i] = (float4*)carve(arr);
+  for (int i = 0; i < 4; i++) r->pathB[i] = (float4*)carve(arr);
+  for (int i = 0; i < 7; i++) r->shadow[i] = (float4*)carve(arr);
+  r->hits = (float4*)carve(arr);
+  r->bin_q = (uint32_t*)(base + off);
   return PT_OK;
 }
 
@@ -529,15 +579,15 @@ int pt_render(pt_renderer* r, int32_t first_frame, int32_t nframes, int32_t max_
   p.pool = r->pool;
   p.accum = r->accum;
   PathBuf A, B;
-  A.o_seed = r->pathA[0].as<float4>(); A.d_pack = r->pathA[1].as<float4>();
-  A.thr = r->pathA[2].as<float4>(); A.rad = r->pathA[3].as<float4>();
-  B.o_seed = r->pathB[0].as<float4>(); B.d_pack = r->pathB[1].as<float4>();
-  B.thr = r->pathB[2].as<float4>(); B.rad = r->pathB[3].as<float4>();
+  A.o_seed = r->pathA[0]; A.d_pack = r->pathA[1];
+  A.thr = r->pathA[2]; A.rad = r->pathA[3];
+  B.o_seed = r->pathB[0]; B.d_pack = r->pathB[1];
+  B.thr = r->pathB[2]; B.rad = r->pathB[3];
   ShadowBuf sb;
-  for (int k = 0; k < 7; k++) sb.s[k] = r->shadow[k].as<float4>();
+  for (int k = 0; k < 7; k++) sb.s[k] = r->shadow[k];
   Ctrl* c = r->ctrl.as<Ctrl>();
-  float4* hits = r->hits.as<float4>();
-  uint32_t* bq = r->bin_q.as<uint32_t>();
+  float4* hits = r->hits;
+  uint32_t* bq = r->bin_q;
   const SceneDev& sc = s->dev;
   const bool count = (r->flags & 1) != 0;
   const bool timing = (r->flags & 2) != 0;
@@ -587,7 +637,7 @@ int pt_render(pt_renderer* r, int32_t first_frame, int32_t nframes, int32_t max_
       if (timing) cudaEventRecord(e[3], st);
       launches++;
       if (mask & ((1u << PT_MAT_LAMBERTIAN) | (1u << PT_MAT_OREN_NAYAR) | (1u << PT_MAT_DIFFUSE_LIGHT))) {
-        if (s->lights.size() > 0) {
+        if (s->lights.size() > 0 || sc.env_n > 0) {
           if (count) k_shadow<true><<<g_trace, PT_TRACE_THREADS, 0, st>>>(sc, p, c, B, sb, sched);
           else k_shadow<false><<<g_trace, PT_TRACE_THREADS, 0, st>>>(sc, p, c, B, sb, sched);
           launches++;

@@ -50,6 +50,11 @@ struct SceneDev {
   const int* texvec;
   const ImageDev* images;
   const pt_light* lights;
+  // environment importance sampling (alias table over the texels of the HDR miss image)
+  const float* env_alias_prob;
+  const int* env_alias_idx;
+  const float* env_texel_pdf;
+  int env_n, env_w, env_h;
   int n_prims, n_materials, n_textures, n_texvec, n_images, n_lights;
   pt_camera camera;
   pt_miss miss;

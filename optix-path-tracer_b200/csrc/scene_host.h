@@ -77,12 +77,16 @@ struct pt_scene {
   pt_camera camera{};
   pt_miss miss{};
   bool committed = false;
+  // environment importance sampling tables (built on the host at commit / get_desc)
+  std::vector<float> env_alias_prob, env_texel_pdf;
+  std::vector<int32_t> env_alias_idx;
+  bool env_tables_valid = false;
 
   // device side
   DevBuf d_prim_ref, d_spheres, d_rects, d_boxes, d_tri_v, d_tri_n, d_tri_uv, d_tri_tex, d_xforms;
   DevBuf d_materials, d_textures, d_texvec, d_images, d_lights;
   std::vector<DevBuf*> d_image_texels;
-  DevBuf d_nodes8, d_leaves, d_prim_leaf;
+  DevBuf d_nodes8, d_leaves, d_prim_leaf, d_env_prob, d_env_idx, d_env_pdf;
   SceneDev dev{};
   pt_bvh_info info{};
   uint32_t material_type_mask = 0;  // which PT_MAT_* occur (host decides which shade kernels to launch)

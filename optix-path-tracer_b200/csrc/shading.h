@@ -542,6 +542,49 @@ PT_HD float3 miss_color(const SceneDev& sc, float3 d) {
   return 2.f * c;
 }
 
+// ---- environment importance sampling (NEW: pt_miss.env_nee; not in the reference) -----------
+// Active when the scene has no rect lights, the miss program is a spherical HDR map and the
+// alias table was built (SceneDev::env_n > 0).  Lambertian / Oren-Nayar hits then sample one
+// direction from the texel distribution (4 draws: texel, alias coin, 2 jitter), trace an
+// any-hit shadow ray and add f * L * w / p with the power heuristic against the BSDF pdf; the
+// BSDF-sampled bounce carries its pdf so that a later miss is weighted the other way round
+// (and the reference's clamp at miss is dropped: it cannot be applied per estimator).
+#ifdef PT_NO_ENV
+PT_HD bool env_nee_active(const SceneDev&) { return false; }
+#else
+PT_HD bool env_nee_active(const SceneDev& sc) { return sc.env_n > 0 && sc.n_lights == 0; }
+#endif
+PT_HD float3 env_dir_from_uv(float u, float v) {  // inverse of miss.cu:70-79 (u = lon/2pi, v = lat/pi)
+  float lon = u * (2.f * PT_PI_F), lat = v * PT_PI_F;
+  float st = sinf(lat);
+  return f3(st * cosf(lon), cosf(lat), st * sinf(lon));
+}
+PT_HD float env_pdf_dir(const SceneDev& sc, float3 d) {  // solid-angle pdf of direction d
+  float r = length(d);
+  float lon = atan2f(d.z, d.x);
+  float lat = acosf(d.y / r);
+  float u = lon * (1.f / (PT_PI_F * 2.f));
+  if (u < 0.f) u += 1.f;
+  float v = lat * (1.f / PT_PI_F);
+  int x = (int)(u * (float)sc.env_w), y = (int)(v * (float)sc.env_h);
+  x = x < 0 ? 0 : (x > sc.env_w - 1 ? sc.env_w - 1 : x);
+  y = y < 0 ? 0 : (y > sc.env_h - 1 ? sc.env_h - 1 : y);
+  float st = sinf(lat);
+  if (!(st > 1e-6f)) return 0.f;
+  return sc.env_texel_pdf[(size_t)y * sc.env_w + x] * ((float)sc.env_n / (2.f * PT_PI_F * PT_PI_F * st));
+}
+PT_HD float3 env_sample_dir(const SceneDev& sc, uint32_t& seed, float& pdf) {
+  float u0 = pt_rnd(seed), u1 = pt_rnd(seed), u2 = pt_rnd(seed), u3 = pt_rnd(seed);
+  int i = (int)(u0 * (float)sc.env_n);
+  i = i > sc.env_n - 1 ? sc.env_n - 1 : i;
+  if (u1 >= sc.env_alias_prob[i]) i = sc.env_alias_idx[i];
+  int x = i % sc.env_w, y = i / sc.env_w;
+  float u = ((float)x + u2) / (float)sc.env_w, v = ((float)y + u3) / (float)sc.env_h;
+  float st = sinf(v * PT_PI_F);
+  pdf = st > 1e-6f ? sc.env_texel_pdf[i] * ((float)sc.env_n / (2.f * PT_PI_F * PT_PI_F * st)) : 0.f;
+  return env_dir_from_uv(u, v);
+}
+
 // ---- one shading event -------------------------------------------------------------------------
 enum { SH_TERMINATE = 0, SH_BOUNCE = 1, SH_SHADOW = 2 };
 
@@ -551,6 +594,7 @@ struct PathIn {
   uint32_t seed;
   int depth;
   bool prev_specular;
+  float last_pdf;  // env NEE: BSDF pdf of the direction that produced this ray (0 = unweighted)
 };
 
 struct ShadeOut {
@@ -564,6 +608,8 @@ struct ShadeOut {
   float3 WiL, dirS, thrS, radS;
   uint32_t seedS;
   bool terminal;  // light-surface NEE (numLights >= 2): rad / radS are final colours
+  float pdf;      // env NEE: pdf of the sampled bounce direction (carried to the next miss)
+  bool env_shadow;  // shadow ray towards the environment: visible <=> nothing is hit
 };
 
 // Direct_Light<T> (light_sample.cuh:35-103) for a cosine-type surface, split
@@ -623,6 +669,8 @@ PT_HD void shade_hit(const SceneDev& sc, const PathIn& in, float t, int leaf, fl
   surf.color = surf.color2 = f3(0.f);
   out.P = P;
   out.terminal = false;
+  out.pdf = 0.f;
+  out.env_shadow = false;
   out.seed = in.seed;
   out.thr = in.thr;
   out.rad = in.rad;
@@ -635,6 +683,36 @@ PT_HD void shade_hit(const SceneDev& sc, const PathIn& in, float t, int leaf, fl
   }
   surf.color = sample_texture(sc, m.tex0, rec.u, rec.v, P, rec.index);
 
+  if ((MAT == PT_MAT_LAMBERTIAN || MAT == PT_MAT_OREN_NAYAR) && env_nee_active(sc)) {
+    uint32_t seed = in.seed;
+    float lpdf;
+    float3 WiL = env_sample_dir(sc, seed, lpdf);
+    float3 direct = f3(0.f);
+    bool need_shadow = false;
+    if (dot(WiL, N) > 0.f && lpdf > 0.f) {
+      float mpdf = 0.f;
+      float3 f = bsdf_eval<MAT>(surf, Wo, WiL, N, mpdf);
+      if (mpdf != 0.f && !(f.x == 0.f && f.y == 0.f && f.z == 0.f)) {
+        float w = power_heuristic(lpdf, mpdf);
+        direct = f * miss_color(sc, WiL) * w / lpdf;
+        need_shadow = true;
+      }
+    }
+    float3 Wi = bsdf_sample<MAT>(surf, Wo, N, seed);
+    float pdf = 0.f;
+    float3 att = bsdf_eval<MAT>(surf, Wo, Wi, N, pdf);
+    out.specular = false;
+    out.dir = out.dirS = Wi;
+    out.thr = out.thrS = in.thr * clamp3(att / pdf, 0.f, 1.f);
+    out.seed = out.seedS = seed;
+    out.pdf = pdf;
+    out.radS = in.rad;
+    out.rad = need_shadow ? in.rad + in.thr * direct : in.rad;
+    out.WiL = WiL;
+    out.env_shadow = need_shadow;
+    out.kind = need_shadow ? SH_SHADOW : SH_BOUNCE;
+    return;
+  }
   if (MAT == PT_MAT_LAMBERTIAN || MAT == PT_MAT_OREN_NAYAR) {  // lambertian.cu:49-73, oren_nayar.cu:46-70
     uint32_t seed = in.seed;
     float3 WiL, directV, misDir;
@@ -767,6 +845,11 @@ PT_HD void shade_hit(const SceneDev& sc, const PathIn& in, float t, int leaf, fl
 // raygen.cu:81-82: miss returns radiance + clamp(throughput * background, 0, 1)
 PT_HD float3 shade_miss(const SceneDev& sc, const PathIn& in) {
   float3 thr = in.thr * miss_color(sc, in.d);
+  if (env_nee_active(sc)) {  // NEW estimator: MIS weight against the env-sampling pdf, no clamp
+    float w = 1.f;
+    if (in.last_pdf > 0.f) w = power_heuristic(in.last_pdf, env_pdf_dir(sc, in.d));
+    return in.rad + thr * w;
+  }
   return in.rad + clamp3(thr, 0.f, 1.f);
 }
 

@@ -18,6 +18,7 @@
 //
 // Policy interface (all __device__):
 //   bool load(int i, float3& o, float3& d, float& tmin, float& tmax)   false = empty interval
+//   bool any_hit(int i)                                                 true = stop at the first hit
 //   void emit(int i, const TraceHit& h, unsigned finished_mask)        called convergently by
 //                                                                        exactly the lanes in the mask
 #pragma once
@@ -41,6 +42,7 @@ __device__ __forceinline__ void trace_persistent(const SceneDev& sc, int n, int*
   uint2 lstack[PT_STACK - PT_SMEM_STACK];
 
   int ray = -1;
+  bool anyhit = false;
   bool exhausted = false;  // warp-uniform: the ray queue is empty
   RayCtx r;
   TraceHit hit;
@@ -79,6 +81,7 @@ __device__ __forceinline__ void trace_persistent(const SceneDev& sc, int n, int*
             float3 o, d;
             float tmin, tmax;
             const bool ok = pol.load(idx, o, d, tmin, tmax);
+            anyhit = pol.any_hit(idx);
             ray_setup(r, o, d, tmin, tmax);
             hit_reset(hit, tmax);
             ng = make_uint2(0u, ok ? 0x80000000u : 0u);  // root group (or nothing: reports a miss)
@@ -100,6 +103,11 @@ __device__ __forceinline__ void trace_persistent(const SceneDev& sc, int n, int*
       if (hasL) {
         bvh8_leaf_step(sc, r, lg, hit);
         if (COUNT) cl++;
+        if (anyhit && hit.leaf >= 0) {  // occlusion query: any hit ends the ray
+          ng.y = 0u;
+          lg.y = 0u;
+          sp = 0;
+        }
       }
     } else if (mN != 0u) {
       if (hasN) {

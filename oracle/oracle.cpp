@@ -1105,10 +1105,15 @@ struct PerRayData {  // P/prd.cuh:45-57
   ScatterEvent scatterEvent;
   bool isSpecular;
   f3 origin, direction;
+  float last_pdf;  // env NEE mode only: BSDF pdf of the direction that produced the current ray
 };
 struct Counters {
   uint64_t closest = 0, shadow = 0, bounces = 0, nodes = 0, prims = 0;
 };
+
+f3 miss_color(const orc_scene& s, f3 d);
+inline bool env_nee_active(const orc_scene& s);
+inline f3 env_sample_dir(const orc_scene& s, uint32_t& seed, float& pdf);
 
 // P/materials/light_sample.cuh:35-103
 f3 Direct_Light(const orc_scene& s, const Surface& surface, f3 P, f3 Wo, f3 N, bool isLight,
@@ -1171,6 +1176,37 @@ void closest_hit_program(const orc_scene& s, const Ray& ray, const Hit& h, PerRa
     case PT_MAT_LAMBERTIAN:   // lambertian.cu:49-73
     case PT_MAT_OREN_NAYAR: {  // oren_nayar.cu:46-70
       surf.color = sample_texture(s, m.tex0, rec.u, rec.v, P, index);
+      if (env_nee_active(s)) {  // NEW estimator (see env_* above)
+        float lpdf;
+        f3 WiL = env_sample_dir(s, prd.seed, lpdf);
+        f3 direct = mk(0.f);
+        bool need_shadow = false;
+        if (dot(WiL, N) > 0.f && lpdf > 0.f) {
+          float mpdf = 0.f;
+          f3 f = Evaluate(surf, P, Wo, WiL, N, mpdf);
+          if (mpdf != 0.f && !isNull(f)) {
+            float w = PowerHeuristic(1, lpdf, 1, mpdf);
+            direct = f * miss_color(s, WiL) * w / lpdf;
+            need_shadow = true;
+          }
+        }
+        f3 Wi = Sample(surf, P, Wo, N, prd.seed);
+        float pdf = 0.f;
+        f3 attenuation = Evaluate(surf, P, Wo, Wi, N, pdf);
+        if (need_shadow) {
+          Ray sh = {P, WiL, 1e-3f, RT_DEFAULT_MAX};
+          Hit hh = closest_hit(s, sh, &cn.nodes, &cn.prims);
+          cn.shadow++;
+          if (hh.prim < 0) prd.radiance = prd.radiance + prd.throughput * direct;
+        }
+        prd.scatterEvent = rayGotBounced;
+        prd.origin = P;
+        prd.direction = Wi;
+        prd.throughput = prd.throughput * clamp3(attenuation / pdf, 0.f, 1.f);
+        prd.isSpecular = false;
+        prd.last_pdf = pdf;
+        break;
+      }
       f3 direct = Direct_Light(s, surf, P, Wo, N, false, prd.seed, cn);
       prd.radiance += prd.throughput * direct;
       f3 Wi = Sample(surf, P, Wo, N, prd.seed);
@@ -1266,53 +1302,86 @@ void closest_hit_program(const orc_scene& s, const Ray& ray, const Hit& h, PerRa
   }
 }
 
-// miss programs — P/miss.cu:30-95
-void miss_program(const orc_scene& s, const Ray& ray, PerRayData& prd) {
+// miss programs — P/miss.cu:30-95: background radiance factor for direction d
+f3 miss_color(const orc_scene& s, f3 d) {
   const pt_miss& ms = s.d.miss;
   switch (ms.type) {
     case PT_MISS_GRADIENT: {
-      const f3 unit_direction = normalize(ray.d);
+      const f3 unit_direction = normalize(d);
       const float t = 0.5f * (unit_direction.y + 1.f);
       f3 c = (1.f - t) * ld3(ms.color1);
       c += t * ld3(ms.color2);
-      prd.throughput *= c;
-      break;
+      return c;
     }
     case PT_MISS_CONSTANT:
-      prd.throughput *= ld3(ms.color1);
-      break;
+      return ld3(ms.color1);
     case PT_MISS_IMG: {
-      float theta = atan2f(ray.d.x, ray.d.z);
-      float phi = OPTIX_PIf * 0.5f - acosf(ray.d.y);
+      float theta = atan2f(d.x, d.z);
+      float phi = OPTIX_PIf * 0.5f - acosf(d.y);
       float u = (theta + OPTIX_PIf) * (0.5f * OPTIX_1_PIf);
       float v = 0.5f * (1.f + sinf(phi));
-      f3 c = (ms.image >= 0 && ms.image < s.d.n_images) ? image_lookup(s.d.images[ms.image], u, v)
-                                                         : mk(0.f);
-      prd.throughput *= c;
-      break;
+      return (ms.image >= 0 && ms.image < s.d.n_images) ? image_lookup(s.d.images[ms.image], u, v) : mk(0.f);
     }
     default: {  // HDR environmental_mapping
       float u, v;
       if (ms.spherical) {
-        float r = length(ray.d);
-        float lon = atan2f(ray.d.z, ray.d.x);
-        float lat = acosf(ray.d.y / r);
+        float r = length(d);
+        float lon = atan2f(d.z, d.x);
+        float lat = acosf(d.y / r);
         float rx = 1.f / (PI_F * 2.f), ry = 1.f / PI_F;
         u = lon * rx;
         v = lat * ry;
       } else {
-        float theta = atan2f(ray.d.x, ray.d.z);
+        float theta = atan2f(d.x, d.z);
         theta = theta < 0.f ? theta + (2.f * PI_F) : theta;
-        float phi = acosf(ray.d.y);
+        float phi = acosf(d.y);
         u = 1.f - (theta / (2.f * PI_F));
         v = phi / PI_F;
       }
-      f3 c = (ms.image >= 0 && ms.image < s.d.n_images) ? image_lookup(s.d.images[ms.image], u, v)
-                                                         : mk(0.f);
-      prd.throughput *= 2.f * c;
-      break;
+      f3 c = (ms.image >= 0 && ms.image < s.d.n_images) ? image_lookup(s.d.images[ms.image], u, v) : mk(0.f);
+      return 2.f * c;
     }
   }
+}
+
+// ---- environment importance sampling (NEW mode pt_miss.env_nee; own definition, mirrored by
+// the product's shading.h): alias table over texels, power-heuristic MIS, no clamp at miss ----
+inline bool env_nee_active(const orc_scene& s) { return s.d.env_n > 0 && s.d.n_lights == 0; }
+inline f3 env_dir_from_uv(float u, float v) {
+  float lon = u * (2.f * PI_F), lat = v * PI_F;
+  float st = sinf(lat);
+  return mk(st * cosf(lon), cosf(lat), st * sinf(lon));
+}
+inline float env_pdf_dir(const orc_scene& s, f3 d) {
+  const pt_image& im = s.d.images[s.d.miss.image];
+  float r = length(d);
+  float lon = atan2f(d.z, d.x);
+  float lat = acosf(d.y / r);
+  float u = lon * (1.f / (PI_F * 2.f));
+  if (u < 0.f) u += 1.f;
+  float v = lat * (1.f / PI_F);
+  int x = (int)(u * (float)im.width), y = (int)(v * (float)im.height);
+  x = x < 0 ? 0 : (x > im.width - 1 ? im.width - 1 : x);
+  y = y < 0 ? 0 : (y > im.height - 1 ? im.height - 1 : y);
+  float st = sinf(lat);
+  if (!(st > 1e-6f)) return 0.f;
+  return s.d.env_texel_pdf[(size_t)y * im.width + x] * ((float)s.d.env_n / (2.f * PI_F * PI_F * st));
+}
+inline f3 env_sample_dir(const orc_scene& s, uint32_t& seed, float& pdf) {
+  const pt_image& im = s.d.images[s.d.miss.image];
+  float u0 = rnd(seed), u1 = rnd(seed), u2 = rnd(seed), u3 = rnd(seed);
+  int i = (int)(u0 * (float)s.d.env_n);
+  i = i > s.d.env_n - 1 ? s.d.env_n - 1 : i;
+  if (u1 >= s.d.env_alias_prob[i]) i = s.d.env_alias_idx[i];
+  int x = i % im.width, y = i / im.width;
+  float u = ((float)x + u2) / (float)im.width, v = ((float)y + u3) / (float)im.height;
+  float st = sinf(v * PI_F);
+  pdf = st > 1e-6f ? s.d.env_texel_pdf[i] * ((float)s.d.env_n / (2.f * PI_F * PI_F * st)) : 0.f;
+  return env_dir_from_uv(u, v);
+}
+
+void miss_program(const orc_scene& s, const Ray& ray, PerRayData& prd) {
+  prd.throughput *= miss_color(s, ray.d);
   prd.scatterEvent = rayMissed;
 }
 
@@ -1324,17 +1393,26 @@ f3 color(const orc_scene& s, Ray ray, uint32_t& seed, int maxDepth, int russian,
   prd.throughput = mk(1.f);
   prd.radiance = mk(0.f);
   prd.isSpecular = false;
+  prd.last_pdf = 0.f;
   bool previousHitSpecular = false;
   for (int depth = 0; depth < maxDepth; depth++) {
     Hit h = closest_hit(s, ray, &cn.nodes, &cn.prims);
     cn.closest++;
     cn.bounces++;
+    const float pdf_in = prd.last_pdf;
+    prd.last_pdf = 0.f;
     if (h.prim >= 0)
       closest_hit_program(s, ray, h, prd, cn);
     else
       miss_program(s, ray, prd);
-    if (prd.scatterEvent == rayMissed)
+    if (prd.scatterEvent == rayMissed) {
+      if (env_nee_active(s)) {  // NEW estimator: MIS weight against the env pdf, no clamp
+        float w = 1.f;
+        if (pdf_in > 0.f) w = PowerHeuristic(1, pdf_in, 1, env_pdf_dir(s, ray.d));
+        return prd.radiance + prd.throughput * w;
+      }
       return prd.radiance + clamp3(prd.throughput, 0.f, 1.f);
+    }
     else if (prd.scatterEvent == rayHitLight) {
       if (depth == 0 || previousHitSpecular) prd.radiance += prd.throughput;
       return prd.radiance;

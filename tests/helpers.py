@@ -459,7 +459,7 @@ def synthetic_hdri(w=256, h=128, peak=0.5):
     return img
 
 
-def build_mesh_scene(grid=32, W=64, H=64, lib=None, normals=False, mat_kind=None, env=True):
+def build_mesh_scene(grid=32, W=64, H=64, lib=None, normals=False, mat_kind=None, env=True, env_nee=False):
     """Config C4 shape: procedural triangle mesh lit by a synthetic HDRI environment map."""
     s = pt.Scene(lib)
     texs = [tex_const(0.7, 0.7, 0.7)]
@@ -472,7 +472,7 @@ def build_mesh_scene(grid=32, W=64, H=64, lib=None, normals=False, mat_kind=None
     s.set_camera(make_camera([0, 4.5, -9], [0, 0, 0], [0, 1, 0], 40.0, W / H, 0.0, 10.0))
     if env:
         img = s.add_image(synthetic_hdri())
-        s.set_miss(pt.Miss(pt.MISS_HDR, pt.F3(0, 0, 0), pt.F3(0, 0, 0), img, 1, 0))
+        s.set_miss(pt.Miss(pt.MISS_HDR, pt.F3(0, 0, 0), pt.F3(0, 0, 0), img, 1, int(env_nee)))
     else:
         s.set_miss(pt.Miss(pt.MISS_GRADIENT, pt.F3(1, 1, 1), pt.F3(0.5, 0.7, 1.0), -1, 1, 0))
     return s

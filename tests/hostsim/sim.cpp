@@ -174,6 +174,12 @@ Sim* sim_create(const pt_scene_desc* desc, int refine) {
   d.texvec = desc->texvec;
   d.images = s->images.data();
   d.lights = desc->lights;
+  d.env_alias_prob = desc->env_alias_prob;
+  d.env_alias_idx = desc->env_alias_idx;
+  d.env_texel_pdf = desc->env_texel_pdf;
+  d.env_n = desc->env_n;
+  d.env_w = desc->env_n ? desc->images[desc->miss.image].width : 0;
+  d.env_h = desc->env_n ? desc->images[desc->miss.image].height : 0;
   d.n_prims = n;
   d.n_materials = desc->n_materials;
   d.n_textures = desc->n_textures;
@@ -281,6 +287,7 @@ int sim_render(const Sim* s, int W, int H, int first_frame, int nframes, int max
         camera_ray(sc.camera, W, H, x, y, f, seed, o, d);
         (void)pt_rnd(seed);
         float3 thr = f3(1.f), rad = f3(0.f);
+        float last_pdf = 0.f;
         bool spec = false;
         int depth = 0;
         float3 col = f3(0.f);
@@ -290,7 +297,7 @@ int sim_render(const Sim* s, int W, int H, int first_frame, int nframes, int max
           uint32_t a = 0, b = 0;
           bvh8_closest<false>(sc, o, d, depth == 0 ? 1e-6f : 1e-3f, PT_RAY_MAX, h, a, b);
           PathIn in;
-          in.o = o; in.d = d; in.thr = thr; in.rad = rad; in.seed = seed; in.depth = depth; in.prev_specular = spec;
+          in.o = o; in.d = d; in.thr = thr; in.rad = rad; in.seed = seed; in.depth = depth; in.prev_specular = spec; in.last_pdf = last_pdf;
           if (h.leaf < 0) {
             col = shade_miss(sc, in);
             break;
@@ -308,7 +315,8 @@ int sim_render(const Sim* s, int W, int H, int first_frame, int nframes, int max
           if (out.kind == SH_SHADOW) {
             TraceHit sh;
             bvh8_closest<false>(sc, out.P, out.WiL, 1e-3f, PT_RAY_MAX, sh, a, b);
-            bool vis = sh.leaf >= 0 && (pt_f2u(sc.leaves[sh.leaf].c.w) >> 24) == PT_MAT_DIFFUSE_LIGHT;
+            bool vis = out.env_shadow ? sh.leaf < 0
+                                      : (sh.leaf >= 0 && (pt_f2u(sc.leaves[sh.leaf].c.w) >> 24) == PT_MAT_DIFFUSE_LIGHT);
             if (vis) { nd = out.dir; nthr = out.thr; nrad = out.rad; nseed = out.seed; }
             else { nd = out.dirS; nthr = out.thrS; nrad = out.radS; nseed = out.seedS; }
             nspec = false;
@@ -335,7 +343,7 @@ int sim_render(const Sim* s, int W, int H, int first_frame, int nframes, int max
             col = f3(0.f);
             break;
           }
-          o = out.P; d = nd; thr = nthr; rad = nrad; seed = nseed; spec = nspec;
+          o = out.P; d = nd; thr = nthr; rad = nrad; seed = nseed; spec = nspec; last_pdf = out.pdf;
         }
         col = pt_de_nan(col);
         float* px = accum + 4 * ((size_t)(H - 1 - y) * W + x);
