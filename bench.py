@@ -42,7 +42,31 @@ WORKLOADS = {
 FACADE_IDS = {"c1": 2, "c2": 0, "c3": 5, "c4": 6}   # scene functions in host_includes/scenes.hpp
 
 
+class _StdoutToStderr:
+    """The facade's scene functions printf progress like the reference does; bench.py must print
+    exactly one JSON line on stdout, so C-level stdout is pointed at stderr while they run."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def __exit__(self, *a):
+        try:
+            import ctypes
+            ctypes.CDLL(None).fflush(None)
+        except Exception:
+            pass
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
 def build_scene(h, name, W, H, lib=None):
+    with _StdoutToStderr():
+        return _build_scene(h, name, W, H, lib)
+
+
+def _build_scene(h, name, W, H, lib=None):
     """Scenes come from the C++ host facade's scene functions (InOneWeekend, Cornell, ... — the
     reference's scene-building surface); the numpy builders are the fallback if it is not built."""
     pt = h.pt
@@ -307,8 +331,15 @@ def main():
         except Exception:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
+        traffic = None
+        try:   # DRAM bytes per launch from the committed ncu capture, scaled to this run's rays per launch
+            tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(args.workload)
+            if tr:
+                traffic = tr["dram_bytes"] / tr["rays"] * (stt.closest_rays / max(1, stt.iterations))
+        except Exception:
+            pass
         roof = {"bound": "hbm", "kernel": "k_trace<closest>", "achieved": ach, "peak": peak, "unit": "GB/s",
-                "frac": ach / peak, "traffic": None,
+                "frac": ach / peak, "traffic": traffic,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "6.65 TB/s (of fallback)",
                 "bytes_per_ray": b_ray, "nodes_per_ray": n_node, "leaves_per_ray": n_leaf,
                 "rays_per_launch": stt.closest_rays / max(1, stt.iterations),
