@@ -97,7 +97,12 @@ enum {
   PT_TEX_CONSTANT = 0, /* color                                               */
   PT_TEX_CHECKER = 1,  /* a=odd texture id, b=even texture id                 */
   PT_TEX_IMAGE = 2,    /* a=image id (bilinear, repeat, normalised coords)    */
-  PT_TEX_VECTOR = 3    /* a=first entry in the texture-vector table, b=count  */
+  PT_TEX_VECTOR = 3,   /* a=first entry in the texture-vector table, b=count  */
+  PT_TEX_NOISE = 4,    /* Perlin turbulence (noise_texture.cu): color[0]=scale, a=offset into the
+                          texture-data table of 768 gradient floats (ranvec) followed by
+                          3x256 permutation entries (perm_x, perm_y, perm_z), b=axis (recorded;
+                          the reference's switch falls through, so Z is always used)          */
+  PT_TEX_GRADIENT = 5  /* gradient_texture.cu: a=offset of 9 floats (colorA,colorB,colorC)   */
 };
 
 typedef struct pt_texture {
@@ -203,6 +208,8 @@ typedef struct pt_scene_desc {
   const pt_texture* textures;
   int32_t n_texvec;
   const int32_t* texvec;     /* texture-vector table (programs/textures/vector.cu) */
+  int32_t n_texdata;
+  const float* texdata;      /* float table for noise / gradient textures          */
   int32_t n_images;
   const pt_image* images;
   int32_t n_lights;
@@ -257,6 +264,9 @@ int pt_scene_add_mesh(pt_scene* scene, const float* v, const float* n, const flo
 int pt_scene_set_materials(pt_scene* scene, const pt_material* m, int32_t n);
 int pt_scene_set_textures(pt_scene* scene, const pt_texture* t, int32_t n);
 int pt_scene_set_texture_vector(pt_scene* scene, const int32_t* texture_ids, int32_t n);
+/* replaces Noise_Texture's ranvec/perm_x/perm_y/perm_z buffers and Gradient_Texture's colours
+ * (host_includes/textures.hpp:64-108,236-252): one float table, textures index into it */
+int pt_scene_set_texture_data(pt_scene* scene, const float* data, int32_t n);
 /* replaces Image_Texture::loadTexture / HDR_Texture::loadHDRTexture buffers
  * (host_includes/textures.hpp:115-165,178-217): RGBA float, row 0 first. */
 int pt_scene_add_image(pt_scene* scene, const float* rgba, int32_t width, int32_t height,

@@ -27,7 +27,7 @@ X_AXIS, Y_AXIS, Z_AXIS = 0, 1, 2
 PRIM_TRIANGLE, PRIM_SPHERE, PRIM_RECT, PRIM_BOX = 0, 1, 2, 3
 (MAT_LAMBERTIAN, MAT_METAL, MAT_DIELECTRIC, MAT_DIFFUSE_LIGHT, MAT_OREN_NAYAR,
  MAT_TORRANCE_SPARROW, MAT_ASHIKHMIN_SHIRLEY, MAT_NORMAL) = range(8)
-TEX_CONSTANT, TEX_CHECKER, TEX_IMAGE, TEX_VECTOR = 0, 1, 2, 3
+TEX_CONSTANT, TEX_CHECKER, TEX_IMAGE, TEX_VECTOR, TEX_NOISE, TEX_GRADIENT = 0, 1, 2, 3, 4, 5
 MISS_GRADIENT, MISS_CONSTANT, MISS_IMG, MISS_HDR = 0, 1, 2, 3
 FLAG_COUNT_FETCHES, FLAG_TIME_KERNELS = 1, 2
 
@@ -105,6 +105,7 @@ class SceneDesc(C.Structure):
         ("n_materials", C.c_int32), ("materials", C.POINTER(Material)),
         ("n_textures", C.c_int32), ("textures", C.POINTER(Texture)),
         ("n_texvec", C.c_int32), ("texvec", C.POINTER(C.c_int32)),
+        ("n_texdata", C.c_int32), ("texdata", C.POINTER(C.c_float)),
         ("n_images", C.c_int32), ("images", C.POINTER(Image)),
         ("n_lights", C.c_int32), ("lights", C.POINTER(Light)),
         ("camera", Camera), ("miss", Miss),
@@ -138,6 +139,7 @@ ABI_SYMBOLS = [
     "pt_last_error", "pt_abi_version", "pt_scene_create", "pt_scene_destroy",
     "pt_scene_add_spheres", "pt_scene_add_rects", "pt_scene_add_boxes", "pt_scene_add_mesh",
     "pt_scene_set_materials", "pt_scene_set_textures", "pt_scene_set_texture_vector",
+    "pt_scene_set_texture_data",
     "pt_scene_add_image", "pt_scene_set_lights", "pt_scene_set_camera", "pt_scene_set_miss",
     "pt_scene_commit", "pt_scene_get_desc", "pt_scene_bvh_info", "pt_trace_rays",
     "pt_trace_rays_device", "pt_renderer_create", "pt_renderer_destroy", "pt_render",
@@ -176,6 +178,7 @@ def load(path: Optional[str] = None) -> C.CDLL:
         "pt_scene_set_materials": [vp, vp, i32],
         "pt_scene_set_textures": [vp, vp, i32],
         "pt_scene_set_texture_vector": [vp, vp, i32],
+        "pt_scene_set_texture_data": [vp, vp, i32],
         "pt_scene_add_image": [vp, vp, i32, i32, P(i32)],
         "pt_scene_set_lights": [vp, vp, i32],
         "pt_scene_set_camera": [vp, P(Camera)],
@@ -291,6 +294,10 @@ class Scene:
     def set_texture_vector(self, ids):
         a = np.ascontiguousarray(ids, dtype=np.int32)
         _check(self.lib, self.lib.pt_scene_set_texture_vector(self.h, _ptr(a), a.size))
+
+    def set_texture_data(self, data):
+        a = np.ascontiguousarray(data, dtype=np.float32)
+        _check(self.lib, self.lib.pt_scene_set_texture_data(self.h, _ptr(a), a.size))
 
     def add_image(self, rgba) -> int:
         a = _f32(rgba)

@@ -325,6 +325,12 @@ int pt_scene_set_texture_vector(pt_scene* s, const int32_t* ids, int32_t n) {
   s->committed = false;
   return PT_OK;
 }
+int pt_scene_set_texture_data(pt_scene* s, const float* data, int32_t n) {
+  if (!s || n < 0 || (n > 0 && !data)) return PT_ERR_INVALID;
+  s->texdata.assign(data, data + n);
+  s->committed = false;
+  return PT_OK;
+}
 int pt_scene_add_image(pt_scene* s, const float* rgba, int32_t w, int32_t h, int32_t* image_id) {
   if (!s || !rgba || w <= 0 || h <= 0) {
     pt_set_error("pt_scene_add_image: bad arguments");
@@ -404,6 +410,15 @@ int pt_scene_commit(pt_scene* s) {
       pt_set_error("vector texture range outside the texture-vector table");
       return PT_ERR_INVALID;
     }
+    if ((t.type == PT_TEX_NOISE && (t.a < 0 || t.a + 1536 > (int)s->texdata.size())) ||
+        (t.type == PT_TEX_GRADIENT && (t.a < 0 || t.a + 9 > (int)s->texdata.size()))) {
+      pt_set_error("noise/gradient texture data outside the texture-data table");
+      return PT_ERR_INVALID;
+    }
+    if (t.type < PT_TEX_CONSTANT || t.type > PT_TEX_GRADIENT) {
+      pt_set_error("unknown texture type %d", t.type);
+      return PT_ERR_INVALID;
+    }
   }
   int rc;
   if ((rc = upload_vec(s->d_prim_ref, s->prims))) return rc;
@@ -418,6 +433,7 @@ int pt_scene_commit(pt_scene* s) {
   if ((rc = upload_vec(s->d_materials, s->materials))) return rc;
   if ((rc = upload_vec(s->d_textures, s->textures))) return rc;
   if ((rc = upload_vec(s->d_texvec, s->texvec))) return rc;
+  if ((rc = upload_vec(s->d_texdata, s->texdata))) return rc;
   if ((rc = upload_vec(s->d_lights, s->lights))) return rc;
   for (auto* b : s->d_image_texels) delete b;
   s->d_image_texels.clear();
@@ -453,6 +469,7 @@ int pt_scene_commit(pt_scene* s) {
   d.materials = s->d_materials.as<pt_material>();
   d.textures = s->d_textures.as<pt_texture>();
   d.texvec = s->d_texvec.as<int>();
+  d.texdata = s->d_texdata.as<float>();
   d.images = s->d_images.as<ImageDev>();
   d.lights = s->d_lights.as<pt_light>();
   d.env_alias_prob = s->d_env_prob.as<float>();
@@ -465,6 +482,7 @@ int pt_scene_commit(pt_scene* s) {
   d.n_materials = nm;
   d.n_textures = (int)s->textures.size();
   d.n_texvec = (int)s->texvec.size();
+  d.n_texdata = (int)s->texdata.size();
   d.n_images = (int)s->images.size();
   d.n_lights = (int)s->lights.size();
   d.camera = s->camera;
@@ -498,6 +516,8 @@ int pt_scene_get_desc(const pt_scene* cs, pt_scene_desc* o) {
   o->textures = s->textures.data();
   o->n_texvec = (int)s->texvec.size();
   o->texvec = s->texvec.data();
+  o->n_texdata = (int)s->texdata.size();
+  o->texdata = s->texdata.data();
   s->image_descs.clear();
   for (const HostImage& im : s->images) s->image_descs.push_back(pt_image{im.width, im.height, im.rgba.data()});
   o->n_images = (int)s->image_descs.size();

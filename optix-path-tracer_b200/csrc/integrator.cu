@@ -61,6 +61,7 @@ struct alignas(128) Ctrl {
   PaddedInt bin_count[NBINS];
   alignas(128) unsigned long long stat_nodes;
   alignas(128) unsigned long long stat_leaves;
+  alignas(128) int error;  // 1 = traversal stack overflow
 };
 #define n_next n_next_.v
 #define n_shadow n_shadow_.v
@@ -199,7 +200,7 @@ __global__ void __launch_bounds__(PT_TRACE_THREADS) k_trace(SceneDev sc, Ctrl* c
   __shared__ uint2 s_stack[PT_SMEM_STACK * PT_TRACE_THREADS];
   ClosestPolicy pol{sc, c, cur, hits, bin_q, pool};
   uint32_t cn = 0, cl = 0;
-  trace_persistent<COUNT>(sc, c->n_cur, &c->fetch_closest, pol, s_stack, sched, cn, cl);
+  trace_persistent<COUNT>(sc, c->n_cur, &c->fetch_closest, pol, s_stack, sched, &c->error, cn, cl);
   if (COUNT) {
     for (int o = 16; o > 0; o >>= 1) {
       cn += __shfl_xor_sync(0xffffffffu, cn, o);
@@ -325,7 +326,7 @@ __global__ void __launch_bounds__(PT_TRACE_THREADS) k_shadow(SceneDev sc, Params
   __shared__ uint2 s_stack[PT_SMEM_STACK * PT_TRACE_THREADS];
   ShadowPolicy pol{sc, p, c, next, sb};
   uint32_t cn = 0, cl = 0;
-  trace_persistent<COUNT>(sc, c->n_shadow, &c->fetch_shadow, pol, s_stack, sched, cn, cl);
+  trace_persistent<COUNT>(sc, c->n_shadow, &c->fetch_shadow, pol, s_stack, sched, &c->error, cn, cl);
   if (COUNT) {
     for (int o = 16; o > 0; o >>= 1) {
       cn += __shfl_xor_sync(0xffffffffu, cn, o);
@@ -338,7 +339,7 @@ __global__ void __launch_bounds__(PT_TRACE_THREADS) k_shadow(SceneDev sc, Params
   }
 }
 
-// standalone traversal of a ray set (pt_trace_rays); counters: [0] nodes, [1] leaves, [2] fetch cursor
+// standalone traversal of a ray set (pt_trace_rays); counters: [0] nodes, [1] leaves, [2] fetch cursor, [3] error flag
 struct RaySetPolicy {
   const pt_ray* rays;
   pt_hit* hits;
@@ -368,7 +369,7 @@ __global__ void __launch_bounds__(PT_TRACE_THREADS) k_trace_rays(SceneDev sc, co
   __shared__ uint2 s_stack[PT_SMEM_STACK * PT_TRACE_THREADS];
   RaySetPolicy pol{rays, hits};
   uint32_t cn = 0, cl = 0;
-  trace_persistent<COUNT>(sc, n, (int*)(counters + 2), pol, s_stack, sched, cn, cl);
+  trace_persistent<COUNT>(sc, n, (int*)(counters + 2), pol, s_stack, sched, (int*)(counters + 3), cn, cl);
   if (COUNT) {
     for (int o = 16; o > 0; o >>= 1) {
       cn += __shfl_xor_sync(0xffffffffu, cn, o);
@@ -452,10 +453,8 @@ static int ensure_pool(pt_renderer* r, long long want) {
   if (pool <= r->pool) return PT_OK;
   r->pool = (int)pool;
   const size_t arr = (size_t)pool * 16;
-  size_t skew = 33 * 256;  // odd multiple of 256 B
-  size_t gap = 64 * 1024;
-  if (const char* e = getenv("PTB200_GAP")) gap = (size_t)atoll(e);    // dev: layout experiments
-  if (const char* e = getenv("PTB200_SKEW")) skew = (size_t)atoll(e);
+  const size_t skew = 33 * 256;  // odd multiple of 256 B
+  const size_t gap = 64 * 1024;
   const int n_arr = 4 + 4 + 7 + 1;
   const size_t total = (arr + gap + 7 * skew + 256) * n_arr + (size_t)pool * 4 * NBINS + 64 * 1024;
   PT_CUDA(r->slab.alloc(total));
@@ -671,6 +670,10 @@ int pt_render(pt_renderer* r, int32_t first_frame, int32_t nframes, int32_t max_
   if (timing)
     for (auto& ev : e) cudaEventDestroy(ev);
   const Ctrl& hc = *r->h_ctrl;
+  if (hc.error) {
+    pt_set_error("pt_render: BVH traversal stack overflow (tree deeper than %d node groups)", PT_STACK);
+    return PT_ERR_INVALID;
+  }
   r->stats.samples = (uint64_t)total;
   r->stats.closest_rays = hc.stat_closest;
   r->stats.shadow_rays = hc.stat_shadow + (uint64_t)hc.n_shadow;
@@ -758,7 +761,16 @@ int pt_trace_rays(pt_scene* scene, const pt_ray* rays, int64_t n, pt_hit* hits, 
                                                     dc.as<unsigned long long>(), sched_params());
   PT_CUDA(cudaGetLastError());
   PT_CUDA(cudaMemcpy(hits, dh.p, (size_t)n * sizeof(pt_hit), cudaMemcpyDeviceToHost));
-  if (counters) PT_CUDA(cudaMemcpy(counters, dc.p, 16, cudaMemcpyDeviceToHost));
+  unsigned long long hc[4];
+  PT_CUDA(cudaMemcpy(hc, dc.p, 32, cudaMemcpyDeviceToHost));
+  if (counters) {
+    counters[0] = hc[0];
+    counters[1] = hc[1];
+  }
+  if (hc[3]) {
+    pt_set_error("pt_trace_rays: BVH traversal stack overflow (tree deeper than %d node groups)", PT_STACK);
+    return PT_ERR_INVALID;
+  }
   return PT_OK;
 }
 

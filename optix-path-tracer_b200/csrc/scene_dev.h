@@ -48,6 +48,7 @@ struct SceneDev {
   const pt_material* materials;
   const pt_texture* textures;
   const int* texvec;
+  const float* texdata;
   const ImageDev* images;
   const pt_light* lights;
   // environment importance sampling (alias table over the texels of the HDR miss image)
@@ -55,7 +56,7 @@ struct SceneDev {
   const int* env_alias_idx;
   const float* env_texel_pdf;
   int env_n, env_w, env_h;
-  int n_prims, n_materials, n_textures, n_texvec, n_images, n_lights;
+  int n_prims, n_materials, n_textures, n_texvec, n_texdata, n_images, n_lights;
   pt_camera camera;
   pt_miss miss;
 };

@@ -71,6 +71,7 @@ struct pt_scene {
   std::vector<pt_material> materials;
   std::vector<pt_texture> textures;
   std::vector<int32_t> texvec;
+  std::vector<float> texdata;
   std::vector<HostImage> images;
   std::vector<pt_image> image_descs;
   std::vector<pt_light> lights;
@@ -84,7 +85,7 @@ struct pt_scene {
 
   // device side
   DevBuf d_prim_ref, d_spheres, d_rects, d_boxes, d_tri_v, d_tri_n, d_tri_uv, d_tri_tex, d_xforms;
-  DevBuf d_materials, d_textures, d_texvec, d_images, d_lights;
+  DevBuf d_materials, d_textures, d_texvec, d_texdata, d_images, d_lights;
   std::vector<DevBuf*> d_image_texels;
   DevBuf d_nodes8, d_leaves, d_prim_leaf, d_env_prob, d_env_idx, d_env_pdf;
   SceneDev dev{};

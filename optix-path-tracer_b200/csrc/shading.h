@@ -372,6 +372,36 @@ PT_HD float3 image_lookup(const ImageDev& im, float u, float v) {
   float3 bot = c01 + fx * (c11 - c01);
   return top + fy * (bot - top);
 }
+// Perlin noise: programs/textures/noise_texture.cu:12-60.  data: 768 floats ranvec, then
+// perm_x, perm_y, perm_z (256 entries each, stored as floats)
+PT_HD float perlin_noise(const float* data, float3 p) {
+  float u = p.x - floorf(p.x), v = p.y - floorf(p.y), w = p.z - floorf(p.z);
+  int i = (int)floorf(p.x), j = (int)floorf(p.y), k = (int)floorf(p.z);
+  float uu = u * u * (3 - 2 * u), vv = v * v * (3 - 2 * v), ww = w * w * (3 - 2 * w);
+  float accum = 0;
+  for (int di = 0; di < 2; di++)
+    for (int dj = 0; dj < 2; dj++)
+      for (int dk = 0; dk < 2; dk++) {
+        int idx = (int)data[768 + ((i + di) & 255)] ^ (int)data[1024 + ((j + dj) & 255)] ^ (int)data[1280 + ((k + dk) & 255)];
+        float3 c = f3(data[3 * idx], data[3 * idx + 1], data[3 * idx + 2]);
+        float3 weight_v = f3(u - di, v - dj, w - dk);
+        accum += (di * uu + (1 - di) * (1 - uu)) * (dj * vv + (1 - dj) * (1 - vv)) * (dk * ww + (1 - dk) * (1 - ww)) *
+                 dot(c, weight_v);
+      }
+  return accum;
+}
+PT_HD float perlin_turb(const float* data, float3 p) {  // noise_texture.cu:46-58
+  float accum = 0;
+  float3 temp_p = p;
+  float weight = 1.0f;
+  for (int i = 0; i < 7; i++) {
+    accum += weight * perlin_noise(data, temp_p);
+    weight *= 0.5f;
+    temp_p *= 2.f;
+  }
+  return fabsf(accum);
+}
+
 PT_HD float3 sample_texture(const SceneDev& sc, int tex, float u, float v, float3 p, int i) {
   for (int guard = 0; guard < 8; guard++) {
     if (tex < 0 || tex >= sc.n_textures) return f3(0.f);
@@ -388,6 +418,16 @@ PT_HD float3 sample_texture(const SceneDev& sc, int tex, float u, float v, float
       if (i >= t.b || i < 0) return f3(0.f);
       tex = sc.texvec[t.a + i];
       i = 0;
+    } else if (t.type == PT_TEX_NOISE) {
+      // noise_texture.cu:62-75: the axis switch falls through, so the Z expression always wins
+      const float scale = t.color[0];
+      float sinValue = sinf(scale * p.z + 5 * perlin_turb(sc.texdata + t.a, scale * p));
+      return f3(1.f) * 0.5f * (1 + sinValue);
+    } else if (t.type == PT_TEX_GRADIENT) {  // gradient_texture.cu:7-14
+      const float* g = sc.texdata + t.a;
+      const float3 ud = normalize(p);
+      const float x = fabsf(ud.x), y = fabsf(ud.y), z = fabsf(ud.z);
+      return x * f3(g[0], g[1], g[2]) + y * f3(g[3], g[4], g[5]) + z * f3(g[6], g[7], g[8]);
     } else {
       return f3(0.f);
     }

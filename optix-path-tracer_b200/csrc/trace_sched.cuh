@@ -34,7 +34,8 @@ struct SchedParams {
 
 template <bool COUNT, class Policy>
 __device__ __forceinline__ void trace_persistent(const SceneDev& sc, int n, int* fetch_counter, Policy& pol,
-                                                 uint2* s_stack, const SchedParams sp_, uint32_t& cn, uint32_t& cl) {
+                                                 uint2* s_stack, const SchedParams sp_, int* error_flag, uint32_t& cn,
+                                                 uint32_t& cl) {
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const unsigned lt_mask = (1u << lane) - 1u;
@@ -118,6 +119,7 @@ __device__ __forceinline__ void trace_persistent(const SceneDev& sc, int n, int*
           if (sp < PT_SMEM_STACK) my_stack[sp * PT_TRACE_THREADS] = rest;
           else if (sp < PT_STACK) lstack[sp - PT_SMEM_STACK] = rest;
           if (sp < PT_STACK) sp++;
+          else atomicExch(error_flag, 1);  // never silently wrong: the host turns this into an error
         }
       }
     }

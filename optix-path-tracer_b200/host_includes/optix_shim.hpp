@@ -178,6 +178,7 @@ class ContextObj {
   // recorded scene
   std::vector<pt_texture> textures;
   std::vector<int32_t> texvec;
+  std::vector<float> texdata;  // noise tables / gradient colours (pt_scene_set_texture_data)
   std::vector<pt_material> materials;
   std::vector<pt_light> lights;
   struct Image { int w, h; std::vector<float> rgba; };
@@ -232,6 +233,7 @@ class ContextObj {
     check(pt_scene_create(&scene));
     check(pt_scene_set_textures(scene, textures.data(), (int)textures.size()));
     check(pt_scene_set_texture_vector(scene, texvec.data(), (int)texvec.size()));
+    check(pt_scene_set_texture_data(scene, texdata.data(), (int)texdata.size()));
     check(pt_scene_set_materials(scene, materials.data(), (int)materials.size()));
     for (auto& im : images) check(pt_scene_add_image(scene, im.rgba.data(), im.w, im.h, nullptr));
     check(pt_scene_set_lights(scene, lights.data(), (int)lights.size()));
@@ -254,6 +256,7 @@ class ContextObj {
     check(pt_scene_create(&s));
     check(pt_scene_set_textures(s, textures.data(), (int)textures.size()));
     check(pt_scene_set_texture_vector(s, texvec.data(), (int)texvec.size()));
+    check(pt_scene_set_texture_data(s, texdata.data(), (int)texdata.size()));
     check(pt_scene_set_materials(s, materials.data(), (int)materials.size()));
     for (auto& im : images) check(pt_scene_add_image(s, im.rgba.data(), im.w, im.h, nullptr));
     check(pt_scene_set_lights(s, lights.data(), (int)lights.size()));

@@ -85,8 +85,8 @@ inline void InOneWeekend(App_State& app) {
 }
 
 // "The Next Week" moving-spheres scene.  Motion blur is broken in the reference
-// (hitables.hpp:130 FIXME) and it uses static Spheres too.  The earth image (JPEG) and the
-// Perlin noise texture are "next" rows: constant stand-ins keep the scene usable.
+// (hitables.hpp:130 FIXME) and it uses static Spheres too.  The earth image (JPEG decoding) is a
+// "next" row: a constant stand-in keeps the scene usable.
 inline void MovingSpheres(App_State& app) {
   using namespace scene_detail;
   auto t0 = std::chrono::system_clock::now();
@@ -117,7 +117,7 @@ inline void MovingSpheres(App_State& app) {
   float3 g = rnd3_rtl(1.f, 0.f);
   list.push(new Sphere(make_float3(4.f, 1.f, 1.f), 1.f,
                        new Dielectric(new Constant_Texture(1.f), new Constant_Texture(g.x, g.y, g.z), 1.5, 0.f)));
-  list.push(new Sphere(make_float3(0.f, 1.f, 1.5f), 1.f, new Metal(new Constant_Texture(0.6f, 0.45f, 0.35f), 0.f)));  // noise
+  list.push(new Sphere(make_float3(0.f, 1.f, 1.5f), 1.f, new Metal(new Noise_Texture(4.f), 0.f)));  // 'rusty' metal
   list.push(new AARect(3.f, 5.f, 1.f, 3.f, -0.5f, false, Z_AXIS, new Diffuse_Light(new Constant_Texture(4.f))));
   list.addElementsTo(group, app.context);
   finishScene(app, group, make_float3(13.f, 2.f, 3.f), make_float3(0.f), 20.f, 0.1f, 10.f, t0);
@@ -153,8 +153,8 @@ inline void Cornell(App_State& app) {
   finishScene(app, group, make_float3(278.f, 278.f, -800.f), make_float3(278.f, 278.f, 0.f), 40.f, 0.f, 10.f, t0);
 }
 
-// "The Next Week" final scene without the volumes (out of scope) and with constant
-// stand-ins for the earth image and the Perlin sphere ("next" rows)
+// "The Next Week" final scene without the volumes (out of scope) and with a constant
+// stand-in for the earth image (JPEG decoding is a "next" row)
 inline void Final_Next_Week(App_State& app) {
   using namespace scene_detail;
   auto t0 = std::chrono::system_clock::now();
@@ -179,7 +179,7 @@ inline void Final_Next_Week(App_State& app) {
   list.push(new Sphere(make_float3(0.f, 150.f, 145.f), 50.f, new Metal(new Constant_Texture(0.8f, 0.8f, 0.9f), 10.f)));
   list.push(new Sphere(make_float3(360.f, 150.f, 45.f), 70.f, glass));
   list.push(new Sphere(make_float3(400.f, 200.f, 400.f), 100.f, new Lambertian(new Constant_Texture(0.2f, 0.4f, 0.7f))));
-  list.push(new Sphere(make_float3(220.f, 280.f, 300.f), 80.f, new Lambertian(new Constant_Texture(0.6f, 0.6f, 0.6f))));
+  list.push(new Sphere(make_float3(220.f, 280.f, 300.f), 80.f, new Lambertian(new Noise_Texture(0.1f))));  // Perlin sphere
   Hitable_List spheres;
   BRDF* white = new Lambertian(new Constant_Texture(0.73f));
   for (int j = 0; j < 1000; j++) {

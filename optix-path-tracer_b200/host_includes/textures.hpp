@@ -53,10 +53,41 @@ struct Checker_Texture : public Texture {
   const Texture* even;
 };
 
-// Perlin noise: "next" row; declared for source compatibility
+// Perlin turbulence texture (host_includes/textures.hpp:64-108, programs/textures/noise_texture.cu).
+// The gradient and permutation tables are drawn from rnd() exactly like the reference does
+// (256 gradients, z component drawn first as g++/MSVC evaluate the argument list right to left,
+// then perm_x, perm_y, perm_z by Fisher-Yates) and stored in the context's texture-data table.
 struct Noise_Texture : public Texture {
   Noise_Texture(const float s, const AXIS ax = X_AXIS) : scale(s), ax(ax) {}
-  Program assignTo(Context&) const override { throw "Noise_Texture is not supported yet (SURVEY 8f)"; }
+  Program assignTo(Context& ctx) const override {
+    auto it = ctx->texture_cache.find(this);
+    pt_texture t{};
+    t.type = PT_TEX_NOISE;
+    t.color[0] = scale;
+    t.b = (int)ax;
+    if (it == ctx->texture_cache.end()) {
+      t.a = (int)ctx->texdata.size();
+      for (int i = 0; i < 256; ++i) {
+        float z = -1 + 2 * rnd(), y = -1 + 2 * rnd(), x = -1 + 2 * rnd();
+        float l = sqrtf(x * x + y * y + z * z);
+        ctx->texdata.push_back(x / l);
+        ctx->texdata.push_back(y / l);
+        ctx->texdata.push_back(z / l);
+      }
+      for (int table = 0; table < 3; table++) {
+        int p[256];
+        for (int i = 0; i < 256; i++) p[i] = i;
+        for (int i = 256 - 1; i > 0; i--) {
+          int target = int(rnd() * (i + 1));
+          int tmp = p[i];
+          p[i] = p[target];
+          p[target] = tmp;
+        }
+        for (int i = 0; i < 256; i++) ctx->texdata.push_back((float)p[i]);
+      }
+    }
+    return registerOnce(ctx, t);
+  }
   const float scale;
   const AXIS ax;
 };
@@ -102,10 +133,23 @@ struct HDR_Texture : public Texture {
   const std::string fileName;
 };
 
-// "next" row; declared for source compatibility
+// |unit(p)| weighted blend of three colours (host_includes/textures.hpp:236-252, gradient_texture.cu)
 struct Gradient_Texture : public Texture {
   Gradient_Texture(const float3& cA, const float3& cB, const float3& cC) : colorA(cA), colorB(cB), colorC(cC) {}
-  Program assignTo(Context&) const override { throw "Gradient_Texture is not supported yet (SURVEY 8f)"; }
+  Program assignTo(Context& ctx) const override {
+    auto it = ctx->texture_cache.find(this);
+    pt_texture t{};
+    t.type = PT_TEX_GRADIENT;
+    if (it == ctx->texture_cache.end()) {
+      t.a = (int)ctx->texdata.size();
+      for (const float3& c : {colorA, colorB, colorC}) {
+        ctx->texdata.push_back(c.x);
+        ctx->texdata.push_back(c.y);
+        ctx->texdata.push_back(c.z);
+      }
+    }
+    return registerOnce(ctx, t);
+  }
   const float3 colorA, colorB, colorC;
 };
 

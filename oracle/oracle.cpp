@@ -1068,6 +1068,49 @@ inline f3 image_lookup(const pt_image& im, float u, float v) {
   return top + fy * (bot - top);
 }
 
+// P/textures/noise_texture.cu:12-60 (ranvec / perm_x / perm_y / perm_z live in the texture-data table)
+inline float perlin_interp(f3 c[2][2][2], float u, float v, float w) {
+  float uu = u * u * (3 - 2 * u);
+  float vv = v * v * (3 - 2 * v);
+  float ww = w * w * (3 - 2 * w);
+  float accum = 0;
+  for (int i = 0; i < 2; i++)
+    for (int j = 0; j < 2; j++)
+      for (int k = 0; k < 2; k++) {
+        f3 weight_v = mk(u - i, v - j, w - k);
+        accum += (i * uu + (1 - i) * (1 - uu)) * (j * vv + (1 - j) * (1 - vv)) * (k * ww + (1 - k) * (1 - ww)) *
+                 dot(c[i][j][k], weight_v);
+      }
+  return accum;
+}
+inline float noise(const float* data, f3 p) {
+  float u = p.x - floorf(p.x);
+  float v = p.y - floorf(p.y);
+  float w = p.z - floorf(p.z);
+  int i = (int)floorf(p.x);
+  int j = (int)floorf(p.y);
+  int k = (int)floorf(p.z);
+  f3 c[2][2][2];
+  for (int di = 0; di < 2; di++)
+    for (int dj = 0; dj < 2; dj++)
+      for (int dk = 0; dk < 2; dk++) {
+        int idx = (int)data[768 + ((i + di) & 255)] ^ (int)data[1024 + ((j + dj) & 255)] ^ (int)data[1280 + ((k + dk) & 255)];
+        c[di][dj][dk] = ld3(data + 3 * idx);
+      }
+  return perlin_interp(c, u, v, w);
+}
+inline float turb(const float* data, f3 p) {
+  float accum = 0;
+  f3 temp_p = p;
+  float weight = 1.0f;
+  for (int i = 0; i < 7; i++) {
+    accum += weight * noise(data, temp_p);
+    weight *= 0.5f;
+    temp_p *= 2.f;
+  }
+  return fabsf(accum);
+}
+
 inline f3 sample_texture(const orc_scene& s, int tex, float u, float v, f3 p, int i) {
   for (int guard = 0; guard < 8; guard++) {
     if (tex < 0 || tex >= s.d.n_textures) return mk(0.f);
@@ -1089,6 +1132,17 @@ inline f3 sample_texture(const orc_scene& s, int tex, float u, float v, f3 p, in
         tex = s.d.texvec[t.a + i];
         i = 0;
         break;
+      case PT_TEX_NOISE: {  // noise_texture.cu:62-75: the axis switch falls through to the Z case
+        const float scale = t.color[0];
+        float sinValue = sinf(scale * p.z + 5 * turb(s.d.texdata + t.a, scale * p));
+        return mk(1.f) * 0.5f * (1 + sinValue);
+      }
+      case PT_TEX_GRADIENT: {  // gradient_texture.cu:7-14
+        const float* g = s.d.texdata + t.a;
+        const f3 unit_direction = normalize(p);
+        const float x = fabsf(unit_direction.x), y = fabsf(unit_direction.y), z = fabsf(unit_direction.z);
+        return x * ld3(g) + y * ld3(g + 3) + z * ld3(g + 6);
+      }
       default:
         return mk(0.f);
     }

@@ -172,6 +172,8 @@ Sim* sim_create(const pt_scene_desc* desc, int refine) {
   d.materials = desc->materials;
   d.textures = desc->textures;
   d.texvec = desc->texvec;
+  d.texdata = desc->texdata;
+  d.n_texdata = desc->n_texdata;
   d.images = s->images.data();
   d.lights = desc->lights;
   d.env_alias_prob = desc->env_alias_prob;

@@ -287,3 +287,17 @@ def test_env_importance_sampling_parity(lib):
     r2.render(0, n)
     b = r2.read_accum()[..., :3] / n
     assert abs(g.mean() - b.mean()) <= 0.02 * b.mean()
+
+
+def test_noise_gradient_checker_textures(lib):
+    """Perlin noise / gradient / checker textures (programs/textures/*.cu) on the GPU vs the oracle."""
+    import test_hostsim
+    sc = test_hostsim._noise_scene(64, 64)
+    sc.commit()
+    r = pt.Renderer(sc, 64, 64)
+    r.render(0, 4)
+    g = r.read_accum()
+    a, _ = h.OracleScene(sc).render(64, 64, 0, 4)
+    d = np.abs(g[..., :3] - a[..., :3]).max(axis=-1)
+    assert (d > 1e-3).mean() <= 0.02
+    assert abs(g[..., :3].mean() - a[..., :3].mean()) <= 0.01 * a[..., :3].mean()
