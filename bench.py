@@ -36,10 +36,12 @@ WORKLOADS = {
     "c3": ("C3 Cornell + glass sphere + Oren-Nayar/Torrance-Sparrow/Ashikhmin-Shirley, RR, 1024x1024 @ 1024 spp",
            1024, 1024, 1024),
     "c4": ("C4 procedural 1M-triangle mesh + synthetic HDRI env map 1920x1080 @ 512 spp", 1920, 1080, 512),
+    # the multi-GPU configuration: 4096 spp are SPLIT across the ranks (strong scaling)
+    "c5": ("C5 procedural 1M-triangle mesh + HDRI 3840x2160 @ 4096 spp, sample-split across ranks", 3840, 2160, 4096),
 }
 
 
-FACADE_IDS = {"c1": 2, "c2": 0, "c3": 5, "c4": 6}   # scene functions in host_includes/scenes.hpp
+FACADE_IDS = {"c1": 2, "c2": 0, "c3": 5, "c4": 6, "c5": 6}   # scene functions in host_includes/scenes.hpp
 
 
 class _StdoutToStderr:
@@ -79,7 +81,7 @@ def _build_scene(h, name, W, H, lib=None):
         return h.build_spheres(22, seed=0, W=W, H=H, lib=lib)
     if name == "c3":
         return h.build_material_zoo(W, H, lib)
-    if name == "c4":
+    if name in ("c4", "c5"):
         return h.build_mesh_scene(708, W, H, lib)
     raise SystemExit(f"unknown workload {name}")
 
@@ -222,7 +224,13 @@ def main():
         r.set_pool(args.pool)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
     from optix_path_tracer_b200 import multigpu
-    first, _ = multigpu.frame_range(rank, world, spp)
+    strong = args.workload == "c5"
+    total_spp = spp
+    if strong:   # C5: the 4096 spp are split over the ranks
+        first, spp = multigpu.split_frames(total_spp, rank, world)
+    else:        # weak scaling: every rank renders the full spp with its own frame indices
+        first, _ = multigpu.frame_range(rank, world, spp)
+        total_spp = spp * world
 
     def step():
         """one pass of the hot path over one batch; returns device ms"""
@@ -267,11 +275,11 @@ def main():
         tsum = t.clone()
         dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
         ms_dev, rays = float(tmax[0]), float(tsum[1])
-    samples_total = float(W) * H * spp * args.steps * world
+    samples_total = float(W) * H * total_spp * args.steps
     value = samples_total / (ms_dev * 1e-3) / 1e6
     final = accum.cpu().numpy() if rank == 0 else None
     if rank == 0:
-        assert multigpu.check_sample_count(final, spp * world), "accumulation .w integrity check failed"
+        assert multigpu.check_sample_count(final, total_spp), "accumulation .w integrity check failed"
 
     # ---- e2e: host buffers -> C ABI -> host result -------------------------------------------------
     e2e_steps = max(1, min(args.steps, 3))
@@ -306,7 +314,7 @@ def main():
     te = torch.tensor([t_e2e], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_val = float(W) * H * spp * e2e_steps * world / float(te[0]) / 1e6
+    e2e_val = float(W) * H * total_spp * e2e_steps / float(te[0]) / 1e6
 
     # ---- roofline of the dominant kernel (closest-hit traversal), separate instrumented passes ----
     roof = None
@@ -360,16 +368,17 @@ def main():
                         "sample": f"{W}x{H} @ {n_spp} spp of the same workload (oracle, OpenMP over scanlines)",
                         "mrays_per_s": (ost.closest_rays + ost.shadow_rays) / dt / 1e6}
             # converged-image agreement on the sample (independent of the timing)
-            gi = np.sqrt(np.clip(final[..., :3] / (spp * world), 0, 1))
+            gi = np.sqrt(np.clip(final[..., :3] / total_spp, 0, 1))
             oi = np.sqrt(np.clip(ref_acc[..., :3] / n_spp, 0, 1))
             cpu_base["rmse_vs_gpu_gamma"] = h.rmse(gi, oi)
 
     if rank == 0:
         out = {
             "metric": "Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps,
-            "warmup": warm, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": warm, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
+            "scaling": "strong" if strong else "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": desc, "width": W, "height": H, "spp": spp, "max_depth": 50, "russian": True,
+            "config": {"workload": desc, "width": W, "height": H, "spp": total_spp if strong else spp, "max_depth": 50, "russian": True,
                        "l2": "flushed between timed steps (256 MiB write); path pool >> L2",
                        "prims": info.n_prims, "bvh8_nodes": info.n_bvh8_nodes, "parallelism": f"sample-split x{world}"},
             "mrays_per_s": rays / (ms_dev * 1e-3) / 1e6,

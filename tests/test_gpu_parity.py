@@ -301,3 +301,53 @@ def test_noise_gradient_checker_textures(lib):
     d = np.abs(g[..., :3] - a[..., :3]).max(axis=-1)
     assert (d > 1e-3).mean() <= 0.02
     assert abs(g[..., :3].mean() - a[..., :3].mean()) <= 0.01 * a[..., :3].mean()
+
+
+def test_two_lights_nee_parity(lib):
+    """numLights = 2: light picking (light_sample.cuh:48), NEE from a light surface
+    (diffuse_light.cu:41 with isLight=true) and its shadow ray, against the oracle."""
+    def extra(s, texs, mats):
+        pass
+    sc = h.build_cornell(48, 48, lib, extra)
+    # second emitter on the floor, facing up, plus its sampler entry
+    sc.add_rects([pt.Rect(100, 200, 100, 200, 1.0, pt.Y_AXIS, 0)], [3])
+    sc.set_lights([pt.Light(0, pt.Y_AXIS, 213, 343, 227, 332, 554, pt.F3(7, 7, 7)),
+                   pt.Light(0, pt.Y_AXIS, 100, 200, 100, 200, 1.0, pt.F3(3, 3, 3))])
+    sc.commit()
+    r = pt.Renderer(sc, 48, 48)
+    r.render(0, 6)
+    g = r.read_accum()
+    a, st = h.OracleScene(sc).render(48, 48, 0, 6)
+    d = np.abs(g[..., :3] - a[..., :3]).max(axis=-1)
+    assert (d > 1e-3).mean() <= 0.02
+    assert abs(g[..., :3].mean() - a[..., :3].mean()) <= 0.01 * a[..., :3].mean()
+    assert abs(int(r.stats().shadow_rays) - int(st.shadow_rays)) <= 0.01 * st.shadow_rays + 8
+
+
+def test_cli_renders_png(lib, tmp_path):
+    """Headless CLI (app/main.cpp: the reference's main.cpp flow without the GUI): scene function ->
+    facade -> C ABI -> GPU -> Save_PNG; the image must match the oracle's tonemapped render."""
+    import os
+    import subprocess
+    from PIL import Image
+    exe = os.path.join(h.PKG_DIR, "csrc", "ptb200_render")
+    if not os.path.exists(exe):
+        subprocess.run(["make", "ptb200_render"], cwd=os.path.join(h.PKG_DIR, "csrc"), check=True)
+    out = str(tmp_path / "cornell")
+    res = subprocess.run([exe, "--scene", "2", "--width", "64", "--height", "64", "--samples", "32", "--file", out],
+                         capture_output=True, text=True)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert "Render time" in res.stdout and "BVH Building Time" in res.stdout
+    img = np.array(Image.open(out + ".png")).astype(int)
+    assert img.shape == (64, 64, 3)
+    sc = h.build_cornell(64, 64, lib)
+    a, _ = h.OracleScene(sc).render(64, 64, 0, 32)
+    ref = pt.tonemap_png8(a, 32).astype(int)
+    assert np.abs(img - ref).mean() <= 0.5
+    # one-launch-per-sample mode (the reference's loop, main.cpp:264-293) gives the same picture
+    res = subprocess.run([exe, "--scene", "2", "--width", "64", "--height", "64", "--samples", "8", "--batch", "1",
+                          "--file", out + "_b1"], capture_output=True, text=True)
+    assert res.returncode == 0, res.stdout + res.stderr
+    img1 = np.array(Image.open(out + "_b1.png")).astype(int)
+    a8, _ = h.OracleScene(sc).render(64, 64, 0, 8)
+    assert np.abs(img1 - pt.tonemap_png8(a8, 8).astype(int)).mean() <= 0.5
