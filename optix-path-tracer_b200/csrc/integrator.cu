@@ -19,6 +19,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <vector>
 
 #include "scene_host.h"
@@ -47,21 +48,26 @@ struct ShadowBuf {  // 112 B / shadow request
 // tails, bin counters and fetch cursors are hammered by warp-aggregated atomics from all SMs while
 // other fields are read as loop bounds, and sharing L2 lines between them (or with whatever small
 // allocation happens to be adjacent) made whole kernels up to 50 % slower depending on placement.
-struct alignas(128) PaddedInt {
+#ifndef PT_CTR_STRIDE
+#define PT_CTR_STRIDE 1024  // measured: 128/256/512-B spacing still left +-5 % placement luck (L2 atomic units pair
+                            // neighbouring lines); at 1 KiB the C1 throughput no longer depends on where Ctrl lands
+#endif
+struct alignas(PT_CTR_STRIDE) PaddedInt {
   int v;
-  int pad[31];
+  int pad[PT_CTR_STRIDE / 4 - 1];
 };
-struct alignas(128) Ctrl {
+struct alignas(PT_CTR_STRIDE) Ctrl {
   // written by k_iter_begin only, read as loop bounds
   int n_cur, gen_base, gen_n;
+  int first_frame;
   unsigned long long sample_base, next_sample, total_samples;
   unsigned long long stat_closest, stat_shadow, stat_iters;
   // atomics
   PaddedInt n_next_, n_shadow_, fetch_closest_, fetch_shadow_;
   PaddedInt bin_count[NBINS];
-  alignas(128) unsigned long long stat_nodes;
-  alignas(128) unsigned long long stat_leaves;
-  alignas(128) int error;  // 1 = traversal stack overflow
+  alignas(PT_CTR_STRIDE) unsigned long long stat_nodes;
+  alignas(PT_CTR_STRIDE) unsigned long long stat_leaves;
+  alignas(PT_CTR_STRIDE) int error;  // 1 = traversal stack overflow
 };
 #define n_next n_next_.v
 #define n_shadow n_shadow_.v
@@ -69,7 +75,7 @@ struct alignas(128) Ctrl {
 #define fetch_shadow fetch_shadow_.v
 
 struct Params {
-  int W, H, first_frame, max_depth, russian, pool;
+  int W, H, max_depth, russian, pool;  // (the first frame index lives in Ctrl so captured graphs stay valid)
   float4* accum;
 };
 
@@ -146,7 +152,7 @@ __global__ void k_generate(SceneDev sc, Params p, const Ctrl* c, PathBuf cur) {
   const unsigned long long npix = (unsigned long long)p.W * p.H;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     unsigned long long sid = sbase + (unsigned long long)i;
-    int frame = p.first_frame + (int)(sid / npix);
+    int frame = c->first_frame + (int)(sid / npix);
     uint32_t pix = (uint32_t)(sid % npix);
     int x = pix % p.W, y = pix / p.W;
     uint32_t seed;
@@ -396,9 +402,10 @@ int sm_count() {
 // scheduler knobs; PTB200_REFILL_MIN / PTB200_LEAF_THRESH override the tuned defaults (dev only)
 SchedParams sched_params() {
   static SchedParams p = [] {
-    SchedParams q{12, 8};
+    SchedParams q{12, 8, 0};
     if (const char* e = getenv("PTB200_REFILL_MIN")) q.refill_min = std::max(1, atoi(e));
     if (const char* e = getenv("PTB200_LEAF_THRESH")) q.leaf_thresh = std::max(1, atoi(e));
+    if (const char* e = getenv("PTB200_FETCH_CHUNK")) q.fetch_chunk = std::max(0, atoi(e));
     return q;
   }();
   return p;
@@ -440,6 +447,11 @@ struct pt_renderer {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool started = false;
+  // the wavefront iteration captured as two CUDA graphs (pools A->B and B->A), reused across
+  // pt_render calls while the launch parameters stay the same
+  cudaGraphExec_t gexec[2] = {nullptr, nullptr};
+  int g_max_depth = -1, g_russian = -1, g_pool = -1, g_flags = -1, g_launches = 0;
+  SceneDev g_scene{};  // kernel arguments are baked into the graphs: re-capture when they change
   pt_stats stats{};
   Ctrl* h_ctrl = nullptr;  // pinned
 };
@@ -523,6 +535,8 @@ int pt_renderer_destroy(pt_renderer* r) {
   if (r->ev0) cudaEventDestroy(r->ev0);
   if (r->ev1) cudaEventDestroy(r->ev1);
   if (r->h_ctrl) cudaFreeHost(r->h_ctrl);
+  for (auto& g : r->gexec)
+    if (g) cudaGraphExecDestroy(g);
   delete r;
   return PT_OK;
 }
@@ -567,12 +581,12 @@ int pt_render(pt_renderer* r, int32_t first_frame, int32_t nframes, int32_t max_
 
   Ctrl init{};
   init.total_samples = (unsigned long long)total;
+  init.first_frame = first_frame;
   PT_CUDA(cudaMemcpyAsync(r->ctrl.p, &init, sizeof(init), cudaMemcpyHostToDevice, st));
 
   Params p;
   p.W = r->W;
   p.H = r->H;
-  p.first_frame = first_frame;
   p.max_depth = max_depth;
   p.russian = russian;
   p.pool = r->pool;
@@ -594,11 +608,83 @@ int pt_render(pt_renderer* r, int32_t first_frame, int32_t nframes, int32_t max_
   const int g_trace = sms * trace_blocks_per_sm(), g_shade = sms * 8, g_gen = sms * 4;
   const uint32_t mask = s->material_type_mask;
   const SchedParams sched = sched_params();
+  const bool need_shadow = (mask & ((1u << PT_MAT_LAMBERTIAN) | (1u << PT_MAT_OREN_NAYAR) | (1u << PT_MAT_DIFFUSE_LIGHT))) &&
+                           (s->lights.size() > 0 || sc.env_n > 0);
 
   cudaEvent_t e[6] = {};
   float ms_gen = 0, ms_trace = 0, ms_shade = 0, ms_shadow = 0;
   if (timing)
     for (auto& ev : e) PT_CUDA(cudaEventCreate(&ev));
+
+  // one wavefront iteration reading pool `cur`, appending survivors to pool `nxt`; returns #launches
+  auto iteration = [&](const PathBuf& cur, const PathBuf& nxt, bool timed) {
+    int n = 0;
+    k_iter_begin<<<1, 1, 0, st>>>(c, r->pool);
+    if (timed) cudaEventRecord(e[0], st);
+    k_generate<<<g_gen, 256, 0, st>>>(sc, p, c, cur);
+    if (timed) cudaEventRecord(e[1], st);
+    if (count) k_trace<true><<<g_trace, PT_TRACE_THREADS, 0, st>>>(sc, c, cur, hits, bq, r->pool, sched);
+    else k_trace<false><<<g_trace, PT_TRACE_THREADS, 0, st>>>(sc, c, cur, hits, bq, r->pool, sched);
+    if (timed) cudaEventRecord(e[2], st);
+    n += 3;
+#define LAUNCH_SHADE(M)                                                       \
+  if (mask & (1u << M)) {                                                     \
+    k_shade<M><<<g_shade, 128, 0, st>>>(sc, p, c, cur, nxt, sb, hits, bq);    \
+    n++;                                                                      \
+  }
+    LAUNCH_SHADE(PT_MAT_LAMBERTIAN)
+    LAUNCH_SHADE(PT_MAT_METAL)
+    LAUNCH_SHADE(PT_MAT_DIELECTRIC)
+    LAUNCH_SHADE(PT_MAT_DIFFUSE_LIGHT)
+    LAUNCH_SHADE(PT_MAT_OREN_NAYAR)
+    LAUNCH_SHADE(PT_MAT_TORRANCE_SPARROW)
+    LAUNCH_SHADE(PT_MAT_ASHIKHMIN_SHIRLEY)
+    LAUNCH_SHADE(PT_MAT_NORMAL)
+#undef LAUNCH_SHADE
+    k_miss<<<g_shade, 128, 0, st>>>(sc, p, c, cur, bq);
+    if (timed) cudaEventRecord(e[3], st);
+    n++;
+    if (need_shadow) {
+      if (count) k_shadow<true><<<g_trace, PT_TRACE_THREADS, 0, st>>>(sc, p, c, nxt, sb, sched);
+      else k_shadow<false><<<g_trace, PT_TRACE_THREADS, 0, st>>>(sc, p, c, nxt, sb, sched);
+      n++;
+    }
+    if (timed) {
+      cudaEventRecord(e[4], st);
+      cudaEventSynchronize(e[4]);
+      float t;
+      cudaEventElapsedTime(&t, e[0], e[1]); ms_gen += t;
+      cudaEventElapsedTime(&t, e[1], e[2]); ms_trace += t;
+      cudaEventElapsedTime(&t, e[2], e[3]); ms_shade += t;
+      cudaEventElapsedTime(&t, e[3], e[4]); ms_shadow += t;
+    }
+    return n;
+  };
+
+  // Capture the iteration once per parameter set as two CUDA graphs (A->B, B->A): replaying a graph
+  // removes the per-kernel launch gaps, which are ~10 % of an iteration on small scenes.  The
+  // per-kernel timing mode launches directly instead.
+  const bool use_graph = !timing && getenv("PTB200_NO_GRAPH") == nullptr;
+  if (use_graph && (r->gexec[0] == nullptr || r->g_max_depth != max_depth || r->g_russian != russian ||
+                    r->g_pool != r->pool || r->g_flags != r->flags || memcmp(&r->g_scene, &sc, sizeof(SceneDev)) != 0)) {
+    for (auto& g : r->gexec) {
+      if (g) cudaGraphExecDestroy(g);
+      g = nullptr;
+    }
+    for (int parity = 0; parity < 2; parity++) {
+      cudaGraph_t graph = nullptr;
+      PT_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+      r->g_launches = parity == 0 ? iteration(A, B, false) : iteration(B, A, false);
+      PT_CUDA(cudaStreamEndCapture(st, &graph));
+      PT_CUDA(cudaGraphInstantiate(&r->gexec[parity], graph, 0));
+      cudaGraphDestroy(graph);
+    }
+    r->g_max_depth = max_depth;
+    r->g_russian = russian;
+    r->g_pool = r->pool;
+    r->g_flags = r->flags;
+    memcpy(&r->g_scene, &sc, sizeof(SceneDev));
+  }
 
   PT_CUDA(cudaEventRecord(r->ev0, st));
   unsigned long long launches = 0;
@@ -610,54 +696,19 @@ int pt_render(pt_renderer* r, int32_t first_frame, int32_t nframes, int32_t max_
   long long poll_every = std::max<long long>(4, total / std::max(1, r->pool));
   while (!done) {
     for (long long k = 0; k < poll_every; k++, iter++) {
-      k_iter_begin<<<1, 1, 0, st>>>(c, r->pool);
-      if (timing) cudaEventRecord(e[0], st);
-      k_generate<<<g_gen, 256, 0, st>>>(sc, p, c, A);
-      if (timing) cudaEventRecord(e[1], st);
-      if (count) k_trace<true><<<g_trace, PT_TRACE_THREADS, 0, st>>>(sc, c, A, hits, bq, r->pool, sched);
-      else k_trace<false><<<g_trace, PT_TRACE_THREADS, 0, st>>>(sc, c, A, hits, bq, r->pool, sched);
-      if (timing) cudaEventRecord(e[2], st);
-      launches += 3;
-#define LAUNCH_SHADE(M)                                                       \
-  if (mask & (1u << M)) {                                                     \
-    k_shade<M><<<g_shade, 128, 0, st>>>(sc, p, c, A, B, sb, hits, bq);        \
-    launches++;                                                               \
-  }
-      LAUNCH_SHADE(PT_MAT_LAMBERTIAN)
-      LAUNCH_SHADE(PT_MAT_METAL)
-      LAUNCH_SHADE(PT_MAT_DIELECTRIC)
-      LAUNCH_SHADE(PT_MAT_DIFFUSE_LIGHT)
-      LAUNCH_SHADE(PT_MAT_OREN_NAYAR)
-      LAUNCH_SHADE(PT_MAT_TORRANCE_SPARROW)
-      LAUNCH_SHADE(PT_MAT_ASHIKHMIN_SHIRLEY)
-      LAUNCH_SHADE(PT_MAT_NORMAL)
-#undef LAUNCH_SHADE
-      k_miss<<<g_shade, 128, 0, st>>>(sc, p, c, A, bq);
-      if (timing) cudaEventRecord(e[3], st);
-      launches++;
-      if (mask & ((1u << PT_MAT_LAMBERTIAN) | (1u << PT_MAT_OREN_NAYAR) | (1u << PT_MAT_DIFFUSE_LIGHT))) {
-        if (s->lights.size() > 0 || sc.env_n > 0) {
-          if (count) k_shadow<true><<<g_trace, PT_TRACE_THREADS, 0, st>>>(sc, p, c, B, sb, sched);
-          else k_shadow<false><<<g_trace, PT_TRACE_THREADS, 0, st>>>(sc, p, c, B, sb, sched);
-          launches++;
-        }
+      if (use_graph) {
+        PT_CUDA(cudaGraphLaunch(r->gexec[iter & 1], st));
+        launches += (unsigned long long)r->g_launches;
+      } else {
+        launches += (unsigned long long)((iter & 1) ? iteration(B, A, timing) : iteration(A, B, timing));
       }
-      if (timing) {
-        cudaEventRecord(e[4], st);
-        cudaEventSynchronize(e[4]);
-        float t;
-        cudaEventElapsedTime(&t, e[0], e[1]); ms_gen += t;
-        cudaEventElapsedTime(&t, e[1], e[2]); ms_trace += t;
-        cudaEventElapsedTime(&t, e[2], e[3]); ms_shade += t;
-        cudaEventElapsedTime(&t, e[3], e[4]); ms_shadow += t;
-      }
-      std::swap(A, B);
     }
     PT_CUDA(cudaGetLastError());
     PT_CUDA(cudaMemcpyAsync(r->h_ctrl, c, sizeof(Ctrl), cudaMemcpyDeviceToHost, st));
     PT_CUDA(cudaStreamSynchronize(st));
     done = r->h_ctrl->next_sample >= r->h_ctrl->total_samples && r->h_ctrl->n_next == 0;
     poll_every = std::max<long long>(4, (long long)((r->h_ctrl->total_samples - r->h_ctrl->next_sample) / (unsigned)std::max(1, r->pool)));
+    if (poll_every & 1) poll_every++;  // keep the pool parity aligned with `iter`
     if (iter > 100000000ll) {
       pt_set_error("pt_render: did not converge");
       return PT_ERR_INVALID;

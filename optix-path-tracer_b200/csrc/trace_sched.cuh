@@ -30,6 +30,7 @@
 struct SchedParams {
   int refill_min;   // refill when at least this many lanes are idle (or the whole warp is)
   int leaf_thresh;  // run a leaf step when >= this many lanes have a pending leaf (or leaf lanes are the majority)
+  int fetch_chunk;  // rays a warp claims from the queue per atomic (surplus stays warp-private); 0 = exactly the idle lanes
 };
 
 template <bool COUNT, class Policy>
@@ -45,6 +46,7 @@ __device__ __forceinline__ void trace_persistent(const SceneDev& sc, int n, int*
   int ray = -1;
   bool anyhit = false;
   bool exhausted = false;  // warp-uniform: the ray queue is empty
+  int w_next = 0, w_end = 0;  // warp-uniform: the warp's private claim [w_next, w_end) of queue indices
   RayCtx r;
   TraceHit hit;
   uint2 ng = make_uint2(0u, 0u), lg = make_uint2(0u, 0u);
@@ -71,12 +73,19 @@ __device__ __forceinline__ void trace_persistent(const SceneDev& sc, int n, int*
       }
       idle |= fin;
       if (!exhausted) {
+        // same-address L2 atomics are the scarce resource of these kernels (one unit serialises them):
+        // claim fetch_chunk indices per atomic and hand them out from the warp-private range
         const int cnt = __popc(idle);
+        const int avail = w_end - w_next;
+        const int chunk = max(sp_.fetch_chunk, cnt - avail);  // fetch_chunk 0: claim exactly what is needed
         int base = 0;
-        if (lane == 0) base = atomicAdd(fetch_counter, cnt);
-        base = __shfl_sync(FULL, base, 0);
+        if (avail < cnt) {
+          if (lane == 0) base = atomicAdd(fetch_counter, chunk);
+          base = __shfl_sync(FULL, base, 0);
+        }
         if (ray < 0) {
-          const int idx = base + __popc(idle & lt_mask);
+          const int k = __popc(idle & lt_mask);
+          const int idx = k < avail ? w_next + k : base + (k - avail);
           if (idx < n) {
             ray = idx;
             float3 o, d;
@@ -90,7 +99,13 @@ __device__ __forceinline__ void trace_persistent(const SceneDev& sc, int n, int*
             sp = 0;
           }
         }
-        if (base + cnt >= n) exhausted = true;
+        if (avail < cnt) {
+          w_next = base + (cnt - avail);
+          w_end = base + chunk;
+        } else {
+          w_next += cnt;
+        }
+        if (w_next >= n) exhausted = true;
       }
       continue;  // re-evaluate lane states (fresh rays, rays loaded with an empty interval)
     }
