@@ -113,7 +113,9 @@ typedef struct pt_texture {
 
 /* host_includes/pdfs.hpp:18-80 `Rectangle_PDF(a0,a1,b0,b1,k,axis)` +
  * Light_Sampler::emissions (host_includes/host_common.hpp:65-68) */
-enum { PT_LIGHT_RECT = 0 };
+/* PT_LIGHT_SPHERE replaces Sphere_PDF (host_includes/pdfs.hpp:82-109, programs/pdfs/sphere_pdf.cu):
+ * centre = (a0, a1, b0), radius = k; axis, b1 unused. */
+enum { PT_LIGHT_RECT = 0, PT_LIGHT_SPHERE = 1 };
 
 typedef struct pt_light {
   int32_t type;

@@ -29,6 +29,7 @@ PRIM_TRIANGLE, PRIM_SPHERE, PRIM_RECT, PRIM_BOX = 0, 1, 2, 3
  MAT_TORRANCE_SPARROW, MAT_ASHIKHMIN_SHIRLEY, MAT_NORMAL) = range(8)
 TEX_CONSTANT, TEX_CHECKER, TEX_IMAGE, TEX_VECTOR, TEX_NOISE, TEX_GRADIENT = 0, 1, 2, 3, 4, 5
 MISS_GRADIENT, MISS_CONSTANT, MISS_IMG, MISS_HDR = 0, 1, 2, 3
+LIGHT_RECT, LIGHT_SPHERE = 0, 1
 FLAG_COUNT_FETCHES, FLAG_TIME_KERNELS = 1, 2
 
 F3 = C.c_float * 3

@@ -25,6 +25,7 @@ int pth_build_scene(int scene_id, int W, int H, int model, pt_scene** out) {
       case 4: Test_Scene(app); break;
       case 5: Cornell_Materials(app); break;
       case 6: Mesh_HDRI(app); break;
+      case 7: Cornell_Sphere_Light(app); break;
 #endif
       default: return PT_ERR_INVALID;
     }

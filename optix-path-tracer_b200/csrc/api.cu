@@ -349,8 +349,8 @@ int pt_scene_add_image(pt_scene* s, const float* rgba, int32_t w, int32_t h, int
 int pt_scene_set_lights(pt_scene* s, const pt_light* l, int32_t n) {
   if (!s || n < 0 || (n > 0 && !l)) return PT_ERR_INVALID;
   for (int i = 0; i < n; i++)
-    if (l[i].type != PT_LIGHT_RECT || l[i].axis < 0 || l[i].axis > 2) {
-      pt_set_error("light %d: only axis-aligned rectangle lights are supported", i);
+    if (!((l[i].type == PT_LIGHT_RECT && l[i].axis >= 0 && l[i].axis <= 2) || l[i].type == PT_LIGHT_SPHERE)) {
+      pt_set_error("light %d: unknown light type %d / axis %d", i, l[i].type, l[i].axis);
       return PT_ERR_INVALID;
     }
   s->lights.assign(l, l + n);
@@ -487,6 +487,7 @@ int pt_scene_commit(pt_scene* s) {
   d.n_lights = (int)s->lights.size();
   d.camera = s->camera;
   d.miss = s->miss;
+  s->commit_gen++;
   s->committed = true;
   return PT_OK;
 }

@@ -222,7 +222,7 @@ __global__ void __launch_bounds__(PT_TRACE_THREADS) k_trace(SceneDev sc, Ctrl* c
 #ifndef PT_SHADE_MINBLOCKS
 #define PT_SHADE_MINBLOCKS 8
 #endif
-template <int MAT>
+template <int MAT, int LK>
 __global__ void __launch_bounds__(128, PT_SHADE_MINBLOCKS) k_shade(SceneDev sc, Params p, Ctrl* c, PathBuf cur, PathBuf next, ShadowBuf sb,
                                                const float4* hits, const uint32_t* bin_q) {
   const int n = c->bin_count[MAT].v;
@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(128, PT_SHADE_MINBLOCKS) k_shade(SceneDev sc, 
     in.last_pdf = t4.w;
     const uint32_t pix = pk & 0x7fffffu;
     ShadeOut out;
-    shade_hit<MAT>(sc, in, h4.x, __float_as_int(h4.y), h4.z, h4.w, out);
+    shade_hit<MAT, LK>(sc, in, h4.x, __float_as_int(h4.y), h4.z, h4.w, out);
     if (out.kind == SH_TERMINATE) {
       accumulate(p, pix, out.col);
     } else if (out.kind == SH_BOUNCE) {
@@ -451,6 +451,7 @@ struct pt_renderer {
   // pt_render calls while the launch parameters stay the same
   cudaGraphExec_t gexec[2] = {nullptr, nullptr};
   int g_max_depth = -1, g_russian = -1, g_pool = -1, g_flags = -1, g_launches = 0;
+  unsigned long long g_commit_gen = 0;
   SceneDev g_scene{};  // kernel arguments are baked into the graphs: re-capture when they change
   pt_stats stats{};
   Ctrl* h_ctrl = nullptr;  // pinned
@@ -611,6 +612,9 @@ int pt_render(pt_renderer* r, int32_t first_frame, int32_t nframes, int32_t max_
   const bool need_shadow = (mask & ((1u << PT_MAT_LAMBERTIAN) | (1u << PT_MAT_OREN_NAYAR) | (1u << PT_MAT_DIFFUSE_LIGHT))) &&
                            (s->lights.size() > 0 || sc.env_n > 0);
 
+  bool sphere_lights = false;
+  for (const pt_light& l : s->lights) sphere_lights |= l.type == PT_LIGHT_SPHERE;
+
   cudaEvent_t e[6] = {};
   float ms_gen = 0, ms_trace = 0, ms_shade = 0, ms_shadow = 0;
   if (timing)
@@ -627,19 +631,26 @@ int pt_render(pt_renderer* r, int32_t first_frame, int32_t nframes, int32_t max_
     else k_trace<false><<<g_trace, PT_TRACE_THREADS, 0, st>>>(sc, c, cur, hits, bq, r->pool, sched);
     if (timed) cudaEventRecord(e[2], st);
     n += 3;
-#define LAUNCH_SHADE(M)                                                       \
-  if (mask & (1u << M)) {                                                     \
-    k_shade<M><<<g_shade, 128, 0, st>>>(sc, p, c, cur, nxt, sb, hits, bq);    \
-    n++;                                                                      \
+#define LAUNCH_SHADE(M, LK)                                                     \
+  if (mask & (1u << M)) {                                                       \
+    k_shade<M, LK><<<g_shade, 128, 0, st>>>(sc, p, c, cur, nxt, sb, hits, bq);  \
+    n++;                                                                        \
   }
-    LAUNCH_SHADE(PT_MAT_LAMBERTIAN)
-    LAUNCH_SHADE(PT_MAT_METAL)
-    LAUNCH_SHADE(PT_MAT_DIELECTRIC)
-    LAUNCH_SHADE(PT_MAT_DIFFUSE_LIGHT)
-    LAUNCH_SHADE(PT_MAT_OREN_NAYAR)
-    LAUNCH_SHADE(PT_MAT_TORRANCE_SPARROW)
-    LAUNCH_SHADE(PT_MAT_ASHIKHMIN_SHIRLEY)
-    LAUNCH_SHADE(PT_MAT_NORMAL)
+    // the three NEE materials exist in a rectangle-lights-only and an any-light build
+    if (sphere_lights) {
+      LAUNCH_SHADE(PT_MAT_LAMBERTIAN, 1)
+      LAUNCH_SHADE(PT_MAT_DIFFUSE_LIGHT, 1)
+      LAUNCH_SHADE(PT_MAT_OREN_NAYAR, 1)
+    } else {
+      LAUNCH_SHADE(PT_MAT_LAMBERTIAN, 0)
+      LAUNCH_SHADE(PT_MAT_DIFFUSE_LIGHT, 0)
+      LAUNCH_SHADE(PT_MAT_OREN_NAYAR, 0)
+    }
+    LAUNCH_SHADE(PT_MAT_METAL, 0)
+    LAUNCH_SHADE(PT_MAT_DIELECTRIC, 0)
+    LAUNCH_SHADE(PT_MAT_TORRANCE_SPARROW, 0)
+    LAUNCH_SHADE(PT_MAT_ASHIKHMIN_SHIRLEY, 0)
+    LAUNCH_SHADE(PT_MAT_NORMAL, 0)
 #undef LAUNCH_SHADE
     k_miss<<<g_shade, 128, 0, st>>>(sc, p, c, cur, bq);
     if (timed) cudaEventRecord(e[3], st);
@@ -666,7 +677,8 @@ int pt_render(pt_renderer* r, int32_t first_frame, int32_t nframes, int32_t max_
   // per-kernel timing mode launches directly instead.
   const bool use_graph = !timing && getenv("PTB200_NO_GRAPH") == nullptr;
   if (use_graph && (r->gexec[0] == nullptr || r->g_max_depth != max_depth || r->g_russian != russian ||
-                    r->g_pool != r->pool || r->g_flags != r->flags || memcmp(&r->g_scene, &sc, sizeof(SceneDev)) != 0)) {
+                    r->g_pool != r->pool || r->g_flags != r->flags || r->g_commit_gen != s->commit_gen ||
+                    memcmp(&r->g_scene, &sc, sizeof(SceneDev)) != 0)) {
     for (auto& g : r->gexec) {
       if (g) cudaGraphExecDestroy(g);
       g = nullptr;
@@ -683,6 +695,7 @@ int pt_render(pt_renderer* r, int32_t first_frame, int32_t nframes, int32_t max_
     r->g_russian = russian;
     r->g_pool = r->pool;
     r->g_flags = r->flags;
+    r->g_commit_gen = s->commit_gen;
     memcpy(&r->g_scene, &sc, sizeof(SceneDev));
   }
 

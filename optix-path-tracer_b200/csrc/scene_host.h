@@ -78,6 +78,7 @@ struct pt_scene {
   pt_camera camera{};
   pt_miss miss{};
   bool committed = false;
+  unsigned long long commit_gen = 0;  // bumped by every successful commit (renderers key cached graphs on it)
   // environment importance sampling tables (built on the host at commit / get_desc)
   std::vector<float> env_alias_prob, env_texel_pdf;
   std::vector<int32_t> env_alias_idx;

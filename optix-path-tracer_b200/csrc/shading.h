@@ -346,6 +346,61 @@ PT_HD float rect_light_pdf(const pt_light& l, float3 P, float3 Wi) {
   float area = (l.a1 - l.a0) * (l.b1 - l.b0);
   return distance_squared / (cosine * area);
 }
+// ---- sphere light: programs/pdfs/sphere_pdf.cu:8-84 (centre = (a0,a1,b0), radius = k) -------
+PT_HD float3 sphere_light_sample(const pt_light& l, float3 P, float r1, float r2) {
+  float3 center = f3(l.a0, l.a1, l.b0);
+  float radius = l.k;
+  float lc = length(center - P);
+  float distance_squared = lc * lc;
+  float z = 1.f + r2 * (sqrtf(1.f - radius * radius / distance_squared) - 1.f);
+  float phi = 2.f * PT_PI_F * r1;
+  float x = cosf(phi) * sqrtf(1.f - z * z);
+  float y = sinf(phi) * sqrtf(1.f - z * z);
+  float3 Wi = f3(x, y, z);
+  // :79-80 as written: the frame is built around the sampled direction itself
+  float3 n = normalize(Wi);
+  float3 bn;
+  if (fabsf(n.x) > fabsf(n.z)) bn = f3(-n.y, n.x, 0.f);
+  else bn = f3(0.f, -n.z, n.y);
+  bn = normalize(bn);
+  float3 tg = cross(bn, n);
+  return Wi.x * tg + Wi.y * bn + Wi.z * n;
+}
+PT_HD float sphere_light_pdf(const pt_light& l, float3 P, float3 Wi) {
+  float3 center = f3(l.a0, l.a1, l.b0);
+  float radius = l.k;
+  const float3 oc = P - center;
+  const float a = dot(Wi, Wi);
+  const float b = dot(oc, Wi);
+  const float c = dot(oc, oc) - radius * radius;
+  const float discriminant = b * b - a * c;
+  if (discriminant < 0.f) return 0.f;
+  const float tmin = 0.001f, tmax = 3.402823466e+38f;
+  float temp = (-b - sqrtf(discriminant)) / a;
+  bool hit = temp < tmax && temp > tmin;
+  if (!hit) {
+    temp = (-b + sqrtf(discriminant)) / a;
+    hit = temp < tmax && temp > tmin;
+  }
+  if (!hit) return 0.f;
+  float lc = length(center - P);
+  float distance_squared = lc * lc;
+  float cos_theta_max = sqrtf(1.f - radius * radius / distance_squared);
+  float solid_angle = 2.f * PT_PI_F * (1.f - cos_theta_max);
+  return 1.f / solid_angle;
+}
+// LK: light kinds the kernel is specialised for (0 = rectangles only — the common case keeps the
+// sphere code out of the hot shading kernels; 1 = any mix)
+template <int LK>
+PT_HD float3 light_sample(const pt_light& l, float3 P, float ua, float ub) {
+  if (LK != 0 && l.type == PT_LIGHT_SPHERE) return sphere_light_sample(l, P, ua, ub);
+  return rect_light_sample(l, P, ua, ub);
+}
+template <int LK>
+PT_HD float light_pdf(const pt_light& l, float3 P, float3 Wi) {
+  if (LK != 0 && l.type == PT_LIGHT_SPHERE) return sphere_light_pdf(l, P, Wi);
+  return rect_light_pdf(l, P, Wi);
+}
 PT_HD float power_heuristic(float fPdf, float gPdf) {  // light_sample.cuh:27-33 (numf=numg=1)
   float f = 1u * fPdf, g = 1u * gPdf;
   return (f * f) / (f * f + g * g);
@@ -654,7 +709,7 @@ struct ShadeOut {
 
 // Direct_Light<T> (light_sample.cuh:35-103) for a cosine-type surface, split
 // around the shadow ray.  Returns false when no shadow ray is needed.
-template <int MAT>
+template <int MAT, int LK>
 PT_HD bool nee_begin(const SceneDev& sc, const Surface& surf, float3 P, float3 Wo, float3 N, bool isLight,
                      uint32_t& seed, float3& WiL, float3& directV, uint32_t& seedV, float3& misDir) {
   directV = f3(0.f);
@@ -666,8 +721,8 @@ PT_HD bool nee_begin(const SceneDev& sc, const Surface& surf, float3 P, float3 W
   float3 emission = f3(L.emission[0], L.emission[1], L.emission[2]);
   float ua = pt_rnd(seed);
   float ub = pt_rnd(seed);
-  float3 Wi = rect_light_sample(L, P, ua, ub);
-  float lightPDF = rect_light_pdf(L, P, Wi);
+  float3 Wi = light_sample<LK>(L, P, ua, ub);
+  float lightPDF = light_pdf<LK>(L, P, Wi);
   if (dot(Wi, N) < 0.f) return false;
   // from here the reference traces the shadow ray; if occluded it returns with
   // `seed` as it is now (candidate S).  Candidate V continues:
@@ -688,7 +743,7 @@ PT_HD bool nee_begin(const SceneDev& sc, const Surface& surf, float3 P, float3 W
   float matPDF = 0.f;
   float3 matValue = bsdf_eval<MAT>(surf, Wo, Wi2, N, matPDF);
   if (matPDF != 0.f && !(matValue.x == 0.f && matValue.y == 0.f && matValue.z == 0.f)) {
-    float lp = rect_light_pdf(L, P, Wi2);
+    float lp = light_pdf<LK>(L, P, Wi2);
     if (!(!lp || emNull)) {
       float weight = power_heuristic(matPDF, lp);
       direct += matValue * emission * weight / matPDF;
@@ -698,7 +753,7 @@ PT_HD bool nee_begin(const SceneDev& sc, const Surface& surf, float3 P, float3 W
   return true;
 }
 
-template <int MAT>
+template <int MAT, int LK = 1>
 PT_HD void shade_hit(const SceneDev& sc, const PathIn& in, float t, int leaf, float bu, float bv, ShadeOut& out) {
   HitRec rec = make_hit_record(sc, in.o, in.d, t, leaf, bu, bv);
   const pt_material m = sc.materials[rec.material];
@@ -757,7 +812,7 @@ PT_HD void shade_hit(const SceneDev& sc, const PathIn& in, float t, int leaf, fl
     uint32_t seed = in.seed;
     float3 WiL, directV, misDir;
     uint32_t seedV;
-    bool need_shadow = nee_begin<MAT>(sc, surf, P, Wo, N, false, seed, WiL, directV, seedV, misDir);
+    bool need_shadow = nee_begin<MAT, LK>(sc, surf, P, Wo, N, false, seed, WiL, directV, seedV, misDir);
     out.specular = false;
     if (!need_shadow) {
       float3 Wi = bsdf_sample<MAT>(surf, Wo, N, seed);
@@ -841,7 +896,7 @@ PT_HD void shade_hit(const SceneDev& sc, const PathIn& in, float t, int leaf, fl
     uint32_t seed = in.seed;
     float3 WiL, directV, misDir;
     uint32_t seedV;
-    bool need_shadow = nee_begin<MAT>(sc, surf, P, Wo, N, true, seed, WiL, directV, seedV, misDir);
+    bool need_shadow = nee_begin<MAT, LK>(sc, surf, P, Wo, N, true, seed, WiL, directV, seedV, misDir);
     float3 thr = in.thr;
     if (dot(N, Wo) < 0.f) thr *= surf.color;
     const bool add = in.depth == 0 || in.prev_specular;

@@ -1,6 +1,6 @@
 // pdfs.hpp — light sampling descriptors (reference surface:
 // host_includes/pdfs.hpp:12-109).  createSample/createPDF return Program
-// handles that carry the rectangle; setRayGenerationProgram pairs them with
+// handles that carry the light shape; setRayGenerationProgram pairs them with
 // Light_Sampler::emissions.
 #pragma once
 #include "host_common.hpp"
@@ -28,11 +28,19 @@ struct Rectangle_PDF : public PDF {
   AXIS ax;
 };
 
-// sphere lights: "next" row; declared for source compatibility
+// sphere lights (reference: host_includes/pdfs.hpp:82-109; device side programs/pdfs/sphere_pdf.cu)
 struct Sphere_PDF : public PDF {
   Sphere_PDF(const float3 c, const float r) : radius(r), center(c) {}
-  Program createSample(Context&) const override { throw "Sphere_PDF is not supported yet (SURVEY 8f)"; }
-  Program createPDF(Context&) const override { throw "Sphere_PDF is not supported yet (SURVEY 8f)"; }
+  Program make() const {
+    Program p{std::make_shared<ProgramObj>()};
+    p->is_light = true;
+    p->light.type = PT_LIGHT_SPHERE;
+    p->light.axis = 0;
+    p->light.a0 = center.x; p->light.a1 = center.y; p->light.b0 = center.z; p->light.b1 = 0.f; p->light.k = radius;
+    return p;
+  }
+  Program createSample(Context&) const override { return make(); }
+  Program createPDF(Context&) const override { return make(); }
   float radius;
   float3 center;
 };

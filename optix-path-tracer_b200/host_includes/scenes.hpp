@@ -298,6 +298,39 @@ inline void Cornell_Materials(App_State& app) {
   finishScene(app, group, make_float3(278.f, 278.f, -800.f), make_float3(278.f, 278.f, 0.f), 40.f, 0.f, 10.f, t0);
 }
 
+// Cornell box lit by an emissive sphere sampled through Sphere_PDF plus the usual ceiling
+// rectangle: two lights of different PDF kinds
+inline void Cornell_Sphere_Light(App_State& app) {
+  using namespace scene_detail;
+  auto t0 = std::chrono::system_clock::now();
+  Light_Sampler lights;
+  Sphere_PDF ball(make_float3(278.f, 400.f, 278.f), 60.f);
+  lights.pdf.push_back(ball.createPDF(app.context));
+  lights.sample.push_back(ball.createSample(app.context));
+  lights.emissions.push_back(make_float3(5.f));
+  addRectLight(lights, app, 213.f, 343.f, 227.f, 332.f, 554.f, Y_AXIS, 7.f);
+  setMissProgram(app.context, CONSTANT);
+  Group group = beginScene(app, lights);
+  BRDF* red = new Lambertian(new Constant_Texture(0.65f, 0.05f, 0.05f));
+  BRDF* white = new Lambertian(new Constant_Texture(0.73f));
+  BRDF* green = new Lambertian(new Constant_Texture(0.12f, 0.45f, 0.15f));
+  BRDF* light = new Diffuse_Light(new Constant_Texture(7.f));
+  Hitable_List list;
+  list.push(new AARect(0.f, 555.f, 0.f, 555.f, 555.f, true, X_AXIS, red));
+  list.push(new AARect(0.f, 555.f, 0.f, 555.f, 0.f, false, X_AXIS, green));
+  list.push(new AARect(213.f, 343.f, 227.f, 332.f, 554.f, true, Y_AXIS, light));
+  list.push(new AARect(0.f, 555.f, 0.f, 555.f, 555.f, true, Y_AXIS, white));
+  list.push(new AARect(0.f, 555.f, 0.f, 555.f, 0.f, false, Y_AXIS, white));
+  list.push(new AARect(0.f, 555.f, 0.f, 555.f, 555.f, true, Z_AXIS, white));
+  Box tall(make_float3(0.f), make_float3(165.f, 330.f, 165.f), green);
+  tall.translate(make_float3(265.f, 0.f, 295.f));
+  tall.rotate(15.f, Y_AXIS);
+  list.push(&tall);
+  list.push(new Sphere(make_float3(278.f, 400.f, 278.f), 60.f, light));
+  list.addElementsTo(group, app.context);
+  finishScene(app, group, make_float3(278.f, 278.f, -800.f), make_float3(278.f, 278.f, 0.f), 40.f, 0.f, 10.f, t0);
+}
+
 // BASELINE configs C4/C5: procedural triangle mesh (OBJ written locally, loaded via Mesh) lit by a
 // synthetic equirect HDRI (Radiance .hdr written locally, loaded via the HDR miss program)
 inline void Mesh_HDRI(App_State& app) {

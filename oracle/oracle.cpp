@@ -560,6 +560,57 @@ inline float Rect_PDF(const pt_light& l, f3 P, f3 Wi) {
   return distance_squared / (cosine * area);
 }
 
+// sphere light — P/pdfs/sphere_pdf.cu:8-84 (centre = (a0,a1,b0), radius = k).  As written: the
+// sampled cone direction is rotated into a frame built around ITSELF (:79-80), not around the
+// direction to the sphere.
+inline f3 SphereL_Sample(const pt_light& l, f3 P, uint32_t& seed) {
+  f3 center = mk(l.a0, l.a1, l.b0);
+  float radius = l.k;
+  float r1 = rnd(seed);
+  float r2 = rnd(seed);
+  float distance_squared = squared_length(center - P);
+  float z = 1.f + r2 * (sqrtf(1.f - radius * radius / distance_squared) - 1.f);
+  float phi = 2.f * PI_F * r1;
+  float x = cosf(phi) * sqrtf(1.f - z * z);
+  float y = sinf(phi) * sqrtf(1.f - z * z);
+  f3 Wi = mk(x, y, z);
+  Onb uvw(normalize(Wi));
+  uvw.inverse_transform(Wi);
+  return Wi;
+}
+inline float SphereL_PDF(const pt_light& l, f3 P, f3 Wi) {
+  f3 center = mk(l.a0, l.a1, l.b0);
+  float radius = l.k;
+  const f3 oc = P - center;
+  const float a = dot(Wi, Wi);
+  const float b = dot(oc, Wi);
+  const float c = dot(oc, oc) - radius * radius;
+  const float discriminant = b * b - a * c;
+  if (discriminant < 0.f) return 0.f;
+  const float tmin = 0.001f, tmax = 3.402823466e+38f;
+  bool hit = false;
+  float temp = (-b - sqrtf(discriminant)) / a;
+  if (temp < tmax && temp > tmin) hit = true;
+  if (!hit) {
+    temp = (-b + sqrtf(discriminant)) / a;
+    if (temp < tmax && temp > tmin) hit = true;
+  }
+  if (!hit) return 0.f;
+  float distance_squared = squared_length(center - P);
+  float cos_theta_max = sqrtf(1.f - radius * radius / distance_squared);
+  float solid_angle = 2.f * PI_F * (1.f - cos_theta_max);
+  return 1.f / solid_angle;
+}
+inline f3 Light_Sample(const pt_light& l, f3 P, uint32_t& seed) {
+  if (l.type == PT_LIGHT_SPHERE) return SphereL_Sample(l, P, seed);
+  float ua = rnd(seed);
+  float ub = rnd(seed);
+  return Rect_Sample(l, P, ua, ub);
+}
+inline float Light_PDF(const pt_light& l, f3 P, f3 Wi) {
+  return l.type == PT_LIGHT_SPHERE ? SphereL_PDF(l, P, Wi) : Rect_PDF(l, P, Wi);
+}
+
 inline float PowerHeuristic(unsigned numf, float fPdf, unsigned numg, float gPdf) {
   float f = numf * fPdf;  // P/materials/light_sample.cuh:27-33
   float g = numg * gPdf;
@@ -1179,10 +1230,8 @@ f3 Direct_Light(const orc_scene& s, const Surface& surface, f3 P, f3 Wo, f3 N, b
   if (isLight && numLights == 1) return mk(0.f);
   const pt_light& L = s.d.lights[index];
   f3 emission = ld3(L.emission);
-  float ua = rnd(seed);
-  float ub = rnd(seed);
-  f3 Wi = Rect_Sample(L, P, ua, ub);
-  float lightPDF = Rect_PDF(L, P, Wi);
+  f3 Wi = Light_Sample(L, P, seed);
+  float lightPDF = Light_PDF(L, P, Wi);
   if (dot(Wi, N) < 0.f) return mk(0.f);
   // shadow ray (type 1, tmin 1e-3, tmax inf) — pinned visibility, see header
   Ray sh = {P, Wi, 1e-3f, RT_DEFAULT_MAX};
@@ -1206,7 +1255,7 @@ f3 Direct_Light(const orc_scene& s, const Surface& surface, f3 P, f3 Wo, f3 N, b
   float matPDF = 0.f;
   f3 matValue = Evaluate(surface, P, Wo, Wi, N, matPDF);
   if (matPDF != 0.f && !isNull(matValue)) {
-    lightPDF = Rect_PDF(L, P, Wi);
+    lightPDF = Light_PDF(L, P, Wi);
     if (!lightPDF || isNull(emission)) return directLight;
     float weight = PowerHeuristic(1, matPDF, 1, lightPDF);
     directLight += matValue * emission * weight / matPDF;

@@ -358,6 +358,20 @@ def build_cornell(W=64, H=64, lib=None, extra=None):
     return s
 
 
+def build_sphere_light_scene(W=48, H=48, lib=None, two=False):
+    """Cornell walls lit by an emissive Sphere sampled through Sphere_PDF
+    (host_includes/pdfs.hpp:82-109, programs/pdfs/sphere_pdf.cu); `two` adds the rect light back
+    so that light picking covers both PDF kinds."""
+    def extra(s, texs, mats):
+        pass
+    s = build_cornell(W, H, lib, extra)
+    s.add_spheres([pt.Sphere(pt.F3(278, 400, 278), 60.0)], [3])
+    sph = pt.Light(pt.LIGHT_SPHERE, 0, 278, 400, 278, 0, 60.0, pt.F3(5, 5, 5))
+    rect = pt.Light(pt.LIGHT_RECT, pt.Y_AXIS, 213, 343, 227, 332, 554, pt.F3(7, 7, 7))
+    s.set_lights([sph, rect] if two else [sph])
+    return s
+
+
 def build_spheres(n_small=22, seed=0, W=64, H=64, lib=None, lights=False):
     """RTOW-style scene (host_includes/scenes.hpp:17-93): ground + grid of small spheres
     (Lambertian / metal / dielectric) + three big ones, gradient sky."""

@@ -80,6 +80,17 @@ def test_other_scenes_build(host_so, tmp_path):
     assert len(ms["prims"]) // 4 == 1 + 484 + 3 + 1 and len(ms["lights"]) // 10 == 1
 
 
+def test_sphere_pdf_light_through_the_facade(host_so, tmp_path):
+    """Sphere_PDF (host_includes/pdfs.hpp:82-109) carries centre/radius into a PT_LIGHT_SPHERE entry;
+    the facade scene equals the hand-built two-light scene the parity tests render."""
+    a = dump(host_so, 7, 48, 48, 0, tmp_path, "mine")
+    hand = h.build_sphere_light_scene(48, 48, two=True)
+    b = facade_dump.desc_arrays(hand.desc())
+    same(a, b, skip=("prims", "materials", "textures"))
+    lights = a["lights"].reshape(-1, 10)
+    assert lights[0][0] == pt.LIGHT_SPHERE and lights[1][0] == pt.LIGHT_RECT
+
+
 @pytest.mark.skipif(not os.path.exists(REF_SCENES), reason="reference tree not present")
 def test_reference_scenes_header_drops_in(host_so, tmp_path):
     """Compile the reference's scenes.hpp (copied to a temp dir, never into the repo) against

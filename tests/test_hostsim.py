@@ -204,3 +204,15 @@ def test_noise_and_gradient_textures_equal_oracle():
     # the noise texture really modulates the albedo: the left sphere is not uniformly shaded
     left = a[8:24, 4:12, 0]
     assert left.std() > 0.02
+
+
+@pytest.mark.parametrize("two", [False, True])
+def test_sphere_light_logic_equals_oracle(two):
+    """Sphere_PDF lights (programs/pdfs/sphere_pdf.cu): the device cores reproduce
+    the oracle's Direct_Light with a sphere sampler bit-identically on the CPU, alone and mixed
+    with a rect light (light picking, light_sample.cuh:48)."""
+    sc = h.build_sphere_light_scene(24, 24, two=two)
+    a, st = h.OracleScene(sc).render(24, 24, 0, 3)
+    b = h.SimScene(sc).render(24, 24, 0, 3)
+    assert np.array_equal(a, b)
+    assert st.shadow_rays > 0 and np.isfinite(a).all()
