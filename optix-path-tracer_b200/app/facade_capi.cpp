@@ -26,6 +26,7 @@ int pth_build_scene(int scene_id, int W, int H, int model, pt_scene** out) {
       case 5: Cornell_Materials(app); break;
       case 6: Mesh_HDRI(app); break;
       case 7: Cornell_Sphere_Light(app); break;
+      case 8: Textured_Mesh(app); break;
 #endif
       default: return PT_ERR_INVALID;
     }
@@ -37,5 +38,34 @@ int pth_build_scene(int scene_id, int W, int H, int model, pt_scene** out) {
     fprintf(stderr, "pth_build_scene: %s\n", e.c_str());
   }
   return PT_ERR_INVALID;
+}
+
+// decodes an image file with the facade's own PNG/JPEG/PPM readers (host_includes/image_decode.hpp).
+// Two-call pattern: pass out == NULL to get the size; returns 0 on success, *n_channels as stored.
+int pth_decode_image(const char* path, int* w, int* h, int* n_channels, unsigned char* out, long long capacity) {
+  ptio::DecodedImage im;
+  if (!ptio::decode_image_file(path, im)) {
+    fprintf(stderr, "pth_decode_image: %s\n", im.error.c_str());
+    return PT_ERR_INVALID;
+  }
+  *w = im.w;
+  *h = im.h;
+  *n_channels = im.n;
+  if (out) {
+    if (capacity < (long long)im.px.size()) return PT_ERR_INVALID;
+    memcpy(out, im.px.data(), im.px.size());
+  }
+  return PT_OK;
+}
+
+// Image_Texture's loader (host_includes/textures.hpp: float4 texels, optional vertical flip)
+int pth_load_ldr_image(const char* path, int flip_y, int* w, int* h, float* rgba, long long capacity_bytes) {
+  std::vector<float> px;
+  if (!ptio::load_ldr_image(path, *w, *h, px, flip_y != 0)) return PT_ERR_INVALID;
+  if (rgba) {
+    if (capacity_bytes < (long long)(px.size() * sizeof(float))) return PT_ERR_INVALID;
+    memcpy(rgba, px.data(), px.size() * sizeof(float));
+  }
+  return PT_OK;
 }
 }

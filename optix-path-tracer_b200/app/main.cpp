@@ -24,6 +24,7 @@ static int Scene_Config(App_State& app) {
     case 5: Cornell_Materials(app); break;
     case 6: Mesh_HDRI(app); break;
     case 7: Cornell_Sphere_Light(app); break;
+    case 8: Textured_Mesh(app); break;
     default: throw "Selected scene is unknown";
   }
   app.accBuffer = createFrameBuffer(app.W, app.H, app.context);

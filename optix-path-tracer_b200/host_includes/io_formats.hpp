@@ -1,5 +1,6 @@
 // io_formats.hpp — small self-contained file-format codecs the host facade
-// needs: PNG writer (stored deflate), Radiance .hdr reader/writer, PPM reader,
+// needs: PNG writer (stored deflate), Radiance .hdr reader/writer, PNG/JPEG/PPM readers
+// (image_decode.hpp),
 // Wavefront OBJ/MTL reader.  They stand in for the third-party libraries the
 // reference vendors (stb_image, stb_image_write, HDRloader, tinyobjloader);
 // written from the format specifications, not derived from those libraries.
@@ -14,6 +15,8 @@
 #include <sstream>
 #include <string>
 #include <vector>
+
+#include "image_decode.hpp"
 
 namespace ptio {
 
@@ -169,35 +172,29 @@ inline bool write_radiance_hdr(const std::string& path, int W, int H, const floa
   return true;
 }
 
-// ---- LDR images: binary PPM (P6).  JPEG/PNG decoding is not implemented. --------
+// ---- LDR images: PNG, baseline JPEG, binary PPM (image_decode.hpp) --------------------------------------
 // Produces the float4 texels the reference's normalised-float sampler would return:
 // rgb/255, alpha = 1/255 for 3-channel images (textures.hpp:152-156 `(unsigned char)1.f`).
 inline bool load_ldr_image(const std::string& path, int& W, int& H, std::vector<float>& rgba, bool flip_y) {
-  FILE* f = fopen(path.c_str(), "rb");
-  if (!f) return false;
-  char magic[3] = {0, 0, 0};
-  int maxv = 0;
-  auto skip = [&]() {
-    int c;
-    while ((c = fgetc(f)) != EOF) {
-      if (c == '#') { while ((c = fgetc(f)) != EOF && c != '\n') {} }
-      else if (!isspace(c)) { ungetc(c, f); break; }
-    }
-  };
-  if (fscanf(f, "%2s", magic) != 1 || strcmp(magic, "P6") != 0) { fclose(f); return false; }
-  skip(); if (fscanf(f, "%d", &W) != 1) { fclose(f); return false; }
-  skip(); if (fscanf(f, "%d", &H) != 1) { fclose(f); return false; }
-  skip(); if (fscanf(f, "%d", &maxv) != 1 || maxv != 255) { fclose(f); return false; }
-  fgetc(f);
-  std::vector<unsigned char> px((size_t)W * H * 3);
-  if (fread(px.data(), 1, px.size(), f) != px.size()) { fclose(f); return false; }
-  fclose(f);
+  DecodedImage im;
+  if (!decode_image_file(path, im)) {
+    fprintf(stderr, "load_ldr_image(%s): %s\n", path.c_str(), im.error.c_str());
+    return false;
+  }
+  W = im.w;
+  H = im.h;
   rgba.resize((size_t)W * H * 4);
   for (int y = 0; y < H; y++)
     for (int x = 0; x < W; x++) {
-      const unsigned char* s = &px[3 * ((size_t)(flip_y ? H - 1 - y : y) * W + x)];
+      const unsigned char* s = &im.px[(size_t)im.n * ((size_t)(flip_y ? H - 1 - y : y) * W + x)];
       float* o = &rgba[4 * ((size_t)y * W + x)];
-      o[0] = s[0] / 255.f; o[1] = s[1] / 255.f; o[2] = s[2] / 255.f; o[3] = 1.f / 255.f;
+      // textures.hpp:143-156: RGB copied, alpha kept for 4-channel files, else (unsigned char)1.f.
+      // Grey files are replicated (the reference indexes past the pixel there).
+      const bool grey = im.n < 3;
+      o[0] = s[0] / 255.f;
+      o[1] = s[grey ? 0 : 1] / 255.f;
+      o[2] = s[grey ? 0 : 2] / 255.f;
+      o[3] = im.n == 4 ? s[3] / 255.f : 1.f / 255.f;
     }
   return true;
 }

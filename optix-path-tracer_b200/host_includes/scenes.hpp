@@ -331,6 +331,80 @@ inline void Cornell_Sphere_Light(App_State& app) {
   finishScene(app, group, make_float3(278.f, 278.f, -800.f), make_float3(278.f, 278.f, 0.f), 40.f, 0.f, 10.f, t0);
 }
 
+// MTL-driven mesh (reference path: mesh.hpp:74-102 + vector.cu + triangle.cu:119-146):
+// a small terrain written as OBJ + MTL + PNG into /tmp, loaded WITHOUT a given material, so its
+// faces pick one of three MTL materials — a map_Kd image, and two plain Ka colours — through a
+// Vector_Texture, with vt texture coordinates and vn shading normals interpolated per hit.
+inline std::string write_textured_obj(const std::string& dir, int n) {
+  const std::string base = dir + "/ptb200_textured";
+  {  // 32x32 RGB PNG: coloured checker with a gradient (decoded again by image_decode.hpp)
+    const int S = 32;
+    std::vector<unsigned char> px((size_t)S * S * 3);
+    for (int y = 0; y < S; y++)
+      for (int x = 0; x < S; x++) {
+        const bool c = ((x / 4) + (y / 4)) & 1;
+        unsigned char* o = &px[3 * ((size_t)y * S + x)];
+        o[0] = (unsigned char)(c ? 230 : 40 + 4 * x);
+        o[1] = (unsigned char)(c ? 200 - 3 * y : 60);
+        o[2] = (unsigned char)(c ? 50 : 220 - 2 * x);
+      }
+    if (!ptio::write_png((base + ".png").c_str(), S, S, px.data())) throw "cannot write " + base + ".png";
+  }
+  {
+    FILE* f = fopen((base + ".mtl").c_str(), "w");
+    if (!f) throw "cannot write " + base + ".mtl";
+    fprintf(f, "newmtl painted\nKa 1 1 1\nKd 1 1 1\nmap_Kd ptb200_textured.png\n\n");
+    fprintf(f, "newmtl clay\nKa 0.75 0.42 0.3\nKd 0.75 0.42 0.3\n\nnewmtl moss\nKa 0.2 0.55 0.25\nKd 0.2 0.55 0.25\n");
+    fclose(f);
+  }
+  FILE* f = fopen((base + ".obj").c_str(), "w");
+  if (!f) throw "cannot write " + base + ".obj";
+  fprintf(f, "mtllib ptb200_textured.mtl\n");
+  const double size = 8.0;
+  auto height = [&](double x, double z) { return 0.5 * sin(1.1 * x) * cos(0.8 * z); };
+  for (int i = 0; i <= n; i++)
+    for (int j = 0; j <= n; j++) {
+      double x = -size / 2 + size * i / n, z = -size / 2 + size * j / n;
+      fprintf(f, "v %.7g %.7g %.7g\n", x, height(x, z), z);
+    }
+  for (int i = 0; i <= n; i++)
+    for (int j = 0; j <= n; j++) fprintf(f, "vt %.6g %.6g\n", 2.0 * i / n, 2.0 * j / n);  // wraps twice (REPEAT)
+  for (int i = 0; i <= n; i++)
+    for (int j = 0; j <= n; j++) {
+      double x = -size / 2 + size * i / n, z = -size / 2 + size * j / n, e = 1e-3;
+      double dx = (height(x + e, z) - height(x - e, z)) / (2 * e), dz = (height(x, z + e) - height(x, z - e)) / (2 * e);
+      double l = sqrt(dx * dx + 1 + dz * dz);
+      fprintf(f, "vn %.6g %.6g %.6g\n", -dx / l, 1 / l, -dz / l);
+    }
+  auto vid = [&](int i, int j) { return i * (n + 1) + j + 1; };
+  const char* names[3] = {"painted", "clay", "moss"};
+  int cur = -1;
+  for (int i = 0; i < n; i++)
+    for (int j = 0; j < n; j++) {
+      int m = (i < n / 2) ? 0 : ((j < n / 2) ? 1 : 2);
+      if (m != cur) fprintf(f, "usemtl %s\n", names[cur = m]);
+      int a = vid(i, j), b = vid(i, j + 1), c = vid(i + 1, j + 1), d = vid(i + 1, j);
+      fprintf(f, "f %d/%d/%d %d/%d/%d %d/%d/%d\nf %d/%d/%d %d/%d/%d %d/%d/%d\n", a, a, a, b, b, b, c, c, c, a, a, a, c, c, c, d, d, d);
+    }
+  fclose(f);
+  return "ptb200_textured.obj";
+}
+inline void Textured_Mesh(App_State& app) {
+  using namespace scene_detail;
+  auto t0 = std::chrono::system_clock::now();
+  Light_Sampler lights;
+  addRectLight(lights, app, -2.f, 2.f, -2.f, 2.f, 6.f, Y_AXIS, 6.f);
+  setMissProgram(app.context, GRADIENT, make_float3(1.f), make_float3(0.5f, 0.7f, 1.f));
+  Group group = beginScene(app, lights);
+  const std::string dir = "/tmp/";
+  Mesh model(write_textured_obj("/tmp", app.model > 0 ? app.model : 24), dir, app.RTX);  // no given material: MTL path
+  model.addTo(group, app.context);
+  Hitable_List list;
+  list.push(new AARect(-2.f, 2.f, -2.f, 2.f, 6.f, true, Y_AXIS, new Diffuse_Light(new Constant_Texture(6.f))));
+  list.addElementsTo(group, app.context);
+  finishScene(app, group, make_float3(0.f, 5.f, -9.f), make_float3(0.f), 40.f, 0.f, 10.f, t0);
+}
+
 // BASELINE configs C4/C5: procedural triangle mesh (OBJ written locally, loaded via Mesh) lit by a
 // synthetic equirect HDRI (Radiance .hdr written locally, loaded via the HDR miss program)
 inline void Mesh_HDRI(App_State& app) {

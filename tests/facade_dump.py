@@ -20,7 +20,9 @@ def desc_arrays(d):
     out = {
         "prims": arr(d.prims, d.n_prims, np.int32, 4), "spheres": arr(d.spheres, d.n_spheres, np.float32, 4),
         "rects": arr(d.rects, d.n_rects, np.uint32, 7), "boxes": arr(d.boxes, d.n_boxes, np.float32, 6),
-        "tri_v": arr(d.tri_v, d.n_tris, np.float32, 9), "xforms": arr(d.xforms, d.n_xforms, np.float32, 24),
+        "tri_v": arr(d.tri_v, d.n_tris, np.float32, 9), "tri_n": arr(d.tri_n, d.n_tris, np.float32, 9),
+        "tri_uv": arr(d.tri_uv, d.n_tris, np.float32, 6), "tri_tex": arr(d.tri_tex, d.n_tris, np.int32),
+        "xforms": arr(d.xforms, d.n_xforms, np.float32, 24),
         "materials": arr(d.materials, d.n_materials, np.uint32, 6), "textures": arr(d.textures, d.n_textures, np.uint32, 6),
         "texvec": arr(d.texvec, d.n_texvec, np.int32), "lights": arr(d.lights, d.n_lights, np.uint32, 10),
         "camera": np.frombuffer(bytes(d.camera), dtype=np.float32).copy(),

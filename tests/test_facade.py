@@ -91,6 +91,28 @@ def test_sphere_pdf_light_through_the_facade(host_so, tmp_path):
     assert lights[0][0] == pt.LIGHT_SPHERE and lights[1][0] == pt.LIGHT_RECT
 
 
+def test_mtl_driven_textured_mesh(host_so, tmp_path):
+    """Mesh(file, assets, RTX) without a given material (reference mesh.hpp:74-102): MTL materials
+    become a Vector_Texture of albedos — a decoded map_Kd PNG and two Ka colours — indexed per
+    triangle; vt / vn arrive as per-corner arrays.  The oracle and the device cores (host build)
+    render the scene bit-identically, so texture lookup, uv and shading-normal interpolation
+    (triangle.cu:119-146, vector.cu, image_texture.cu) agree."""
+    a = dump(host_so, 8, 32, 32, 12, tmp_path, "mine")
+    ntri = 12 * 12 * 2
+    assert len(a["tri_v"]) == ntri * 9 and len(a["tri_n"]) == ntri * 9 and len(a["tri_uv"]) == ntri * 6
+    assert a["n_images"] == 1
+    kinds = [int(k) for k in a["textures"].reshape(-1, 6)[:, 0]]
+    assert pt.TEX_IMAGE in kinds and pt.TEX_VECTOR in kinds
+    tri_tex = a["tri_tex"]
+    assert len(tri_tex) == ntri and set(np.unique(tri_tex)) == {0, 1, 2}
+    sc = facade_dump.build(host_so, 8, 32, 32, 12)
+    o, _ = h.OracleScene(sc).render(32, 32, 0, 2)
+    s = h.SimScene(sc).render(32, 32, 0, 2)
+    assert np.array_equal(o, s)
+    # the painted half really shows the checker: strong colour variation on that side only
+    assert np.isfinite(o).all() and o[..., :3].std() > 0.05
+
+
 @pytest.mark.skipif(not os.path.exists(REF_SCENES), reason="reference tree not present")
 def test_reference_scenes_header_drops_in(host_so, tmp_path):
     """Compile the reference's scenes.hpp (copied to a temp dir, never into the repo) against
