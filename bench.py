@@ -36,6 +36,8 @@ WORKLOADS = {
     "c3": ("C3 Cornell + glass sphere + Oren-Nayar/Torrance-Sparrow/Ashikhmin-Shirley, RR, 1024x1024 @ 1024 spp",
            1024, 1024, 1024),
     "c4": ("C4 procedural 1M-triangle mesh + synthetic HDRI env map 1920x1080 @ 512 spp", 1920, 1080, 512),
+    "c4_10m": ("C4 procedural 10M-triangle mesh + synthetic HDRI env map 1920x1080 @ 512 spp (scene arrays built "
+               "directly, not through the OBJ file)", 1920, 1080, 512),
     # the multi-GPU configuration: 4096 spp are SPLIT across the ranks (strong scaling)
     "c5": ("C5 procedural 1M-triangle mesh + HDRI 3840x2160 @ 4096 spp, sample-split across ranks", 3840, 2160, 4096),
 }
@@ -72,7 +74,7 @@ def _build_scene(h, name, W, H, lib=None):
     """Scenes come from the C++ host facade's scene functions (InOneWeekend, Cornell, ... — the
     reference's scene-building surface); the numpy builders are the fallback if it is not built."""
     pt = h.pt
-    if os.path.exists(pt.HOST_LIB_PATH) and not os.environ.get("PTB200_NO_FACADE"):
+    if name in FACADE_IDS and os.path.exists(pt.HOST_LIB_PATH) and not os.environ.get("PTB200_NO_FACADE"):
         import facade_dump
         return facade_dump.build(pt.HOST_LIB_PATH, FACADE_IDS[name], W, H, 0)
     if name == "c1":
@@ -83,6 +85,8 @@ def _build_scene(h, name, W, H, lib=None):
         return h.build_material_zoo(W, H, lib)
     if name in ("c4", "c5"):
         return h.build_mesh_scene(708, W, H, lib)
+    if name == "c4_10m":
+        return h.build_mesh_scene(2237, W, H, lib)
     raise SystemExit(f"unknown workload {name}")
 
 
@@ -316,6 +320,46 @@ def main():
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_val = float(W) * H * total_spp * e2e_steps / float(te[0]) / 1e6
 
+    # ---- north_star target: incoherent secondary rays on the triangle scenes --------------------------
+    # uniformly random directions from the first-hit points of the camera rays (origins scattered over
+    # the whole mesh, directions uncorrelated), traced through pt_trace_rays_device on resident buffers
+    incoherent = None
+    if rank == 0 and args.workload.startswith("c4"):
+        g = torch.Generator(device="cuda").manual_seed(1)
+        n_r = 1 << 22
+        cam = sc.desc().camera
+        o = torch.tensor(list(cam.origin), device="cuda")
+        llc, hor, ver = (torch.tensor(list(v), device="cuda") for v in (cam.lower_left_corner, cam.horizontal, cam.vertical))
+        uv = torch.rand(n_r, 2, device="cuda", generator=g)
+        d = llc + uv[:, :1] * hor + uv[:, 1:] * ver - o
+        cam_rays = torch.zeros(n_r, 8, device="cuda")
+        cam_rays[:, 0:3], cam_rays[:, 3], cam_rays[:, 4:7], cam_rays[:, 7] = o, 1e-6, d, 1e27
+        hits = torch.zeros(n_r, 4, device="cuda")
+        lib.pt_trace_rays_device(sc.h, cam_rays.data_ptr(), n_r, hits.data_ptr(), None)
+        torch.cuda.synchronize()
+        t = hits[:, 0:1]
+        hit = (hits.view(torch.int32)[:, 1] >= 0)
+        P = (o + t * d)[hit]
+        n_s = P.shape[0]
+        dirs = torch.randn(n_s, 3, device="cuda", generator=g)
+        dirs = dirs / dirs.norm(dim=1, keepdim=True)
+        sec = torch.zeros(n_s, 8, device="cuda")
+        sec[:, 0:3], sec[:, 3], sec[:, 4:7], sec[:, 7] = P, 1e-3, dirs, 1e27
+        hits2 = torch.zeros(n_s, 4, device="cuda")
+        for _ in range(3):
+            lib.pt_trace_rays_device(sc.h, sec.data_ptr(), n_s, hits2.data_ptr(), None)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 10
+        e0.record()
+        for _ in range(reps):
+            lib.pt_trace_rays_device(sc.h, sec.data_ptr(), n_s, hits2.data_ptr(), None)
+        e1.record()
+        e1.synchronize()
+        incoherent = {"rays": int(n_s), "mrays_per_s": n_s * reps / (e0.elapsed_time(e1) * 1e-3) / 1e6,
+                      "hit_fraction": float((hits2.view(torch.int32)[:, 1] >= 0).float().mean()),
+                      "what": "uniform random directions from first-hit points, closest-hit queries, resident buffers"}
+        del cam_rays, hits, sec, hits2
+
     # ---- roofline of the dominant kernel (closest-hit traversal), separate instrumented passes ----
     roof = None
     cpu_base = None
@@ -382,6 +426,7 @@ def main():
                        "l2": "flushed between timed steps (256 MiB write); path pool >> L2",
                        "prims": info.n_prims, "bvh8_nodes": info.n_bvh8_nodes, "parallelism": f"sample-split x{world}"},
             "mrays_per_s": rays / (ms_dev * 1e-3) / 1e6,
+            "incoherent_secondary": incoherent,
             "wall_ms_per_step": wall / args.steps * 1e3,
             "clocks": sampler.result(),
             "e2e": {"value": e2e_val, "unit": "Msamples/s", "h2d_bytes_per_step": int(h2d),

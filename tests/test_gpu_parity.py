@@ -361,7 +361,7 @@ def test_textured_mtl_mesh_parity(lib):
     assert (d > 1e-3).mean() <= 0.02
     assert abs(g[..., :3].mean() - a[..., :3].mean()) <= 0.01 * a[..., :3].mean()
     rays = h.random_rays(20000, 11, extent=5.0)
-    hg, _ = sc.trace(rays)
+    hg = sc.trace(rays)
     ho, _ = h.OracleScene(sc, mode=1).trace(rays)
     assert same_hits(ho, hg).all()
 
