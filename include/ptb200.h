@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define PTB200_ABI_VERSION 1
+#define PTB200_ABI_VERSION 2
 
 typedef enum pt_status {
   PT_OK = 0,
@@ -45,8 +45,19 @@ typedef enum pt_status {
 /* programs/common.hpp:26 `typedef enum { X_AXIS, Y_AXIS, Z_AXIS } AXIS;` */
 enum { PT_X_AXIS = 0, PT_Y_AXIS = 1, PT_Z_AXIS = 2 };
 
-/* primitive kinds: programs/hitables/{triangle,sphere,aarect,box}.cu */
-enum { PT_PRIM_TRIANGLE = 0, PT_PRIM_SPHERE = 1, PT_PRIM_RECT = 2, PT_PRIM_BOX = 3 };
+/* primitive kinds: programs/hitables/{triangle,sphere,aarect,box,moving_sphere,volume_sphere,
+ * volume_box}.cu.  Kinds >= PT_PRIM_MOVING_SPHERE read per-ray data during traversal (the
+ * sample's shutter time `prd.time`, the path's RNG state `prd.seed`). */
+enum {
+  PT_PRIM_TRIANGLE = 0,
+  PT_PRIM_SPHERE = 1,
+  PT_PRIM_RECT = 2,
+  PT_PRIM_BOX = 3,
+  PT_PRIM_MOVING_SPHERE = 4,
+  PT_PRIM_VOLUME_SPHERE = 5,
+  PT_PRIM_VOLUME_BOX = 6,
+  PT_PRIM_KIND_COUNT = 7
+};
 
 /* host_includes/hitables.hpp:73-128 `Sphere(center, radius, BRDF*)` */
 typedef struct pt_sphere {
@@ -68,6 +79,33 @@ typedef struct pt_box {
   float bmax[3];
 } pt_box;
 
+/* host_includes/hitables.hpp:131-173 `Moving_Sphere(c0, c1, t0, t1, r, BRDF*)`,
+ * programs/hitables/moving_sphere.cu: centre moves linearly from center0 (time0) to center1
+ * (time1); a ray sees it at its sample's shutter time (programs/raygen.cu:69). */
+typedef struct pt_moving_sphere {
+  float center0[3];
+  float center1[3];
+  float radius;
+  float time0, time1;
+} pt_moving_sphere;
+
+/* host_includes/hitables.hpp:175-217 `Volumetric_Sphere(center, radius, density, BRDF*)`,
+ * programs/hitables/volume_sphere.cu: constant-density medium bounded by a sphere; the hit is a
+ * scattering event at an exponentially distributed distance after the entry point. */
+typedef struct pt_volume_sphere {
+  float center[3];
+  float radius;
+  float density;
+} pt_volume_sphere;
+
+/* host_includes/hitables.hpp:316-350 `Volumetric_Box(p0, p1, density, BRDF*)`,
+ * programs/hitables/volume_box.cu */
+typedef struct pt_volume_box {
+  float bmin[3];
+  float bmax[3];
+  float density;
+} pt_volume_box;
+
 /* host_includes/materials.hpp:42-242 */
 enum {
   PT_MAT_LAMBERTIAN = 0,        /* Lambertian(tex)                              */
@@ -82,7 +120,9 @@ enum {
   PT_MAT_ASHIKHMIN_SHIRLEY = 6, /* Ashikhmin_Shirley(diff,spec,nu,nv) tex0=diffuse
                                    tex1=specular p0=max(1,nu) p1=max(1,nv)      */
   PT_MAT_NORMAL = 7,            /* Normal_Shader(useShadingNormal) flags bit0   */
-  PT_MAT_TYPE_COUNT = 8
+  PT_MAT_ISOTROPIC = 8,         /* Isotropic(tex): phase function of the volumes
+                                   (materials.hpp:125-141, programs/materials/isotropic.*) */
+  PT_MAT_TYPE_COUNT = 9
 };
 
 typedef struct pt_material {
@@ -227,6 +267,13 @@ typedef struct pt_scene_desc {
   const float* env_alias_prob;
   const int32_t* env_alias_idx;
   const float* env_texel_pdf;
+  /* ABI 2: time-dependent and volumetric primitives */
+  int32_t n_moving_spheres;
+  const pt_moving_sphere* moving_spheres;
+  int32_t n_volume_spheres;
+  const pt_volume_sphere* volume_spheres;
+  int32_t n_volume_boxes;
+  const pt_volume_box* volume_boxes;
 } pt_scene_desc;
 
 /* ---- scene construction --------------------------------------------------- */
@@ -252,6 +299,16 @@ int pt_scene_add_rects(pt_scene* scene, const pt_rect* prims, const float* xform
                        const int32_t* material, int32_t n, int32_t* first_prim_id);
 int pt_scene_add_boxes(pt_scene* scene, const pt_box* prims, const float* xform_o2w,
                        const int32_t* material, int32_t n, int32_t* first_prim_id);
+
+/* replaces Moving_Sphere / Volumetric_Sphere / Volumetric_Box ::getGeometryInstance
+ * (host_includes/hitables.hpp:131-217,316-350).  Volumes need a PT_MAT_ISOTROPIC material to
+ * scatter like the reference's scenes do, but any material is accepted (as in the reference). */
+int pt_scene_add_moving_spheres(pt_scene* scene, const pt_moving_sphere* prims, const float* xform_o2w,
+                                const int32_t* material, int32_t n, int32_t* first_prim_id);
+int pt_scene_add_volume_spheres(pt_scene* scene, const pt_volume_sphere* prims, const float* xform_o2w,
+                                const int32_t* material, int32_t n, int32_t* first_prim_id);
+int pt_scene_add_volume_boxes(pt_scene* scene, const pt_volume_box* prims, const float* xform_o2w,
+                              const int32_t* material, int32_t n, int32_t* first_prim_id);
 
 /* replaces Mesh::getGeometryInstance buffers (host_includes/mesh.hpp:158-201):
  * unindexed per-face arrays.  v: ntris*9; n: ntris*9 or NULL; uv: ntris*6 or

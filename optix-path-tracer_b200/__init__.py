@@ -25,8 +25,9 @@ HOST_LIB_PATH = os.path.join(_HERE, "csrc", "libptb200_host.so")
 # ---- enums (include/ptb200.h) -------------------------------------------------
 X_AXIS, Y_AXIS, Z_AXIS = 0, 1, 2
 PRIM_TRIANGLE, PRIM_SPHERE, PRIM_RECT, PRIM_BOX = 0, 1, 2, 3
+PRIM_MOVING_SPHERE, PRIM_VOLUME_SPHERE, PRIM_VOLUME_BOX = 4, 5, 6
 (MAT_LAMBERTIAN, MAT_METAL, MAT_DIELECTRIC, MAT_DIFFUSE_LIGHT, MAT_OREN_NAYAR,
- MAT_TORRANCE_SPARROW, MAT_ASHIKHMIN_SHIRLEY, MAT_NORMAL) = range(8)
+ MAT_TORRANCE_SPARROW, MAT_ASHIKHMIN_SHIRLEY, MAT_NORMAL, MAT_ISOTROPIC) = range(9)
 TEX_CONSTANT, TEX_CHECKER, TEX_IMAGE, TEX_VECTOR, TEX_NOISE, TEX_GRADIENT = 0, 1, 2, 3, 4, 5
 MISS_GRADIENT, MISS_CONSTANT, MISS_IMG, MISS_HDR = 0, 1, 2, 3
 LIGHT_RECT, LIGHT_SPHERE = 0, 1
@@ -46,6 +47,19 @@ class Rect(C.Structure):
 
 class Box(C.Structure):
     _fields_ = [("bmin", F3), ("bmax", F3)]
+
+
+class MovingSphere(C.Structure):
+    _fields_ = [("center0", F3), ("center1", F3), ("radius", C.c_float),
+                ("time0", C.c_float), ("time1", C.c_float)]
+
+
+class VolumeSphere(C.Structure):
+    _fields_ = [("center", F3), ("radius", C.c_float), ("density", C.c_float)]
+
+
+class VolumeBox(C.Structure):
+    _fields_ = [("bmin", F3), ("bmax", F3), ("density", C.c_float)]
 
 
 class Material(C.Structure):
@@ -112,6 +126,9 @@ class SceneDesc(C.Structure):
         ("camera", Camera), ("miss", Miss),
         ("env_n", C.c_int32), ("env_alias_prob", C.POINTER(C.c_float)),
         ("env_alias_idx", C.POINTER(C.c_int32)), ("env_texel_pdf", C.POINTER(C.c_float)),
+        ("n_moving_spheres", C.c_int32), ("moving_spheres", C.POINTER(MovingSphere)),
+        ("n_volume_spheres", C.c_int32), ("volume_spheres", C.POINTER(VolumeSphere)),
+        ("n_volume_boxes", C.c_int32), ("volume_boxes", C.POINTER(VolumeBox)),
     ]
 
 
@@ -139,6 +156,7 @@ HIT_DTYPE = np.dtype([("t", np.float32), ("prim", np.int32), ("u", np.float32), 
 ABI_SYMBOLS = [
     "pt_last_error", "pt_abi_version", "pt_scene_create", "pt_scene_destroy",
     "pt_scene_add_spheres", "pt_scene_add_rects", "pt_scene_add_boxes", "pt_scene_add_mesh",
+    "pt_scene_add_moving_spheres", "pt_scene_add_volume_spheres", "pt_scene_add_volume_boxes",
     "pt_scene_set_materials", "pt_scene_set_textures", "pt_scene_set_texture_vector",
     "pt_scene_set_texture_data",
     "pt_scene_add_image", "pt_scene_set_lights", "pt_scene_set_camera", "pt_scene_set_miss",
@@ -175,6 +193,9 @@ def load(path: Optional[str] = None) -> C.CDLL:
         "pt_scene_add_spheres": [vp, vp, vp, vp, i32, P(i32)],
         "pt_scene_add_rects": [vp, vp, vp, vp, i32, P(i32)],
         "pt_scene_add_boxes": [vp, vp, vp, vp, i32, P(i32)],
+        "pt_scene_add_moving_spheres": [vp, vp, vp, vp, i32, P(i32)],
+        "pt_scene_add_volume_spheres": [vp, vp, vp, vp, i32, P(i32)],
+        "pt_scene_add_volume_boxes": [vp, vp, vp, vp, i32, P(i32)],
         "pt_scene_add_mesh": [vp, vp, vp, vp, vp, i32, vp, i32, P(i32)],
         "pt_scene_set_materials": [vp, vp, i32],
         "pt_scene_set_textures": [vp, vp, i32],
@@ -271,6 +292,15 @@ class Scene:
 
     def add_boxes(self, prims: Sequence[Box], materials, xforms=None) -> int:
         return self._add(self.lib.pt_scene_add_boxes, Box, prims, xforms, materials)
+
+    def add_moving_spheres(self, prims: Sequence[MovingSphere], materials, xforms=None) -> int:
+        return self._add(self.lib.pt_scene_add_moving_spheres, MovingSphere, prims, xforms, materials)
+
+    def add_volume_spheres(self, prims: Sequence[VolumeSphere], materials, xforms=None) -> int:
+        return self._add(self.lib.pt_scene_add_volume_spheres, VolumeSphere, prims, xforms, materials)
+
+    def add_volume_boxes(self, prims: Sequence[VolumeBox], materials, xforms=None) -> int:
+        return self._add(self.lib.pt_scene_add_volume_boxes, VolumeBox, prims, xforms, materials)
 
     def add_mesh(self, v, material: int, n=None, uv=None, tex_index=None, xform=None) -> int:
         v = _f32(v).reshape(-1, 9)

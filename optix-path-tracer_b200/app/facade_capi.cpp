@@ -18,15 +18,17 @@ int pth_build_scene(int scene_id, int W, int H, int model, pt_scene** out) {
     app.model = model;
     switch (scene_id) {
       case 0: InOneWeekend(app); break;
+      case 1: MovingSpheres(app); break;    // reference build: needs ../../../assets/other_textures/map.jpg
       case 2: Cornell(app); break;
+      case 3: Final_Next_Week(app); break;  // reference build: same asset
 #ifndef PTH_REFERENCE_SCENES
-      case 1: MovingSpheres(app); break;
-      case 3: Final_Next_Week(app); break;
       case 4: Test_Scene(app); break;
       case 5: Cornell_Materials(app); break;
       case 6: Mesh_HDRI(app); break;
       case 7: Cornell_Sphere_Light(app); break;
       case 8: Textured_Mesh(app); break;
+      case 9: Motion_Blur(app); break;
+      case 10: Cornell_Smoke(app); break;
 #endif
       default: return PT_ERR_INVALID;
     }

@@ -25,6 +25,8 @@ static int Scene_Config(App_State& app) {
     case 6: Mesh_HDRI(app); break;
     case 7: Cornell_Sphere_Light(app); break;
     case 8: Textured_Mesh(app); break;
+    case 9: Motion_Blur(app); break;
+    case 10: Cornell_Smoke(app); break;
     default: throw "Selected scene is unknown";
   }
   app.accBuffer = createFrameBuffer(app.W, app.H, app.context);
@@ -54,7 +56,7 @@ int main(int ac, char** av) {
     else if (arg("--type")) app.fileType = atoi(av[++i]);
     else if (arg("--batch")) batch = atoi(av[++i]);
     else {
-      printf("usage: %s [--width W] [--height H] [--samples N] [--scene 0..6] [--model M] [--depth D]\n"
+      printf("usage: %s [--width W] [--height H] [--samples N] [--scene 0..10] [--model M] [--depth D]\n"
              "          [--russian 0|1] [--file name] [--type 0(PNG)|1(HDR)] [--batch frames-per-launch]\n", av[0]);
       return 1;
     }

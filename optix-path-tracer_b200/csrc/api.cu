@@ -205,6 +205,31 @@ int pt_scene_add_boxes(pt_scene* s, const pt_box* p, const float* xf, const int3
   return add_analytic(s, s->boxes, PT_PRIM_BOX, p, xf, m, n, first);
 }
 
+int pt_scene_add_moving_spheres(pt_scene* s, const pt_moving_sphere* p, const float* xf, const int32_t* m, int32_t n,
+                                int32_t* first) {
+  return add_analytic(s, s->moving_spheres, PT_PRIM_MOVING_SPHERE, p, xf, m, n, first);
+}
+int pt_scene_add_volume_spheres(pt_scene* s, const pt_volume_sphere* p, const float* xf, const int32_t* m, int32_t n,
+                                int32_t* first) {
+  if (s && p)
+    for (int i = 0; i < n; i++)
+      if (!(p[i].density > 0.f)) {
+        pt_set_error("Volumetric_Sphere: density must be > 0");
+        return PT_ERR_INVALID;
+      }
+  return add_analytic(s, s->volume_spheres, PT_PRIM_VOLUME_SPHERE, p, xf, m, n, first);
+}
+int pt_scene_add_volume_boxes(pt_scene* s, const pt_volume_box* p, const float* xf, const int32_t* m, int32_t n,
+                              int32_t* first) {
+  if (s && p)
+    for (int i = 0; i < n; i++)
+      if (!(p[i].density > 0.f)) {
+        pt_set_error("Volumetric_Box: density must be > 0");
+        return PT_ERR_INVALID;
+      }
+  return add_analytic(s, s->volume_boxes, PT_PRIM_VOLUME_BOX, p, xf, m, n, first);
+}
+
 int pt_scene_add_mesh(pt_scene* s, const float* v, const float* nrm, const float* uv, const int32_t* tex_index,
                       int32_t ntris, const float* xf, int32_t material, int32_t* first) {
   if (!s || ntris < 0 || (ntris > 0 && !v)) {
@@ -425,6 +450,9 @@ int pt_scene_commit(pt_scene* s) {
   if ((rc = upload_vec(s->d_spheres, s->spheres))) return rc;
   if ((rc = upload_vec(s->d_rects, s->rects))) return rc;
   if ((rc = upload_vec(s->d_boxes, s->boxes))) return rc;
+  if ((rc = upload_vec(s->d_moving_spheres, s->moving_spheres))) return rc;
+  if ((rc = upload_vec(s->d_volume_spheres, s->volume_spheres))) return rc;
+  if ((rc = upload_vec(s->d_volume_boxes, s->volume_boxes))) return rc;
   if ((rc = upload_vec(s->d_tri_v, s->tri_v))) return rc;
   if ((rc = upload_vec(s->d_tri_n, s->tri_n))) return rc;
   if ((rc = upload_vec(s->d_tri_uv, s->tri_uv))) return rc;
@@ -478,6 +506,7 @@ int pt_scene_commit(pt_scene* s) {
   d.env_n = (int)s->env_alias_prob.size();
   d.env_w = d.env_n ? s->images[s->miss.image].width : 0;
   d.env_h = d.env_n ? s->images[s->miss.image].height : 0;
+  d.special_mask = (s->moving_spheres.empty() ? 0 : 1) | (s->volume_spheres.empty() && s->volume_boxes.empty() ? 0 : 2);
   d.n_prims = (int)s->prims.size();
   d.n_materials = nm;
   d.n_textures = (int)s->textures.size();
@@ -532,6 +561,12 @@ int pt_scene_get_desc(const pt_scene* cs, pt_scene_desc* o) {
   o->env_alias_prob = s->env_alias_prob.data();
   o->env_alias_idx = s->env_alias_idx.data();
   o->env_texel_pdf = s->env_texel_pdf.data();
+  o->n_moving_spheres = (int)s->moving_spheres.size();
+  o->moving_spheres = s->moving_spheres.data();
+  o->n_volume_spheres = (int)s->volume_spheres.size();
+  o->volume_spheres = s->volume_spheres.data();
+  o->n_volume_boxes = (int)s->volume_boxes.size();
+  o->volume_boxes = s->volume_boxes.data();
   return PT_OK;
 }
 

@@ -201,6 +201,11 @@ int pt_bvh_build(pt_scene* s) {
   in.spheres = s->d_spheres.as<pt_sphere>();
   in.rects = s->d_rects.as<pt_rect>();
   in.boxes = s->d_boxes.as<pt_box>();
+  in.moving_spheres = s->d_moving_spheres.as<pt_moving_sphere>();
+  in.volume_spheres = s->d_volume_spheres.as<pt_volume_sphere>();
+  in.volume_boxes = s->d_volume_boxes.as<pt_volume_box>();
+  in.cam_time0 = s->camera.time0;
+  in.cam_time1 = s->camera.time1;
   in.tri_v = s->d_tri_v.as<float>();
   in.xforms = s->d_xforms.as<pt_xform>();
   in.materials = s->d_materials.as<pt_material>();

@@ -24,6 +24,10 @@ struct BuildIn {  // device copies of the flat scene arrays
   const pt_sphere* spheres;
   const pt_rect* rects;
   const pt_box* boxes;
+  const pt_moving_sphere* moving_spheres;
+  const pt_volume_sphere* volume_spheres;
+  const pt_volume_box* volume_boxes;
+  float cam_time0, cam_time1;  // shutter interval of the camera (bounds of moving spheres)
   const float* tri_v;
   const pt_xform* xforms;
   const pt_material* materials;
@@ -44,6 +48,13 @@ struct Bvh2 {  // LBVH / refined binary BVH over Morton-sorted primitives
 };
 
 // ---- 1: primitive bounds ---------------------------------------------------------
+// programs/hitables/moving_sphere.cu:44-46 `center(time)`, never-contracted arithmetic
+PT_HD float3 moving_center(const float* c0, const float* c1, float t0, float t1, float time) {
+  const float s = XDIV(XSUB(time, t0), XSUB(t1, t0));
+  return f3(XADD(c0[0], XMUL(s, XSUB(c1[0], c0[0]))), XADD(c0[1], XMUL(s, XSUB(c1[1], c0[1]))),
+            XADD(c0[2], XMUL(s, XSUB(c1[2], c0[2]))));
+}
+
 PT_HD void prim_bounds(const BuildIn& in, int id, float3& lo, float3& hi) {
   const pt_prim_ref p = in.prim_ref[id];
   if (p.type == PT_PRIM_TRIANGLE) {  // programs/hitables/triangle.cu:61-83
@@ -68,10 +79,28 @@ PT_HD void prim_bounds(const BuildIn& in, int id, float3& lo, float3& hi) {
       lo = f3(q.a0, q.b0, q.k);
       hi = f3(q.a1, q.b1, q.k);
     }
-  } else {  // programs/hitables/box.cu:84-88
-    const pt_box q = in.boxes[p.index];
-    lo = f3(q.bmin[0], q.bmin[1], q.bmin[2]);
-    hi = f3(q.bmax[0], q.bmax[1], q.bmax[2]);
+  } else if (p.type == PT_PRIM_MOVING_SPHERE) {  // programs/hitables/moving_sphere.cu:136-147
+    // union of the sphere's boxes at its own time0/time1 (as the reference) and at the camera's
+    // shutter times (a ray's time always lies in the camera interval; motion is linear)
+    const pt_moving_sphere q = in.moving_spheres[p.index];
+    const float ts[4] = {q.time0, q.time1, in.cam_time0, in.cam_time1};
+    lo = f3(INFINITY);
+    hi = f3(-INFINITY);
+    for (int k = 0; k < 4; k++) {
+      float3 c = moving_center(q.center0, q.center1, q.time0, q.time1, ts[k]);
+      if (!(c.x == c.x && c.y == c.y && c.z == c.z)) continue;  // time0 == time1
+      lo = fmin3(lo, c - q.radius);
+      hi = fmax3(hi, c + q.radius);
+    }
+  } else if (p.type == PT_PRIM_VOLUME_SPHERE) {  // programs/hitables/volume_sphere.cu:111-115
+    const pt_volume_sphere s = in.volume_spheres[p.index];
+    float3 c = f3(s.center[0], s.center[1], s.center[2]);
+    lo = c - s.radius;
+    hi = c + s.radius;
+  } else {  // programs/hitables/box.cu:84-88, volume_box.cu:86-90
+    const float* q = p.type == PT_PRIM_VOLUME_BOX ? in.volume_boxes[p.index].bmin : in.boxes[p.index].bmin;
+    lo = f3(q[0], q[1], q[2]);
+    hi = f3(q[3], q[4], q[5]);
     float3 l2 = fmin3(lo, hi), h2 = fmax3(lo, hi);
     lo = l2;
     hi = h2;
@@ -385,6 +414,20 @@ PT_HD LeafRec make_leaf_rec(const BuildIn& in, int id) {
     L.a.x = q.a0; L.a.y = q.a1; L.a.z = q.b0;
     L.b.x = q.b1; L.b.y = q.k;
     L.b.z = pt_u2f((uint32_t)(q.axis & 3) | (q.flip ? 4u : 0u));
+  } else if (p.type == PT_PRIM_MOVING_SPHERE) {
+    const pt_moving_sphere q = in.moving_spheres[p.index];
+    L.a.x = q.center0[0]; L.a.y = q.center0[1]; L.a.z = q.center0[2];
+    L.b.x = q.radius; L.b.y = q.time0; L.b.z = q.time1;
+    L.c.x = q.center1[0]; L.c.y = q.center1[1]; L.c.z = q.center1[2];
+  } else if (p.type == PT_PRIM_VOLUME_SPHERE) {
+    const pt_volume_sphere q = in.volume_spheres[p.index];
+    L.a.x = q.center[0]; L.a.y = q.center[1]; L.a.z = q.center[2];
+    L.b.x = q.radius; L.b.y = q.density;
+  } else if (p.type == PT_PRIM_VOLUME_BOX) {
+    const pt_volume_box q = in.volume_boxes[p.index];
+    L.a.x = q.bmin[0]; L.a.y = q.bmin[1]; L.a.z = q.bmin[2];
+    L.b.x = q.bmax[0]; L.b.y = q.bmax[1]; L.b.z = q.bmax[2];
+    L.c.x = q.density;
   } else {
     const pt_box q = in.boxes[p.index];
     L.a.x = q.bmin[0]; L.a.y = q.bmin[1]; L.a.z = q.bmin[2];

@@ -31,17 +31,18 @@ namespace cg = cooperative_groups;
 
 namespace {
 
-constexpr int NBINS = 9;  // PT_MAT_* (8) + miss
-constexpr int BIN_MISS = 8;
+constexpr int NBINS = PT_MAT_TYPE_COUNT + 1;  // PT_MAT_* + miss
+constexpr int BIN_MISS = PT_MAT_TYPE_COUNT;
+constexpr int NSHADOW = 8;
 
 struct PathBuf {  // 64 B / path
   float4* o_seed;  // origin.xyz, seed
   float4* d_pack;  // dir.xyz, pix | depth<<23 | prevSpecular<<31
   float4* thr;     // throughput.xyz, -
-  float4* rad;     // radiance.xyz, -
+  float4* rad;     // radiance.xyz, prd.time (shutter time of the sample, raygen.cu:69)
 };
-struct ShadowBuf {  // 112 B / shadow request
-  float4* s[7];
+struct ShadowBuf {  // 112 B / shadow request (+16 B: s[7].x = prd.time, only in scenes with moving/volumetric primitives)
+  float4* s[NSHADOW];
 };
 
 // Device control block.  Every atomically updated counter sits on its own 128-byte line: queue
@@ -103,7 +104,7 @@ __device__ __forceinline__ int push_slot(int* counter) {
 // then either accumulate or append the path to the next wavefront
 __device__ __forceinline__ void finish_bounce(const Params& p, Ctrl* c, const PathBuf& next, uint32_t pix,
                                               int depth, float3 o, float3 d, float3 thr, float3 rad,
-                                              uint32_t seed, bool specular, float pdf) {
+                                              uint32_t seed, bool specular, float pdf, float time) {
   if (p.russian) {
     float prob = pt_ffmax(pt_ffmax(thr.x, thr.y), thr.z);
     if (depth > 10) {
@@ -123,7 +124,7 @@ __device__ __forceinline__ void finish_bounce(const Params& p, Ctrl* c, const Pa
   next.o_seed[slot] = make_float4(o.x, o.y, o.z, __uint_as_float(seed));
   next.d_pack[slot] = make_float4(d.x, d.y, d.z, __uint_as_float(pack_state(pix, depth, specular)));
   next.thr[slot] = make_float4(thr.x, thr.y, thr.z, pdf);  // .w: BSDF pdf of this ray (env NEE MIS)
-  next.rad[slot] = make_float4(rad.x, rad.y, rad.z, 0.f);
+  next.rad[slot] = make_float4(rad.x, rad.y, rad.z, time);
 }
 
 __global__ void k_iter_begin(Ctrl* c, int pool) {
@@ -158,12 +159,12 @@ __global__ void k_generate(SceneDev sc, Params p, const Ctrl* c, PathBuf cur) {
     uint32_t seed;
     float3 o, d;
     camera_ray(sc.camera, p.W, p.H, x, y, frame, seed, o, d);
-    (void)pt_rnd(seed);  // prd.time draw, raygen.cu:69 (motion blur is out of scope; the draw is not)
+    const float time = sc.camera.time0 + pt_rnd(seed) * (sc.camera.time1 - sc.camera.time0);  // raygen.cu:69
     int s = base + i;
     cur.o_seed[s] = make_float4(o.x, o.y, o.z, __uint_as_float(seed));
     cur.d_pack[s] = make_float4(d.x, d.y, d.z, __uint_as_float(pack_state(pix, 0, false)));
     cur.thr[s] = make_float4(1.f, 1.f, 1.f, 0.f);
-    cur.rad[s] = make_float4(0.f, 0.f, 0.f, 0.f);
+    cur.rad[s] = make_float4(0.f, 0.f, 0.f, time);
   }
 }
 
@@ -185,6 +186,9 @@ struct ClosestPolicy {
     return true;
   }
   __device__ __forceinline__ bool any_hit(int) const { return false; }
+  __device__ __forceinline__ RayAux aux(int i) const {
+    return RayAux{cur.rad[i].w, __float_as_uint(cur.o_seed[i].w)};
+  }
   __device__ __forceinline__ void emit(int i, const TraceHit& h, unsigned fin) const {
     hits[i] = make_float4(h.t, __int_as_float(h.leaf), h.u, h.v);
     int key = BIN_MISS;
@@ -200,13 +204,13 @@ struct ClosestPolicy {
   }
 };
 
-template <bool COUNT>
+template <bool COUNT, bool SPECIAL>
 __global__ void __launch_bounds__(PT_TRACE_THREADS) k_trace(SceneDev sc, Ctrl* c, PathBuf cur, float4* hits,
                                                             uint32_t* bin_q, int pool, SchedParams sched) {
   __shared__ uint2 s_stack[PT_SMEM_STACK * PT_TRACE_THREADS];
   ClosestPolicy pol{sc, c, cur, hits, bin_q, pool};
   uint32_t cn = 0, cl = 0;
-  trace_persistent<COUNT>(sc, c->n_cur, &c->fetch_closest, pol, s_stack, sched, &c->error, cn, cl);
+  trace_persistent<COUNT, SPECIAL>(sc, c->n_cur, &c->fetch_closest, pol, s_stack, sched, &c->error, cn, cl);
   if (COUNT) {
     for (int o = 16; o > 0; o >>= 1) {
       cn += __shfl_xor_sync(0xffffffffu, cn, o);
@@ -240,13 +244,15 @@ __global__ void __launch_bounds__(128, PT_SHADE_MINBLOCKS) k_shade(SceneDev sc, 
     in.depth = (pk >> 23) & 0xff;
     in.prev_specular = (pk >> 31) != 0;
     in.last_pdf = t4.w;
+    in.time = r4.w;
     const uint32_t pix = pk & 0x7fffffu;
     ShadeOut out;
     shade_hit<MAT, LK>(sc, in, h4.x, __float_as_int(h4.y), h4.z, h4.w, out);
     if (out.kind == SH_TERMINATE) {
       accumulate(p, pix, out.col);
     } else if (out.kind == SH_BOUNCE) {
-      finish_bounce(p, c, next, pix, in.depth, out.P, out.dir, out.thr, out.rad, out.seed, out.specular, out.pdf);
+      finish_bounce(p, c, next, pix, in.depth, out.P, out.dir, out.thr, out.rad, out.seed, out.specular, out.pdf,
+                    in.time);
     } else {
       int s = push_slot(&c->n_shadow);
       uint32_t pk2 = pack_state(pix, in.depth, out.terminal);
@@ -257,6 +263,7 @@ __global__ void __launch_bounds__(128, PT_SHADE_MINBLOCKS) k_shade(SceneDev sc, 
       sb.s[4][s] = make_float4(out.thr.y, out.thr.z, out.rad.x, out.rad.y);
       sb.s[5][s] = make_float4(out.rad.z, out.thrS.x, out.thrS.y, out.thrS.z);
       sb.s[6][s] = make_float4(out.radS.x, out.radS.y, out.radS.z, out.env_shadow ? out.pdf : -1.f);
+      if (sc.special_mask) sb.s[7][s] = make_float4(in.time, __uint_as_float(out.seedShadow), 0.f, 0.f);
     }
   }
 }
@@ -298,6 +305,12 @@ struct ShadowPolicy {
 #else
   __device__ __forceinline__ bool any_hit(int i) const { return sb.s[6][i].w >= 0.f; }
 #endif
+  // PINNED: the reference's volume programs would read prd.seed through a PerRayData_Shadow
+  // payload (undefined); shadow rays use prd.seed as it is when Direct_Light traces them
+  __device__ __forceinline__ RayAux aux(int i) const {
+    const float4 s7 = sb.s[7][i];
+    return RayAux{s7.x, __float_as_uint(s7.y)};
+  }
   __device__ __forceinline__ void emit(int i, const TraceHit& h, unsigned) const {
     float4 s0 = sb.s[0][i], s1 = sb.s[1][i], s2 = sb.s[2][i], s3 = sb.s[3][i], s4 = sb.s[4][i], s5 = sb.s[5][i],
            s6 = sb.s[6][i];
@@ -322,17 +335,18 @@ struct ShadowPolicy {
       seed = __float_as_uint(s1.w);
     }
     if (terminal) accumulate(p, pix, rad);
-    else finish_bounce(p, c, next, pix, depth, f3(s0.x, s0.y, s0.z), dir, thr, rad, seed, false, env ? s6.w : 0.f);
+    else finish_bounce(p, c, next, pix, depth, f3(s0.x, s0.y, s0.z), dir, thr, rad, seed, false, env ? s6.w : 0.f,
+                       sc.special_mask ? sb.s[7][i].x : 0.f);
   }
 };
 
-template <bool COUNT>
+template <bool COUNT, bool SPECIAL>
 __global__ void __launch_bounds__(PT_TRACE_THREADS) k_shadow(SceneDev sc, Params p, Ctrl* c, PathBuf next, ShadowBuf sb,
                                                              SchedParams sched) {
   __shared__ uint2 s_stack[PT_SMEM_STACK * PT_TRACE_THREADS];
   ShadowPolicy pol{sc, p, c, next, sb};
   uint32_t cn = 0, cl = 0;
-  trace_persistent<COUNT>(sc, c->n_shadow, &c->fetch_shadow, pol, s_stack, sched, &c->error, cn, cl);
+  trace_persistent<COUNT, SPECIAL>(sc, c->n_shadow, &c->fetch_shadow, pol, s_stack, sched, &c->error, cn, cl);
   if (COUNT) {
     for (int o = 16; o > 0; o >>= 1) {
       cn += __shfl_xor_sync(0xffffffffu, cn, o);
@@ -349,6 +363,8 @@ __global__ void __launch_bounds__(PT_TRACE_THREADS) k_shadow(SceneDev sc, Params
 struct RaySetPolicy {
   const pt_ray* rays;
   pt_hit* hits;
+  float time;  // ray sets carry no per-ray data: every ray sees the scene at the camera's time0, seed = ray index
+  __device__ __forceinline__ RayAux aux(int i) const { return RayAux{time, (uint32_t)i}; }
   __device__ __forceinline__ bool load(int i, float3& o, float3& d, float& tmin, float& tmax) const {
     const float4* rp = (const float4*)(rays + i);
     float4 a = __ldg(rp), b = __ldg(rp + 1);
@@ -369,13 +385,13 @@ struct RaySetPolicy {
   }
 };
 
-template <bool COUNT>
+template <bool COUNT, bool SPECIAL>
 __global__ void __launch_bounds__(PT_TRACE_THREADS) k_trace_rays(SceneDev sc, const pt_ray* rays, int n, pt_hit* hits,
                                                                  unsigned long long* counters, SchedParams sched) {
   __shared__ uint2 s_stack[PT_SMEM_STACK * PT_TRACE_THREADS];
-  RaySetPolicy pol{rays, hits};
+  RaySetPolicy pol{rays, hits, sc.camera.time0};
   uint32_t cn = 0, cl = 0;
-  trace_persistent<COUNT>(sc, n, (int*)(counters + 2), pol, s_stack, sched, (int*)(counters + 3), cn, cl);
+  trace_persistent<COUNT, SPECIAL>(sc, n, (int*)(counters + 2), pol, s_stack, sched, (int*)(counters + 3), cn, cl);
   if (COUNT) {
     for (int o = 16; o > 0; o >>= 1) {
       cn += __shfl_xor_sync(0xffffffffu, cn, o);
@@ -412,20 +428,39 @@ SchedParams sched_params() {
 }
 
 // resident CTAs per SM of the persistent traversal kernels (they must all be co-resident)
-int g_trace_bpm = 0;
-int trace_blocks_per_sm() {
-  if (!g_trace_bpm) {
+int g_trace_bpm[2] = {0, 0};
+int trace_blocks_per_sm(bool special) {
+  int& bpm = g_trace_bpm[special ? 1 : 0];
+  if (!bpm) {
     int a = 0, b = 0, c = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_trace<false>, PT_TRACE_THREADS, 0);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_shadow<false>, PT_TRACE_THREADS, 0);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c, k_trace_rays<false>, PT_TRACE_THREADS, 0);
-    g_trace_bpm = std::max(1, std::min(a, std::min(b, c)));
+    if (special) {
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_trace<false, true>, PT_TRACE_THREADS, 0);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_shadow<false, true>, PT_TRACE_THREADS, 0);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c, k_trace_rays<false, true>, PT_TRACE_THREADS, 0);
+    } else {
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_trace<false, false>, PT_TRACE_THREADS, 0);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_shadow<false, false>, PT_TRACE_THREADS, 0);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c, k_trace_rays<false, false>, PT_TRACE_THREADS, 0);
+    }
+    bpm = std::max(1, std::min(a, std::min(b, c)));
 #ifdef PT_TRACE_BPM
-    g_trace_bpm = PT_TRACE_BPM;
+    bpm = PT_TRACE_BPM;
 #endif
   }
-  return g_trace_bpm;
+  return bpm;
 }
+
+// launches KERNEL<COUNT, SPECIAL> for the run-time (count, special) pair
+#define PT_LAUNCH_TRACE(KERNEL, count, special, grid, stream, ...)                                        \
+  do {                                                                                                    \
+    if (special) {                                                                                        \
+      if (count) KERNEL<true, true><<<grid, PT_TRACE_THREADS, 0, stream>>>(__VA_ARGS__);                  \
+      else KERNEL<false, true><<<grid, PT_TRACE_THREADS, 0, stream>>>(__VA_ARGS__);                       \
+    } else {                                                                                              \
+      if (count) KERNEL<true, false><<<grid, PT_TRACE_THREADS, 0, stream>>>(__VA_ARGS__);                 \
+      else KERNEL<false, false><<<grid, PT_TRACE_THREADS, 0, stream>>>(__VA_ARGS__);                      \
+    }                                                                                                     \
+  } while (0)
 
 }  // namespace
 
@@ -442,7 +477,7 @@ struct pt_renderer {
   // path index in different arrays never maps to the same DRAM/L2 partition (arrays of exactly
   // 2^26 bytes allocated back to back alias badly: measured -30 % on NEE scenes)
   DevBuf slab, ctrl;
-  float4 *pathA[4] = {}, *pathB[4] = {}, *shadow[7] = {}, *hits = nullptr;
+  float4 *pathA[4] = {}, *pathB[4] = {}, *shadow[NSHADOW] = {}, *hits = nullptr;
   uint32_t* bin_q = nullptr;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -468,7 +503,7 @@ static int ensure_pool(pt_renderer* r, long long want) {
   const size_t arr = (size_t)pool * 16;
   const size_t skew = 33 * 256;  // odd multiple of 256 B
   const size_t gap = 64 * 1024;
-  const int n_arr = 4 + 4 + 7 + 1;
+  const int n_arr = 4 + 4 + NSHADOW + 1;
   const size_t total = (arr + gap + 7 * skew + 256) * n_arr + (size_t)pool * 4 * NBINS + 64 * 1024;
   PT_CUDA(r->slab.alloc(total));
   char* base = r->slab.as<char>();
@@ -483,7 +518,7 @@ static int ensure_pool(pt_renderer* r, long long want) {
   };
   for (int i = 0; i < 4; i++) r->pathA[i] = (float4*)carve(arr);
   for (int i = 0; i < 4; i++) r->pathB[i] = (float4*)carve(arr);
-  for (int i = 0; i < 7; i++) r->shadow[i] = (float4*)carve(arr);
+  for (int i = 0; i < NSHADOW; i++) r->shadow[i] = (float4*)carve(arr);
   r->hits = (float4*)carve(arr);
   r->bin_q = (uint32_t*)(base + off);
   return PT_OK;
@@ -598,7 +633,7 @@ int pt_render(pt_renderer* r, int32_t first_frame, int32_t nframes, int32_t max_
   B.o_seed = r->pathB[0]; B.d_pack = r->pathB[1];
   B.thr = r->pathB[2]; B.rad = r->pathB[3];
   ShadowBuf sb;
-  for (int k = 0; k < 7; k++) sb.s[k] = r->shadow[k];
+  for (int k = 0; k < NSHADOW; k++) sb.s[k] = r->shadow[k];
   Ctrl* c = r->ctrl.as<Ctrl>();
   float4* hits = r->hits;
   uint32_t* bq = r->bin_q;
@@ -606,10 +641,12 @@ int pt_render(pt_renderer* r, int32_t first_frame, int32_t nframes, int32_t max_
   const bool count = (r->flags & 1) != 0;
   const bool timing = (r->flags & 2) != 0;
   const int sms = sm_count();
-  const int g_trace = sms * trace_blocks_per_sm(), g_shade = sms * 8, g_gen = sms * 4;
+  const bool special = sc.special_mask != 0;
+  const int g_trace = sms * trace_blocks_per_sm(special), g_shade = sms * 8, g_gen = sms * 4;
   const uint32_t mask = s->material_type_mask;
   const SchedParams sched = sched_params();
-  const bool need_shadow = (mask & ((1u << PT_MAT_LAMBERTIAN) | (1u << PT_MAT_OREN_NAYAR) | (1u << PT_MAT_DIFFUSE_LIGHT))) &&
+  const bool need_shadow = (mask & ((1u << PT_MAT_LAMBERTIAN) | (1u << PT_MAT_OREN_NAYAR) | (1u << PT_MAT_DIFFUSE_LIGHT) |
+                                    (1u << PT_MAT_ISOTROPIC))) &&
                            (s->lights.size() > 0 || sc.env_n > 0);
 
   bool sphere_lights = false;
@@ -627,8 +664,7 @@ int pt_render(pt_renderer* r, int32_t first_frame, int32_t nframes, int32_t max_
     if (timed) cudaEventRecord(e[0], st);
     k_generate<<<g_gen, 256, 0, st>>>(sc, p, c, cur);
     if (timed) cudaEventRecord(e[1], st);
-    if (count) k_trace<true><<<g_trace, PT_TRACE_THREADS, 0, st>>>(sc, c, cur, hits, bq, r->pool, sched);
-    else k_trace<false><<<g_trace, PT_TRACE_THREADS, 0, st>>>(sc, c, cur, hits, bq, r->pool, sched);
+    PT_LAUNCH_TRACE(k_trace, count, special, g_trace, st, sc, c, cur, hits, bq, r->pool, sched);
     if (timed) cudaEventRecord(e[2], st);
     n += 3;
 #define LAUNCH_SHADE(M, LK)                                                     \
@@ -641,10 +677,12 @@ int pt_render(pt_renderer* r, int32_t first_frame, int32_t nframes, int32_t max_
       LAUNCH_SHADE(PT_MAT_LAMBERTIAN, 1)
       LAUNCH_SHADE(PT_MAT_DIFFUSE_LIGHT, 1)
       LAUNCH_SHADE(PT_MAT_OREN_NAYAR, 1)
+      LAUNCH_SHADE(PT_MAT_ISOTROPIC, 1)
     } else {
       LAUNCH_SHADE(PT_MAT_LAMBERTIAN, 0)
       LAUNCH_SHADE(PT_MAT_DIFFUSE_LIGHT, 0)
       LAUNCH_SHADE(PT_MAT_OREN_NAYAR, 0)
+      LAUNCH_SHADE(PT_MAT_ISOTROPIC, 0)
     }
     LAUNCH_SHADE(PT_MAT_METAL, 0)
     LAUNCH_SHADE(PT_MAT_DIELECTRIC, 0)
@@ -656,8 +694,7 @@ int pt_render(pt_renderer* r, int32_t first_frame, int32_t nframes, int32_t max_
     if (timed) cudaEventRecord(e[3], st);
     n++;
     if (need_shadow) {
-      if (count) k_shadow<true><<<g_trace, PT_TRACE_THREADS, 0, st>>>(sc, p, c, nxt, sb, sched);
-      else k_shadow<false><<<g_trace, PT_TRACE_THREADS, 0, st>>>(sc, p, c, nxt, sb, sched);
+      PT_LAUNCH_TRACE(k_shadow, count, special, g_trace, st, sc, p, c, nxt, sb, sched);
       n++;
     }
     if (timed) {
@@ -792,8 +829,9 @@ int pt_trace_rays_device(pt_scene* scene, const void* d_rays, int64_t n, void* d
   unsigned long long* dc = nullptr;
   PT_CUDA(cudaMallocAsync((void**)&dc, 32, st));
   PT_CUDA(cudaMemsetAsync(dc, 0, 32, st));
-  k_trace_rays<false><<<sm_count() * trace_blocks_per_sm(), PT_TRACE_THREADS, 0, st>>>(
-      scene->dev, (const pt_ray*)d_rays, (int)n, (pt_hit*)d_hits, dc, sched_params());
+  const bool special = scene->dev.special_mask != 0;
+  PT_LAUNCH_TRACE(k_trace_rays, false, special, sm_count() * trace_blocks_per_sm(special), st, scene->dev,
+                  (const pt_ray*)d_rays, (int)n, (pt_hit*)d_hits, dc, sched_params());
   PT_CUDA(cudaGetLastError());
   PT_CUDA(cudaFreeAsync(dc, st));
   return PT_OK;
@@ -816,13 +854,10 @@ int pt_trace_rays(pt_scene* scene, const pt_ray* rays, int64_t n, pt_hit* hits, 
   PT_CUDA(dc.alloc(32));
   PT_CUDA(cudaMemset(dc.p, 0, 32));
   PT_CUDA(cudaMemcpy(dr.p, rays, (size_t)n * sizeof(pt_ray), cudaMemcpyHostToDevice));
-  const int grid = sm_count() * trace_blocks_per_sm();
-  if (counters)
-    k_trace_rays<true><<<grid, PT_TRACE_THREADS>>>(scene->dev, dr.as<pt_ray>(), (int)n, dh.as<pt_hit>(),
-                                                   dc.as<unsigned long long>(), sched_params());
-  else
-    k_trace_rays<false><<<grid, PT_TRACE_THREADS>>>(scene->dev, dr.as<pt_ray>(), (int)n, dh.as<pt_hit>(),
-                                                    dc.as<unsigned long long>(), sched_params());
+  const bool special = scene->dev.special_mask != 0;
+  const int grid = sm_count() * trace_blocks_per_sm(special);
+  PT_LAUNCH_TRACE(k_trace_rays, counters != nullptr, special, grid, (cudaStream_t)0, scene->dev, dr.as<pt_ray>(), (int)n,
+                  dh.as<pt_hit>(), dc.as<unsigned long long>(), sched_params());
   PT_CUDA(cudaGetLastError());
   PT_CUDA(cudaMemcpy(hits, dh.p, (size_t)n * sizeof(pt_hit), cudaMemcpyDeviceToHost));
   unsigned long long hc[4];

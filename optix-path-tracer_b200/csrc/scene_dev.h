@@ -14,6 +14,8 @@
 //               a = { v0.xyz | centre | (a0,a1,b0) | bmin, prim id }
 //               b = { v1.xyz | (r,0,0)  | (b1,k,axis+4*flip) | bmax, kind | (xform+1)<<8 }
 //               c = { v2.xyz | unused                           , material id | type<<24 }
+//             moving sphere: a = centre0, b = (r, time0, time1), c = centre1
+//             volume sphere: a = centre,  b = (r, density, 0);  volume box: a = bmin, b = bmax, c.x = density
 //  prim_ref : pt_prim_ref per primitive id (typed index for normals/uvs)
 #pragma once
 #include "../../include/ptb200.h"
@@ -56,6 +58,7 @@ struct SceneDev {
   const int* env_alias_idx;
   const float* env_texel_pdf;
   int env_n, env_w, env_h;
+  int special_mask;  // bit0: moving spheres present (rays carry prd.time), bit1: volumes present (rays carry a seed)
   int n_prims, n_materials, n_textures, n_texvec, n_texdata, n_images, n_lights;
   pt_camera camera;
   pt_miss miss;

@@ -64,6 +64,9 @@ struct pt_scene {
   std::vector<pt_sphere> spheres;
   std::vector<pt_rect> rects;
   std::vector<pt_box> boxes;
+  std::vector<pt_moving_sphere> moving_spheres;
+  std::vector<pt_volume_sphere> volume_spheres;
+  std::vector<pt_volume_box> volume_boxes;
   std::vector<float> tri_v, tri_n, tri_uv;
   std::vector<int32_t> tri_tex;
   bool any_n = false, any_uv = false, any_tex = false;
@@ -85,6 +88,7 @@ struct pt_scene {
   bool env_tables_valid = false;
 
   // device side
+  DevBuf d_moving_spheres, d_volume_spheres, d_volume_boxes;
   DevBuf d_prim_ref, d_spheres, d_rects, d_boxes, d_tri_v, d_tri_n, d_tri_uv, d_tri_tex, d_xforms;
   DevBuf d_materials, d_textures, d_texvec, d_texdata, d_images, d_lights;
   std::vector<DevBuf*> d_image_texels;

@@ -184,7 +184,8 @@ struct Surface {
 
 template <int MAT>
 PT_HD float3 bsdf_sample(const Surface& s, float3 Wo, float3 N, uint32_t& seed) {
-  if (MAT == PT_MAT_DIFFUSE_LIGHT) {  // diffuse_light.cuh:7-13 random_on_unit_sphere
+  if (MAT == PT_MAT_DIFFUSE_LIGHT || MAT == PT_MAT_ISOTROPIC) {
+    // diffuse_light.cuh:7-13, isotropic.cuh:7-13: random_on_unit_sphere (3 draws)
     float3 r = pt_random_in_unit_sphere(seed);
     return r / length(r);
   }
@@ -237,6 +238,10 @@ PT_HD float3 bsdf_sample(const Surface& s, float3 Wo, float3 N, uint32_t& seed) 
 // pdf is left untouched on early-outs (callers initialise it to 0: pinned)
 template <int MAT>
 PT_HD float3 bsdf_eval(const Surface& s, float3 Wo, float3 Wi, float3 N, float& pdf) {
+  if (MAT == PT_MAT_ISOTROPIC) {  // isotropic.cuh:15-33: pdf = 0.25 * PI_F, f = 0.25 * PI_F * color
+    pdf = 0.25f * PT_PI_F;
+    return (0.25f * PT_PI_F) * s.color;
+  }
   if (MAT == PT_MAT_LAMBERTIAN) {  // lambertian.cuh:29-43
     float cosine = dot(normalize(Wi), normalize(N));
     if (cosine < 0.f) return f3(0.f);
@@ -498,7 +503,8 @@ struct HitRec {
   int material;
 };
 
-PT_HD HitRec make_hit_record(const SceneDev& sc, float3 o, float3 d, float t, int leaf, float bu, float bv) {
+PT_HD HitRec make_hit_record(const SceneDev& sc, float3 o, float3 d, float t, int leaf, float bu, float bv,
+                             float time = 0.f) {
   const LeafRec L = sc.leaves[leaf];
   HitRec rec;
   rec.Wo = normalize(-d);
@@ -548,8 +554,15 @@ PT_HD HitRec make_hit_record(const SceneDev& sc, float3 o, float3 d, float t, in
   rec.P = o2w ? xf_point(o2w, hp) : hp;
   float3 n;
   rec.u = rec.v = 0.f;
-  if (kind == PT_PRIM_SPHERE) {  // sphere.cu:65-93
-    float3 T = (hp - xyz(L.a)) / L.b.x;
+  if (kind == PT_PRIM_VOLUME_SPHERE || kind == PT_PRIM_VOLUME_BOX) {
+    n = f3(1.f, 0.f, 0.f);  // volume_sphere.cu:92-99, volume_box.cu:67-74
+  } else if (kind == PT_PRIM_SPHERE || kind == PT_PRIM_MOVING_SPHERE) {  // sphere.cu:65-93, moving_sphere.cu:82-100
+    float3 ctr = xyz(L.a);
+    if (kind == PT_PRIM_MOVING_SPHERE) {
+      const float c0[3] = {L.a.x, L.a.y, L.a.z}, c1[3] = {L.c.x, L.c.y, L.c.z};
+      ctr = moving_center(c0, c1, L.b.y, L.b.z, time);
+    }
+    float3 T = (hp - ctr) / L.b.x;
     n = T;
     float phi = atan2f(T.z, T.x);
     float theta = asinf(T.y);
@@ -690,6 +703,7 @@ struct PathIn {
   int depth;
   bool prev_specular;
   float last_pdf;  // env NEE: BSDF pdf of the direction that produced this ray (0 = unweighted)
+  float time;      // prd.time (raygen.cu:69): shutter time of the sample, read by moving spheres
 };
 
 struct ShadeOut {
@@ -705,6 +719,7 @@ struct ShadeOut {
   bool terminal;  // light-surface NEE (numLights >= 2): rad / radS are final colours
   float pdf;      // env NEE: pdf of the sampled bounce direction (carried to the next miss)
   bool env_shadow;  // shadow ray towards the environment: visible <=> nothing is hit
+  uint32_t seedShadow;  // SH_SHADOW: prd.seed when the reference traces the shadow ray (volumes read it)
 };
 
 // Direct_Light<T> (light_sample.cuh:35-103) for a cosine-type surface, split
@@ -755,7 +770,7 @@ PT_HD bool nee_begin(const SceneDev& sc, const Surface& surf, float3 P, float3 W
 
 template <int MAT, int LK = 1>
 PT_HD void shade_hit(const SceneDev& sc, const PathIn& in, float t, int leaf, float bu, float bv, ShadeOut& out) {
-  HitRec rec = make_hit_record(sc, in.o, in.d, t, leaf, bu, bv);
+  HitRec rec = make_hit_record(sc, in.o, in.d, t, leaf, bu, bv, in.time);
   const pt_material m = sc.materials[rec.material];
   float3 P = rec.P, Wo = rec.Wo, N = rec.Ns;
   Surface surf;
@@ -766,6 +781,7 @@ PT_HD void shade_hit(const SceneDev& sc, const PathIn& in, float t, int leaf, fl
   out.terminal = false;
   out.pdf = 0.f;
   out.env_shadow = false;
+  out.seedShadow = 0u;
   out.seed = in.seed;
   out.thr = in.thr;
   out.rad = in.rad;
@@ -782,6 +798,7 @@ PT_HD void shade_hit(const SceneDev& sc, const PathIn& in, float t, int leaf, fl
     uint32_t seed = in.seed;
     float lpdf;
     float3 WiL = env_sample_dir(sc, seed, lpdf);
+    out.seedShadow = seed;
     float3 direct = f3(0.f);
     bool need_shadow = false;
     if (dot(WiL, N) > 0.f && lpdf > 0.f) {
@@ -808,11 +825,13 @@ PT_HD void shade_hit(const SceneDev& sc, const PathIn& in, float t, int leaf, fl
     out.kind = need_shadow ? SH_SHADOW : SH_BOUNCE;
     return;
   }
-  if (MAT == PT_MAT_LAMBERTIAN || MAT == PT_MAT_OREN_NAYAR) {  // lambertian.cu:49-73, oren_nayar.cu:46-70
+  if (MAT == PT_MAT_LAMBERTIAN || MAT == PT_MAT_OREN_NAYAR || MAT == PT_MAT_ISOTROPIC) {
+    // lambertian.cu:49-73, oren_nayar.cu:46-70, isotropic.cu:34-60 (the latter without the clamp)
     uint32_t seed = in.seed;
     float3 WiL, directV, misDir;
     uint32_t seedV;
     bool need_shadow = nee_begin<MAT, LK>(sc, surf, P, Wo, N, false, seed, WiL, directV, seedV, misDir);
+    out.seedShadow = seed;  // state after the light draws
     out.specular = false;
     if (!need_shadow) {
       float3 Wi = bsdf_sample<MAT>(surf, Wo, N, seed);
@@ -820,7 +839,7 @@ PT_HD void shade_hit(const SceneDev& sc, const PathIn& in, float t, int leaf, fl
       float3 att = bsdf_eval<MAT>(surf, Wo, Wi, N, pdf);
       out.kind = SH_BOUNCE;
       out.dir = Wi;
-      out.thr = in.thr * clamp3(att / pdf, 0.f, 1.f);
+      out.thr = in.thr * (MAT == PT_MAT_ISOTROPIC ? att / pdf : clamp3(att / pdf, 0.f, 1.f));
       out.seed = seed;
       return;
     }
@@ -829,7 +848,7 @@ PT_HD void shade_hit(const SceneDev& sc, const PathIn& in, float t, int leaf, fl
       float pdf = 0.f;
       float3 att = bsdf_eval<MAT>(surf, Wo, misDir, N, pdf);
       out.dirS = misDir;
-      out.thrS = in.thr * clamp3(att / pdf, 0.f, 1.f);
+      out.thrS = in.thr * (MAT == PT_MAT_ISOTROPIC ? att / pdf : clamp3(att / pdf, 0.f, 1.f));
       out.radS = in.rad;
       out.seedS = seedV;  // two draws after `seed`
     }
@@ -839,7 +858,7 @@ PT_HD void shade_hit(const SceneDev& sc, const PathIn& in, float t, int leaf, fl
       float pdf = 0.f;
       float3 att = bsdf_eval<MAT>(surf, Wo, Wi, N, pdf);
       out.dir = Wi;
-      out.thr = in.thr * clamp3(att / pdf, 0.f, 1.f);
+      out.thr = in.thr * (MAT == PT_MAT_ISOTROPIC ? att / pdf : clamp3(att / pdf, 0.f, 1.f));
       out.rad = in.rad + in.thr * directV;
       out.seed = seedV;
     }
@@ -897,6 +916,7 @@ PT_HD void shade_hit(const SceneDev& sc, const PathIn& in, float t, int leaf, fl
     float3 WiL, directV, misDir;
     uint32_t seedV;
     bool need_shadow = nee_begin<MAT, LK>(sc, surf, P, Wo, N, true, seed, WiL, directV, seedV, misDir);
+    out.seedShadow = seed;
     float3 thr = in.thr;
     if (dot(N, Wo) < 0.f) thr *= surf.color;
     const bool add = in.depth == 0 || in.prev_specular;
@@ -966,6 +986,7 @@ PT_HD void shade_hit_any(const SceneDev& sc, int mat_type, const PathIn& in, flo
     case PT_MAT_OREN_NAYAR: shade_hit<PT_MAT_OREN_NAYAR>(sc, in, t, leaf, bu, bv, out); break;
     case PT_MAT_TORRANCE_SPARROW: shade_hit<PT_MAT_TORRANCE_SPARROW>(sc, in, t, leaf, bu, bv, out); break;
     case PT_MAT_ASHIKHMIN_SHIRLEY: shade_hit<PT_MAT_ASHIKHMIN_SHIRLEY>(sc, in, t, leaf, bu, bv, out); break;
+    case PT_MAT_ISOTROPIC: shade_hit<PT_MAT_ISOTROPIC>(sc, in, t, leaf, bu, bv, out); break;
     default: shade_hit<PT_MAT_NORMAL>(sc, in, t, leaf, bu, bv, out); break;
   }
 }

@@ -19,6 +19,8 @@
 // Policy interface (all __device__):
 //   bool load(int i, float3& o, float3& d, float& tmin, float& tmax)   false = empty interval
 //   bool any_hit(int i)                                                 true = stop at the first hit
+//   RayAux aux(int i)                                                   shutter time + seed of ray i (read only
+//                                                                        when a moving / volumetric leaf is tested)
 //   void emit(int i, const TraceHit& h, unsigned finished_mask)        called convergently by
 //                                                                        exactly the lanes in the mask
 #pragma once
@@ -33,7 +35,16 @@ struct SchedParams {
   int fetch_chunk;  // rays a warp claims from the queue per atomic (surplus stays warp-private); 0 = exactly the idle lanes
 };
 
-template <bool COUNT, class Policy>
+template <class Policy, bool SPECIAL>
+struct PolicyAux {
+  static constexpr bool enabled = SPECIAL;
+  const Policy& pol;
+  int ray;
+  __device__ __forceinline__ RayAux operator()() const { return pol.aux(ray); }
+};
+
+// SPECIAL: the scene holds moving / volumetric primitives (SceneDev::special_mask != 0)
+template <bool COUNT, bool SPECIAL, class Policy>
 __device__ __forceinline__ void trace_persistent(const SceneDev& sc, int n, int* fetch_counter, Policy& pol,
                                                  uint2* s_stack, const SchedParams sp_, int* error_flag, uint32_t& cn,
                                                  uint32_t& cl) {
@@ -117,7 +128,7 @@ __device__ __forceinline__ void trace_persistent(const SceneDev& sc, int n, int*
     const unsigned mN = __ballot_sync(FULL, hasN);
     if (mL != 0u && (__popc(mL) >= sp_.leaf_thresh || __popc(mL) >= __popc(mN))) {
       if (hasL) {
-        bvh8_leaf_step(sc, r, lg, hit);
+        bvh8_leaf_step(sc, r, lg, hit, PolicyAux<Policy, SPECIAL>{pol, ray});
         if (COUNT) cl++;
         if (anyhit && hit.leaf >= 0) {  // occlusion query: any hit ends the ray
           ng.y = 0u;

@@ -9,6 +9,7 @@
 // bit-identical to the CPU oracle.  The node (box) tests are allowed to use
 // FMA: boxes are padded (bvh_build) so the test only has to be conservative.
 #pragma once
+#include "bvh_core.h"
 #include "scene_dev.h"
 
 struct TraceHit {
@@ -126,9 +127,99 @@ PT_HD bool isect_box(float3 bmin, float3 bmax, float3 o, float3 d, float tmin, f
   return false;
 }
 
+// ---- time-dependent and volumetric primitives (rare: kept out of line on the device so the
+// hot triangle/sphere path of the traversal kernels keeps its register budget) ----------------
+// Per-ray data these primitives read: the sample's shutter time (prd.time, raygen.cu:69) and an
+// RNG seed.  PINNED: the reference draws `rnd(prd.seed)` inside the volume intersection programs
+// (volume_sphere.cu:80, volume_box.cu:55), i.e. once per intersection-program invocation in
+// OptiX's traversal order with OptiX's culling - unknowable and order-dependent.  Here the uniform
+// of (ray, volume primitive) is a pure function of the ray's seed and the primitive id:
+// rnd(tea<4>(seed, prim)).  Same distribution, independent of traversal order, and the path's
+// own stream is not advanced by traversal.
+struct RayAux {
+  float time;
+  uint32_t seed;
+};
+// Aux providers: `enabled == false` compiles the special-primitive branch out of the leaf test
+// (scenes without such primitives run kernels whose hot path is exactly the plain one).
+struct NoAux {
+  static constexpr bool enabled = false;
+  PT_HD RayAux operator()() const { return RayAux{0.f, 0u}; }
+};
+PT_HD float pt_volume_uniform(uint32_t seed, uint32_t prim) {
+  uint32_t v0 = seed, v1 = prim, s0 = 0;  // programs/random.cuh:33-47 tea<4>
+  for (int n = 0; n < 4; n++) {
+    s0 += 0x9e3779b9u;
+    v0 += ((v1 << 4) + 0xa341316cu) ^ (v1 + s0) ^ ((v1 >> 5) + 0xc8013ea4u);
+    v1 += ((v0 << 4) + 0xad90777du) ^ (v0 + s0) ^ ((v0 >> 5) + 0x7e95761eu);
+  }
+  v0 = 1664525u * v0 + 1013904223u;  // random.cuh:50-65 lcg + rnd
+  return (float)(v0 & 0x00FFFFFFu) / (float)0x01000000;
+}
+// programs/hitables/volume_sphere.cu:20-54 hit_boundary
+PT_HD bool vol_boundary_sphere(float3 center, float radius, float3 o, float3 d, float tmin, float tmax, float& rec) {
+  return isect_sphere(center, radius, o, d, tmin, tmax, rec);
+}
+// programs/hitables/volume_box.cu:20-42 hit_boundary
+PT_HD bool vol_boundary_box(float3 bmin, float3 bmax, float3 o, float3 d, float tmin, float tmax, float& rec) {
+  float3 t0 = f3(XDIV(XSUB(bmin.x, o.x), d.x), XDIV(XSUB(bmin.y, o.y), d.y), XDIV(XSUB(bmin.z, o.z), d.z));
+  float3 t1 = f3(XDIV(XSUB(bmax.x, o.x), d.x), XDIV(XSUB(bmax.y, o.y), d.y), XDIV(XSUB(bmax.z, o.z), d.z));
+  float temp1 = pt_ffmax(pt_ffmax(pt_ffmin(t0.x, t1.x), pt_ffmin(t0.y, t1.y)), pt_ffmin(t0.z, t1.z));
+  float temp2 = pt_ffmin(pt_ffmin(pt_ffmax(t0.x, t1.x), pt_ffmax(t0.y, t1.y)), pt_ffmax(t0.z, t1.z));
+  if (temp1 > temp2) return false;
+  if (temp1 < tmax && temp1 > tmin) {
+    rec = temp1;
+    return true;
+  }
+  if (temp2 < tmax && temp2 > tmin) {
+    rec = temp2;
+    return true;
+  }
+  return false;
+}
+// volume_sphere.cu:62-105 / volume_box.cu:44-82: scattering distance inside a constant-density
+// medium.  As written in the reference the exit distance only bounds the entry (rec1 < rec2); the
+// sampled distance itself is accepted anywhere in the ray interval.
+#ifdef __CUDACC__
+static __host__ __device__ __noinline__
+#else
+inline
+#endif
+bool isect_special(int kind, float4 La, float4 Lb, float4 Lc, float3 o, float3 d, float tmin, float tmax,
+                   float time, uint32_t seed, float& t) {
+  if (kind == PT_PRIM_MOVING_SPHERE) {  // moving_sphere.cu:54-131
+    const float c0[3] = {La.x, La.y, La.z}, c1[3] = {Lc.x, Lc.y, Lc.z};
+    return isect_sphere(moving_center(c0, c1, Lb.y, Lb.z, time), Lb.x, o, d, tmin, tmax, t);
+  }
+  const float FMAX = 3.402823466e+38f;
+  const bool box = kind == PT_PRIM_VOLUME_BOX;
+  const float density = box ? Lc.x : Lb.y;
+  float rec1, rec2;
+  if (!(box ? vol_boundary_box(xyz(La), xyz(Lb), o, d, -FMAX, FMAX, rec1)
+            : vol_boundary_sphere(xyz(La), Lb.x, o, d, -FMAX, FMAX, rec1)))
+    return false;
+  const float after = (float)((double)rec1 + 0.0001);  // `rec1 + 0.0001` is a double sum in the reference
+  if (!(box ? vol_boundary_box(xyz(La), xyz(Lb), o, d, after, FMAX, rec2)
+            : vol_boundary_sphere(xyz(La), Lb.x, o, d, after, FMAX, rec2)))
+    return false;
+  if (rec1 < tmin) rec1 = tmin;
+  if (rec2 > tmax) rec2 = tmax;
+  if (rec1 >= rec2) return false;
+  if (rec1 < 0.f) rec1 = 0.f;
+  const float len = XSQRT(xdot(d, d));
+  const float hit_distance = XMUL(-XDIV(1.f, density), logf(pt_volume_uniform(seed, pt_f2u(La.w))));
+  const float temp = XADD(rec1, XDIV(hit_distance, len));
+  if (temp > tmin && temp < tmax) {  // rtPotentialIntersection
+    t = temp;
+    return true;
+  }
+  return false;
+}
+
 // one leaf record against the (world) ray
+template <class Aux>
 PT_HD bool isect_leaf(const SceneDev& sc, const LeafRec& L, float3 o, float3 d, float tmin, float tmax, float tbest,
-                      float& t, float& u, float& v) {
+                      float& t, float& u, float& v, const Aux& aux) {
   uint32_t w = pt_f2u(L.b.w);
   int kind = PT_LEAF_KIND(w);
   u = 0.f;
@@ -139,6 +230,10 @@ PT_HD bool isect_leaf(const SceneDev& sc, const LeafRec& L, float3 o, float3 d, 
     const float* m = sc.xforms[xf].w2o;
     o = xf_point(m, o);
     d = xf_vector(m, d);
+  }
+  if (Aux::enabled && kind >= PT_PRIM_MOVING_SPHERE) {
+    const RayAux a = aux();
+    return isect_special(kind, L.a, L.b, L.c, o, d, tmin, tmax, a.time, a.seed, t);
   }
   if (kind == PT_PRIM_SPHERE) return isect_sphere(xyz(L.a), L.b.x, o, d, tmin, tmax, t);
   if (kind == PT_PRIM_RECT) {
@@ -269,7 +364,8 @@ PT_HD void bvh8_node_step(const SceneDev& sc, const RayCtx& r, float tbest, uint
 }
 
 // Tests ONE pending leaf record of `lg` (highest bit) and updates the closest hit.
-PT_HD void bvh8_leaf_step(const SceneDev& sc, const RayCtx& r, uint2& lg, TraceHit& hit) {
+template <class Aux>
+PT_HD void bvh8_leaf_step(const SceneDev& sc, const RayCtx& r, uint2& lg, TraceHit& hit, const Aux& aux) {
   const uint32_t b = (uint32_t)pt_bfind(lg.y);
   lg.y &= ~(1u << b);
   const uint32_t li = lg.x + b;
@@ -279,7 +375,7 @@ PT_HD void bvh8_leaf_step(const SceneDev& sc, const RayCtx& r, uint2& lg, TraceH
   L.b = PT_LDGF4(lp + 1);
   L.c = PT_LDGF4(lp + 2);
   float t, u, v;
-  if (isect_leaf(sc, L, r.o, r.d, r.tmin, r.tmax, hit.t, t, u, v)) {
+  if (isect_leaf(sc, L, r.o, r.d, r.tmin, r.tmax, hit.t, t, u, v, aux)) {
     const int prim = (int)pt_f2u(L.a.w);
     if (t < hit.t || (t == hit.t && (hit.prim < 0 || prim < hit.prim))) {
       hit.t = t;
@@ -295,9 +391,15 @@ PT_HD void bvh8_leaf_step(const SceneDev& sc, const RayCtx& r, uint2& lg, TraceH
 
 // Straightforward single-ray loop over the step functions (host simulation, reference for the
 // warp-scheduled GPU driver in trace_sched.cuh).
+struct FixedAux {
+  static constexpr bool enabled = true;
+  RayAux a;
+  PT_HD RayAux operator()() const { return a; }
+};
 template <bool COUNT>
 PT_HD void bvh8_closest(const SceneDev& sc, float3 o, float3 d, float tmin, float tmax,
-                        TraceHit& hit, uint32_t& n_nodes, uint32_t& n_leaves) {
+                        TraceHit& hit, uint32_t& n_nodes, uint32_t& n_leaves, RayAux ra = RayAux{0.f, 0u}) {
+  const FixedAux aux{ra};
   RayCtx r;
   ray_setup(r, o, d, tmin, tmax);
   hit_reset(hit, tmax);
@@ -313,7 +415,7 @@ PT_HD void bvh8_closest(const SceneDev& sc, float3 o, float3 d, float tmin, floa
       if ((rest.y & 0xff000000u) && sp < PT_STACK) stack[sp++] = rest;
     }
     while (lg.y) {
-      bvh8_leaf_step(sc, r, lg, hit);
+      bvh8_leaf_step(sc, r, lg, hit, aux);
       if (COUNT) n_leaves++;
     }
     if ((ng.y & 0xff000000u) == 0) {

@@ -87,23 +87,51 @@ class Box : public Hitable {
   const float3 p0, p1;
 };
 
-// Out of scope (broken/WIP in the reference); declared so
-// scene code that mentions them still compiles, rejected when added to a scene.
+// Sphere whose centre moves linearly from c0 (time t0) to c1 (time t1); a sample sees it at its
+// shutter time prd.time (reference: host_includes/hitables.hpp:131-173, constructor argument
+// order c0, c1, r, t0, t1 as there).
 class Moving_Sphere : public Hitable {
  public:
-  Moving_Sphere(const float3&, const float3&, const float, const float, const float, BRDF* m) : Hitable(m) {}
-  void emit(Context&, const Matrix4x4&) override { throw "Moving_Sphere (motion blur) is out of scope"; }
+  Moving_Sphere(const float3& c0, const float3& c1, const float r, const float t0, const float t1, BRDF* material)
+      : Hitable(material), center0(c0), center1(c1), radius(r), time0(t0), time1(t1) {}
+  void emit(Context& ctx, const Matrix4x4& o2w) override {
+    ContextObj::Batch& b = newBatch(ctx, PT_PRIM_MOVING_SPHERE, o2w);
+    b.ms = pt_moving_sphere{{center0.x, center0.y, center0.z}, {center1.x, center1.y, center1.z}, radius, time0, time1};
+  }
+
+ protected:
+  const float3 center0, center1;
+  const float radius, time0, time1;
 };
+// constant-density media (reference: host_includes/hitables.hpp:175-217, 316-350)
 class Volumetric_Sphere : public Hitable {
  public:
-  Volumetric_Sphere(const float3&, const float, const float, BRDF* m) : Hitable(m) {}
-  void emit(Context&, const Matrix4x4&) override { throw "Volumetric_Sphere (volumes) is out of scope"; }
+  Volumetric_Sphere(const float3& c, const float r, const float d, BRDF* material)
+      : Hitable(material), center(c), radius(r), density(d) {}
+  void emit(Context& ctx, const Matrix4x4& o2w) override {
+    ContextObj::Batch& b = newBatch(ctx, PT_PRIM_VOLUME_SPHERE, o2w);
+    b.vs = pt_volume_sphere{{center.x, center.y, center.z}, radius, density};
+  }
+
+ protected:
+  const float3 center;
+  const float radius, density;
 };
 class Volumetric_Box : public Hitable {
  public:
-  Volumetric_Box(const float3&, const float3&, const float, BRDF* m) : Hitable(m) {}
-  void emit(Context&, const Matrix4x4&) override { throw "Volumetric_Box (volumes) is out of scope"; }
+  Volumetric_Box(const float3& p0, const float3& p1, const float d, BRDF* material)
+      : Hitable(material), p0(p0), p1(p1), density(d) {}
+  void emit(Context& ctx, const Matrix4x4& o2w) override {
+    ContextObj::Batch& b = newBatch(ctx, PT_PRIM_VOLUME_BOX, o2w);
+    b.vb = pt_volume_box{{p0.x, p0.y, p0.z}, {p1.x, p1.y, p1.z}, density};
+  }
+
+ protected:
+  const float3 p0, p1;
+  const float density;
 };
+// Out of scope (broken in the reference); declared so scene code that
+// mentions them still compiles, rejected when added to a scene.
 class Triangle : public Hitable {
  public:
   Triangle(const float3&, const float2&, const float3&, const float2&, const float3&, const float2&, BRDF* m) : Hitable(m) {}

@@ -59,10 +59,10 @@ struct Diffuse_Light : public BRDF {
   const Texture* texture;
 };
 
-// volumes are out of scope; declared for source compatibility
+// phase function of the volumes (reference: host_includes/materials.hpp:125-141)
 struct Isotropic : public BRDF {
   Isotropic(const Texture* t) : texture(t) {}
-  Material assignTo(Context&) const override { throw "Isotropic (volumes) is out of scope"; }
+  Material assignTo(Context& c) const override { return registerOnce(c, PT_MAT_ISOTROPIC, texture, nullptr, 0, 0); }
   const Texture* texture;
 };
 

@@ -186,6 +186,7 @@ class ContextObj {
   struct Batch {  // primitives in insertion order
     int kind;
     pt_sphere s; pt_rect r; pt_box b;
+    pt_moving_sphere ms; pt_volume_sphere vs; pt_volume_box vb;
     std::vector<float> v, n, uv; std::vector<int32_t> tex;
     float xf[12]; int material;
   };
@@ -241,6 +242,9 @@ class ContextObj {
       if (b.kind == PT_PRIM_SPHERE) check(pt_scene_add_spheres(scene, &b.s, b.xf, &b.material, 1, nullptr));
       else if (b.kind == PT_PRIM_RECT) check(pt_scene_add_rects(scene, &b.r, b.xf, &b.material, 1, nullptr));
       else if (b.kind == PT_PRIM_BOX) check(pt_scene_add_boxes(scene, &b.b, b.xf, &b.material, 1, nullptr));
+      else if (b.kind == PT_PRIM_MOVING_SPHERE) check(pt_scene_add_moving_spheres(scene, &b.ms, b.xf, &b.material, 1, nullptr));
+      else if (b.kind == PT_PRIM_VOLUME_SPHERE) check(pt_scene_add_volume_spheres(scene, &b.vs, b.xf, &b.material, 1, nullptr));
+      else if (b.kind == PT_PRIM_VOLUME_BOX) check(pt_scene_add_volume_boxes(scene, &b.vb, b.xf, &b.material, 1, nullptr));
       else
         check(pt_scene_add_mesh(scene, b.v.data(), b.n.empty() ? nullptr : b.n.data(), b.uv.empty() ? nullptr : b.uv.data(),
                                 b.tex.empty() ? nullptr : b.tex.data(), (int)(b.v.size() / 9), b.xf, b.material, nullptr));
@@ -264,6 +268,9 @@ class ContextObj {
       if (b.kind == PT_PRIM_SPHERE) check(pt_scene_add_spheres(s, &b.s, b.xf, &b.material, 1, nullptr));
       else if (b.kind == PT_PRIM_RECT) check(pt_scene_add_rects(s, &b.r, b.xf, &b.material, 1, nullptr));
       else if (b.kind == PT_PRIM_BOX) check(pt_scene_add_boxes(s, &b.b, b.xf, &b.material, 1, nullptr));
+      else if (b.kind == PT_PRIM_MOVING_SPHERE) check(pt_scene_add_moving_spheres(s, &b.ms, b.xf, &b.material, 1, nullptr));
+      else if (b.kind == PT_PRIM_VOLUME_SPHERE) check(pt_scene_add_volume_spheres(s, &b.vs, b.xf, &b.material, 1, nullptr));
+      else if (b.kind == PT_PRIM_VOLUME_BOX) check(pt_scene_add_volume_boxes(s, &b.vb, b.xf, &b.material, 1, nullptr));
       else
         check(pt_scene_add_mesh(s, b.v.data(), b.n.empty() ? nullptr : b.n.data(), b.uv.empty() ? nullptr : b.uv.data(),
                                 b.tex.empty() ? nullptr : b.tex.data(), (int)(b.v.size() / 9), b.xf, b.material, nullptr));

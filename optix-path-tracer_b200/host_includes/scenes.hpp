@@ -153,8 +153,8 @@ inline void Cornell(App_State& app) {
   finishScene(app, group, make_float3(278.f, 278.f, -800.f), make_float3(278.f, 278.f, 0.f), 40.f, 0.f, 10.f, t0);
 }
 
-// "The Next Week" final scene without the volumes (out of scope) and with a constant
-// stand-in for the earth image (JPEG decoding is a "next" row)
+// "The Next Week" final scene (reference: host_includes/scenes.hpp:263-375) including its two
+// Volumetric_Spheres; a constant texture stands in for the earth image (the asset is not in the tree)
 inline void Final_Next_Week(App_State& app) {
   using namespace scene_detail;
   auto t0 = std::chrono::system_clock::now();
@@ -178,6 +178,9 @@ inline void Final_Next_Week(App_State& app) {
   list.push(new Sphere(make_float3(260.f, 150.f, 45.f), 50.f, glass));
   list.push(new Sphere(make_float3(0.f, 150.f, 145.f), 50.f, new Metal(new Constant_Texture(0.8f, 0.8f, 0.9f), 10.f)));
   list.push(new Sphere(make_float3(360.f, 150.f, 45.f), 70.f, glass));
+  list.push(new Volumetric_Sphere(make_float3(360.f, 150.f, 45.f), 70.f, 0.2f,
+                                  new Isotropic(new Constant_Texture(0.2f, 0.4f, 0.9f))));  // blue fog inside the glass
+  list.push(new Volumetric_Sphere(make_float3(0.f), 5000.f, 0.0001f, new Isotropic(one)));  // white fog everywhere
   list.push(new Sphere(make_float3(400.f, 200.f, 400.f), 100.f, new Lambertian(new Constant_Texture(0.2f, 0.4f, 0.7f))));
   list.push(new Sphere(make_float3(220.f, 280.f, 300.f), 80.f, new Lambertian(new Noise_Texture(0.1f))));  // Perlin sphere
   Hitable_List spheres;
@@ -191,6 +194,76 @@ inline void Final_Next_Week(App_State& app) {
   spheres.addListTo(group, app.context);
   list.addElementsTo(group, app.context);
   finishScene(app, group, make_float3(478.f, 278.f, -600.f), make_float3(278.f, 278.f, 0.f), 40.f, 0.f, 10.f, t0);
+}
+
+// Motion blur: the bouncing spheres of "The Next Week" through Moving_Sphere
+// (reference class: host_includes/hitables.hpp:131-173; its own MovingSpheres scene computes
+// `center2` but then adds static Spheres, host_includes/scenes.hpp:124-142)
+inline void Motion_Blur(App_State& app) {
+  using namespace scene_detail;
+  auto t0 = std::chrono::system_clock::now();
+  Light_Sampler lights;
+  setMissProgram(app.context, GRADIENT, make_float3(1.f), make_float3(0.5f, 0.7f, 1.f));
+  Group group = beginScene(app, lights);
+  Hitable_List list;
+  Texture* checker = new Checker_Texture(new Constant_Texture(0.2f, 0.3f, 0.1f), new Constant_Texture(0.9f, 0.9f, 0.9f));
+  list.push(new Sphere(make_float3(0.f, -1000.f, 0.f), 1000.f, new Lambertian(checker)));
+  for (int a = -6; a < 6; a++)
+    for (int b = -6; b < 6; b++) {
+      float choose_mat = rnd();
+      float cz = b + 0.9f * rnd();
+      float cx = a + 0.9f * rnd();
+      float3 center = make_float3(cx, 0.2f, cz);
+      float3 c = rnd3_rtl(0.5f, 1.f);
+      Texture* tx = new Constant_Texture(c.x, c.y, c.z);
+      if (choose_mat < 0.7f) {
+        float3 center2 = center + make_float3(0.f, 0.5f * rnd(), 0.f);
+        list.push(new Moving_Sphere(center, center2, 0.2f, 0.f, 1.f, new Lambertian(tx)));
+      } else if (choose_mat < 0.9f) {
+        list.push(new Sphere(center, 0.2f, new Metal(tx, 0.5f * rnd())));
+      } else {
+        list.push(new Sphere(center, 0.2f, new Dielectric(tx, tx, 1.5, 0.f)));
+      }
+    }
+  list.push(new Moving_Sphere(make_float3(-3.f, 1.f, 0.f), make_float3(-3.f, 1.f, 1.5f), 1.f, 0.f, 1.f,
+                              new Lambertian(new Constant_Texture(0.4f, 0.2f, 0.1f))));
+  list.push(new Sphere(make_float3(3.f, 1.f, 0.f), 1.f, new Metal(new Constant_Texture(0.7f, 0.6f, 0.5f), 0.f)));
+  list.addElementsTo(group, app.context);
+  finishScene(app, group, make_float3(13.f, 2.f, 3.f), make_float3(0.f), 20.f, 0.f, 10.f, t0);
+}
+
+// Volumes: Cornell box with two blocks of smoke (Volumetric_Box + Isotropic) and a fog ball
+// (Volumetric_Sphere), the "cornell_smoke" arrangement of "The Next Week"
+// (reference classes: host_includes/hitables.hpp:175-217,316-350, materials.hpp:125-141)
+inline void Cornell_Smoke(App_State& app) {
+  using namespace scene_detail;
+  auto t0 = std::chrono::system_clock::now();
+  Light_Sampler lights;
+  addRectLight(lights, app, 113.f, 443.f, 127.f, 432.f, 554.f, Y_AXIS, 7.f);
+  setMissProgram(app.context, CONSTANT);
+  Group group = beginScene(app, lights);
+  Hitable_List list;
+  BRDF* red = new Lambertian(new Constant_Texture(0.65f, 0.05f, 0.05f));
+  BRDF* white = new Lambertian(new Constant_Texture(0.73f));
+  BRDF* green = new Lambertian(new Constant_Texture(0.12f, 0.45f, 0.15f));
+  list.push(new AARect(0.f, 555.f, 0.f, 555.f, 555.f, true, X_AXIS, red));
+  list.push(new AARect(0.f, 555.f, 0.f, 555.f, 0.f, false, X_AXIS, green));
+  list.push(new AARect(113.f, 443.f, 127.f, 432.f, 554.f, true, Y_AXIS, new Diffuse_Light(new Constant_Texture(7.f))));
+  list.push(new AARect(0.f, 555.f, 0.f, 555.f, 555.f, true, Y_AXIS, white));
+  list.push(new AARect(0.f, 555.f, 0.f, 555.f, 0.f, false, Y_AXIS, white));
+  list.push(new AARect(0.f, 555.f, 0.f, 555.f, 555.f, true, Z_AXIS, white));
+  Volumetric_Box smoke0(make_float3(0.f), make_float3(165.f, 330.f, 165.f), 0.01f, new Isotropic(new Constant_Texture(0.f)));
+  smoke0.translate(make_float3(265.f, 0.f, 295.f));
+  smoke0.rotate(15.f, Y_AXIS);
+  list.push(&smoke0);
+  Volumetric_Box smoke1(make_float3(0.f), make_float3(165.f, 165.f, 165.f), 0.01f, new Isotropic(new Constant_Texture(1.f)));
+  smoke1.translate(make_float3(130.f, 0.f, 65.f));
+  smoke1.rotate(-18.f, Y_AXIS);
+  list.push(&smoke1);
+  list.push(new Volumetric_Sphere(make_float3(400.f, 420.f, 150.f), 70.f, 0.02f,
+                                  new Isotropic(new Constant_Texture(0.2f, 0.4f, 0.9f))));
+  list.addElementsTo(group, app.context);
+  finishScene(app, group, make_float3(278.f, 278.f, -800.f), make_float3(278.f, 278.f, 0.f), 40.f, 0.f, 10.f, t0);
 }
 
 // ---- procedural assets for the mesh scenes (written locally, then loaded through Mesh / HDR paths) ----

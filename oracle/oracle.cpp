@@ -25,11 +25,21 @@
 //  * `pdf` left unset by an early-out Evaluate reads as 0.
 //  * image textures: software bilinear, repeat addressing, texel centres at
 //    +0.5 (the reference uses the hardware sampler's 8-bit weights).
+//  * volumes (P/hitables/volume_sphere.cu, volume_box.cu) draw rnd(prd.seed)
+//    inside the intersection program, i.e. once per program invocation in
+//    OptiX's traversal order and under OptiX's culling - unknowable.  Pinned:
+//    the uniform of (ray, volume primitive) is rnd(tea<4>(ray seed, prim id)),
+//    where the ray seed is prd.seed when the ray is traced; the path's stream
+//    is not advanced by traversal.  Shadow rays (whose payload has no seed in
+//    the reference) use the seed at the time Direct_Light traces them.
+//  * moving spheres are bounded over the camera's shutter interval as well as
+//    their own [time0,time1] (the reference bounds only the latter).
 #include "oracle.h"
 
 #include <omp.h>
 
 #include <algorithm>
+#include <cfloat>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -400,6 +410,7 @@ inline f3 Sample(const Surface& s, f3 /*P*/, f3 Wo, f3 N, uint32_t& seed) {
       return Sample_AS(s, Wo, N, u1, u2);
     }
     case PT_MAT_DIFFUSE_LIGHT:  // P/materials/diffuse_light.cuh:7-13
+    case PT_MAT_ISOTROPIC:      // P/materials/isotropic.cuh:7-13
       return random_on_unit_sphere(seed);
     default:
       return mk(0.f);
@@ -504,6 +515,9 @@ inline f3 Evaluate(const Surface& s, f3 /*P*/, f3 Wo, f3 Wi, f3 N, float& pdf) {
     case PT_MAT_DIFFUSE_LIGHT:  // P/materials/diffuse_light.cuh:15-22
       pdf = 1.f;
       return s.color;
+    case PT_MAT_ISOTROPIC:  // P/materials/isotropic.cuh:15-33
+      pdf = 0.25f * PI_F;
+      return (0.25f * PI_F) * s.color;
     default:
       return mk(0.f);
   }
@@ -623,6 +637,8 @@ inline float PowerHeuristic(unsigned numf, float fPdf, unsigned numg, float gPdf
 struct Ray {
   f3 o, d;
   float tmin, tmax;
+  float time;     // prd.time of the sample (P/raygen.cu:69), read by moving spheres
+  uint32_t seed;  // prd.seed when the ray is traced, read by volumes (pinned, see header)
 };
 struct Box3 {
   f3 lo, hi;
@@ -752,10 +768,71 @@ inline bool hit_triangle(const float* v9, const Ray& r, float& t, float& bu, flo
   return false;
 }
 
+// P/hitables/moving_sphere.cu:44-46
+inline f3 moving_center(const pt_moving_sphere& q, float time) {
+  return ld3(q.center0) + ((time - q.time0) / (q.time1 - q.time0)) * (ld3(q.center1) - ld3(q.center0));
+}
+// P/hitables/moving_sphere.cu:54-131
+inline bool hit_moving_sphere(const pt_moving_sphere& q, const Ray& r, float& t) {
+  pt_sphere s;
+  st3(s.center, moving_center(q, r.time));
+  s.radius = q.radius;
+  return hit_sphere(s, r, t);
+}
+// pinned volume uniform: rnd(tea<4>(seed, prim))
+inline float volume_uniform(uint32_t seed, uint32_t prim) {
+  uint32_t s = tea<4>(seed, prim);
+  return rnd(s);
+}
+// P/hitables/volume_sphere.cu:20-54
+inline bool vol_boundary_sphere(const pt_volume_sphere& q, const Ray& r, float tmin, float tmax, float& rec) {
+  pt_sphere s = {{q.center[0], q.center[1], q.center[2]}, q.radius};
+  Ray rr = r;
+  rr.tmin = tmin;
+  rr.tmax = tmax;
+  return hit_sphere(s, rr, rec);
+}
+// P/hitables/volume_box.cu:20-42
+inline bool vol_boundary_box(const pt_volume_box& q, const Ray& r, float tmin, float tmax, float& rec) {
+  f3 t0 = (ld3(q.bmin) - r.o) / r.d;
+  f3 t1 = (ld3(q.bmax) - r.o) / r.d;
+  float temp1 = max_component(min_vec(t0, t1));
+  float temp2 = min_component(max_vec(t0, t1));
+  if (temp1 > temp2) return false;
+  if (temp1 < tmax && temp1 > tmin) {
+    rec = temp1;
+    return true;
+  }
+  if (temp2 < tmax && temp2 > tmin) {
+    rec = temp2;
+    return true;
+  }
+  return false;
+}
+// P/hitables/volume_sphere.cu:62-105, volume_box.cu:44-82 (as written: the sampled distance is
+// not compared with the distance inside the boundary)
+template <class Q, class B>
+inline bool hit_volume(const Q& q, B boundary, const Ray& r, int prim, float& t) {
+  float rec1, rec2;
+  if (!boundary(q, r, -FLT_MAX, FLT_MAX, rec1)) return false;
+  if (!boundary(q, r, (float)(rec1 + 0.0001), FLT_MAX, rec2)) return false;
+  if (rec1 < r.tmin) rec1 = r.tmin;
+  if (rec2 > r.tmax) rec2 = r.tmax;
+  if (rec1 >= rec2) return false;
+  if (rec1 < 0.f) rec1 = 0.f;
+  float hit_distance = -(1.f / q.density) * logf(volume_uniform(r.seed, (uint32_t)prim));
+  float temp = rec1 + hit_distance / length(r.d);
+  if (temp > r.tmin && temp < r.tmax) {
+    t = temp;
+    return true;
+  }
+  return false;
+}
+
 inline Ray to_object(const orc_scene& s, const pt_prim_ref& p, const Ray& r) {
   if (p.xform < 0) return r;
   const float* m = s.d.xforms[p.xform].w2o;
-  Ray o;
+  Ray o = r;
   o.o = xf_point(m, r.o);
   o.d = xf_vector(m, r.d);
   o.tmin = r.tmin;
@@ -775,6 +852,12 @@ inline bool intersect_prim(const orc_scene& s, int id, const Ray& r, float& t, f
       return hit_rect(s.d.rects[p.index], to_object(s, p, r), t);
     case PT_PRIM_BOX:
       return hit_box(s.d.boxes[p.index], to_object(s, p, r), t);
+    case PT_PRIM_MOVING_SPHERE:
+      return hit_moving_sphere(s.d.moving_spheres[p.index], to_object(s, p, r), t);
+    case PT_PRIM_VOLUME_SPHERE:
+      return hit_volume(s.d.volume_spheres[p.index], vol_boundary_sphere, to_object(s, p, r), id, t);
+    case PT_PRIM_VOLUME_BOX:
+      return hit_volume(s.d.volume_boxes[p.index], vol_boundary_box, to_object(s, p, r), id, t);
   }
   return false;
 }
@@ -809,6 +892,31 @@ inline Box3 prim_bounds(const orc_scene& s, int id) {
         lo = mk(q.a0, q.b0, q.k);
         hi = mk(q.a1, q.b1, q.k);
       }
+      break;
+    }
+    case PT_PRIM_MOVING_SPHERE: {  // P/hitables/moving_sphere.cu:136-147 (+ camera shutter, see header)
+      const pt_moving_sphere& q = s.d.moving_spheres[p.index];
+      const float ts[4] = {q.time0, q.time1, s.d.camera.time0, s.d.camera.time1};
+      lo = mk(INFINITY);
+      hi = mk(-INFINITY);
+      for (float tt : ts) {
+        f3 c = moving_center(q, tt);
+        if (!(c.x == c.x && c.y == c.y && c.z == c.z)) continue;
+        lo = min_vec(lo, c - q.radius);
+        hi = max_vec(hi, c + q.radius);
+      }
+      break;
+    }
+    case PT_PRIM_VOLUME_SPHERE: {  // P/hitables/volume_sphere.cu:111-115
+      const pt_volume_sphere& q = s.d.volume_spheres[p.index];
+      lo = ld3(q.center) - q.radius;
+      hi = ld3(q.center) + q.radius;
+      break;
+    }
+    case PT_PRIM_VOLUME_BOX: {  // P/hitables/volume_box.cu:86-90
+      const pt_volume_box& q = s.d.volume_boxes[p.index];
+      lo = min_vec(ld3(q.bmin), ld3(q.bmax));
+      hi = max_vec(ld3(q.bmin), ld3(q.bmax));
       break;
     }
     default: {  // P/hitables/box.cu:84-88
@@ -1012,8 +1120,24 @@ inline HitRecord get_hit_record(const orc_scene& s, const Ray& wr, const Hit& h)
   auto toWorldP = [&](f3 q) { return o2w ? xf_point(o2w, q) : q; };
   auto toWorldN = [&](f3 n) { return normalize(w2o ? xf_normal(w2o, n) : n); };
   switch (p.type) {
-    case PT_PRIM_SPHERE: {  // P/hitables/sphere.cu:65-93
-      const pt_sphere& q = s.d.spheres[p.index];
+    case PT_PRIM_VOLUME_SPHERE:
+    case PT_PRIM_VOLUME_BOX: {  // P/hitables/volume_sphere.cu:86-103, volume_box.cu:61-78
+      f3 hit_point = r.o + h.t * r.d;
+      rec.P = toWorldP(hit_point);
+      rec.shading_normal = rec.geometric_normal = toWorldN(mk(1.f, 0.f, 0.f));
+      rec.u = rec.v = 0.f;
+      break;
+    }
+    case PT_PRIM_SPHERE:
+    case PT_PRIM_MOVING_SPHERE: {  // P/hitables/sphere.cu:65-93, moving_sphere.cu:82-100
+      pt_sphere q;
+      if (p.type == PT_PRIM_SPHERE) {
+        q = s.d.spheres[p.index];
+      } else {
+        const pt_moving_sphere& ms = s.d.moving_spheres[p.index];
+        st3(q.center, moving_center(ms, wr.time));
+        q.radius = ms.radius;
+      }
       f3 hit_point = r.o + h.t * r.d;
       rec.P = toWorldP(hit_point);
       f3 T = (hit_point - ld3(q.center)) / q.radius;
@@ -1222,7 +1346,7 @@ inline f3 env_sample_dir(const orc_scene& s, uint32_t& seed, float& pdf);
 
 // P/materials/light_sample.cuh:35-103
 f3 Direct_Light(const orc_scene& s, const Surface& surface, f3 P, f3 Wo, f3 N, bool isLight,
-                uint32_t& seed, Counters& cn) {
+                uint32_t& seed, Counters& cn, float time) {
   f3 directLight = mk(0.f);
   int numLights = s.d.n_lights;
   if (numLights == 0) return mk(0.f);
@@ -1234,7 +1358,7 @@ f3 Direct_Light(const orc_scene& s, const Surface& surface, f3 P, f3 Wo, f3 N, b
   float lightPDF = Light_PDF(L, P, Wi);
   if (dot(Wi, N) < 0.f) return mk(0.f);
   // shadow ray (type 1, tmin 1e-3, tmax inf) — pinned visibility, see header
-  Ray sh = {P, Wi, 1e-3f, RT_DEFAULT_MAX};
+  Ray sh = {P, Wi, 1e-3f, RT_DEFAULT_MAX, time, seed};
   Hit h = closest_hit(s, sh, &cn.nodes, &cn.prims);
   cn.shadow++;
   bool inShadow = true;
@@ -1293,11 +1417,12 @@ void closest_hit_program(const orc_scene& s, const Ray& ray, const Hit& h, PerRa
             need_shadow = true;
           }
         }
+        const uint32_t shadow_seed = prd.seed;  // seed when the shadow ray is decided (after the 4 light draws)
         f3 Wi = Sample(surf, P, Wo, N, prd.seed);
         float pdf = 0.f;
         f3 attenuation = Evaluate(surf, P, Wo, Wi, N, pdf);
         if (need_shadow) {
-          Ray sh = {P, WiL, 1e-3f, RT_DEFAULT_MAX};
+          Ray sh = {P, WiL, 1e-3f, RT_DEFAULT_MAX, prd.time, shadow_seed};
           Hit hh = closest_hit(s, sh, &cn.nodes, &cn.prims);
           cn.shadow++;
           if (hh.prim < 0) prd.radiance = prd.radiance + prd.throughput * direct;
@@ -1310,7 +1435,7 @@ void closest_hit_program(const orc_scene& s, const Ray& ray, const Hit& h, PerRa
         prd.last_pdf = pdf;
         break;
       }
-      f3 direct = Direct_Light(s, surf, P, Wo, N, false, prd.seed, cn);
+      f3 direct = Direct_Light(s, surf, P, Wo, N, false, prd.seed, cn, prd.time);
       prd.radiance += prd.throughput * direct;
       f3 Wi = Sample(surf, P, Wo, N, prd.seed);
       float pdf = 0.f;
@@ -1319,6 +1444,20 @@ void closest_hit_program(const orc_scene& s, const Ray& ray, const Hit& h, PerRa
       prd.origin = P;
       prd.direction = Wi;
       prd.throughput *= clamp3(attenuation / pdf, 0.f, 1.f);
+      prd.isSpecular = false;
+      break;
+    }
+    case PT_MAT_ISOTROPIC: {  // isotropic.cu:34-60
+      surf.color = sample_texture(s, m.tex0, rec.u, rec.v, P, index);
+      f3 direct = Direct_Light(s, surf, P, Wo, N, false, prd.seed, cn, prd.time);
+      prd.radiance += prd.throughput * direct;
+      f3 Wi = Sample(surf, P, Wo, N, prd.seed);
+      float pdf = 0.f;
+      f3 attenuation = Evaluate(surf, P, Wo, Wi, N, pdf);
+      prd.scatterEvent = rayGotBounced;
+      prd.origin = P;
+      prd.direction = Wi;
+      prd.throughput *= attenuation / pdf;
       prd.isSpecular = false;
       break;
     }
@@ -1365,7 +1504,7 @@ void closest_hit_program(const orc_scene& s, const Ray& ray, const Hit& h, PerRa
     }
     case PT_MAT_DIFFUSE_LIGHT: {  // diffuse_light.cu:30-48
       surf.color = sample_texture(s, m.tex0, rec.u, rec.v, P, index);
-      f3 direct = Direct_Light(s, surf, P, Wo, N, true, prd.seed, cn);
+      f3 direct = Direct_Light(s, surf, P, Wo, N, true, prd.seed, cn, prd.time);
       prd.radiance += prd.throughput * direct;
       if (dot(N, Wo) < 0.f) prd.throughput *= surf.color;
       prd.scatterEvent = rayHitLight;
@@ -1499,6 +1638,8 @@ f3 color(const orc_scene& s, Ray ray, uint32_t& seed, int maxDepth, int russian,
   prd.last_pdf = 0.f;
   bool previousHitSpecular = false;
   for (int depth = 0; depth < maxDepth; depth++) {
+    ray.time = prd.time;
+    ray.seed = prd.seed;
     Hit h = closest_hit(s, ray, &cn.nodes, &cn.prims);
     cn.closest++;
     cn.bounces++;
@@ -1522,7 +1663,7 @@ f3 color(const orc_scene& s, Ray ray, uint32_t& seed, int maxDepth, int russian,
     } else if (prd.scatterEvent == rayGotCancelled)
       return prd.radiance;
     else {
-      ray = {prd.origin, prd.direction, 1e-3f, RT_DEFAULT_MAX};
+      ray = {prd.origin, prd.direction, 1e-3f, RT_DEFAULT_MAX, prd.time, prd.seed};
       previousHitSpecular = prd.isSpecular;
     }
     if (russian) {
@@ -1556,7 +1697,7 @@ inline Ray camera_ray(const orc_scene& s, int W, int H, int x, int y, int frame,
   const f3 origin = ld3(c.origin) + lens_offset;
   const f3 direction =
       ld3(c.lower_left_corner) + u * ld3(c.horizontal) + v * ld3(c.vertical) - origin;
-  return {origin, direction, 1e-6f, RT_DEFAULT_MAX};
+  return {origin, direction, 1e-6f, RT_DEFAULT_MAX, 0.f, 0u};
 }
 
 inline Surface make_surface(int mat, const float* color, const float* color2, float p0, float p1) {
@@ -1591,7 +1732,8 @@ int orc_trace(const orc_scene* s, const pt_ray* rays, int64_t n, pt_hit* hits, o
   auto t0 = std::chrono::steady_clock::now();
 #pragma omp parallel for schedule(dynamic, 256) reduction(+ : nodes, prims)
   for (int64_t i = 0; i < n; i++) {
-    Ray r = {ld3(rays[i].origin), ld3(rays[i].dir), rays[i].tmin, rays[i].tmax};
+    // ray sets carry no per-ray data: time = the camera's time0, seed = ray index (as pt_trace_rays)
+    Ray r = {ld3(rays[i].origin), ld3(rays[i].dir), rays[i].tmin, rays[i].tmax, s->d.camera.time0, (uint32_t)i};
     if (!(r.tmax > r.tmin)) {
       hits[i] = {r.tmax, -1, 0.f, 0.f};
       continue;
@@ -1627,7 +1769,7 @@ int orc_camera_rays(const orc_scene* s, int W, int H, int frame, pt_ray* out) {
 int orc_bounce_rays(const orc_scene* s, const pt_ray* in, int64_t n, uint32_t seed0, pt_ray* out) {
 #pragma omp parallel for schedule(dynamic, 256)
   for (int64_t i = 0; i < n; i++) {
-    Ray r = {ld3(in[i].origin), ld3(in[i].dir), in[i].tmin, in[i].tmax};
+    Ray r = {ld3(in[i].origin), ld3(in[i].dir), in[i].tmin, in[i].tmax, s->d.camera.time0, (uint32_t)i};
     pt_ray& o = out[i];
     memset(&o, 0, sizeof(o));
     o.tmax = -1.f;

@@ -28,6 +28,9 @@ def desc_arrays(d):
         "camera": np.frombuffer(bytes(d.camera), dtype=np.float32).copy(),
         "miss": np.frombuffer(bytes(d.miss), dtype=np.uint32).copy(),
         "n_images": d.n_images,
+        "moving_spheres": arr(d.moving_spheres, d.n_moving_spheres, np.float32, 9),
+        "volume_spheres": arr(d.volume_spheres, d.n_volume_spheres, np.float32, 5),
+        "volume_boxes": arr(d.volume_boxes, d.n_volume_boxes, np.float32, 7),
     }
     return out
 

@@ -372,6 +372,78 @@ def build_sphere_light_scene(W=48, H=48, lib=None, two=False):
     return s
 
 
+def build_motion_scene(W=48, H=32, lib=None, n=5, seed=3):
+    """Moving_Sphere (programs/hitables/moving_sphere.cu): a ground sphere, a grid of small spheres
+    bouncing upwards during the shutter interval [0, 1], one big sphere sliding sideways, static
+    metal / glass spheres in between; gradient sky."""
+    rng = np.random.default_rng(seed)
+    s = pt.Scene(lib)
+    texs = [tex_const(0.5, 0.5, 0.5), tex_const(0.4, 0.2, 0.1), tex_const(0.7, 0.6, 0.5), tex_const(1.0)]
+    mats = [material(pt.MAT_LAMBERTIAN, 0), material(pt.MAT_LAMBERTIAN, 1), material(pt.MAT_METAL, 2, -1, 0.0),
+            material(pt.MAT_DIELECTRIC, 3, 3, 1.5)]
+    moving, mmat, static, smat = [], [], [pt.Sphere(pt.F3(0, -1000, 0), 1000.0)], [0]
+    for a in range(-n, n):
+        for b in range(-n, n):
+            c = (a + 0.9 * rng.random(), 0.2, b + 0.9 * rng.random())
+            k = rng.random()
+            if k < 0.7:
+                texs.append(tex_const(*rng.random(3)))
+                mats.append(material(pt.MAT_LAMBERTIAN, len(texs) - 1))
+                c2 = (c[0], c[1] + 0.5 * rng.random(), c[2])
+                moving.append(pt.MovingSphere(pt.F3(*c), pt.F3(*c2), 0.2, 0.0, 1.0))
+                mmat.append(len(mats) - 1)
+            else:
+                static.append(pt.Sphere(pt.F3(*c), 0.2))
+                smat.append(2 if k < 0.9 else 3)
+    moving.append(pt.MovingSphere(pt.F3(-3, 1, 0), pt.F3(-3, 1, 1.5), 1.0, 0.0, 1.0))
+    mmat.append(1)
+    static.append(pt.Sphere(pt.F3(3, 1, 0), 1.0))
+    smat.append(2)
+    s.set_textures(texs)
+    s.set_materials(mats)
+    s.add_spheres(static, smat)
+    s.add_moving_spheres(moving, mmat)
+    s.set_camera(make_camera([13, 2, 3], [0, 0, 0], [0, 1, 0], 20.0, W / H, 0.0, 10.0, 0.0, 1.0))
+    s.set_miss(pt.Miss(pt.MISS_GRADIENT, pt.F3(1, 1, 1), pt.F3(0.5, 0.7, 1.0), -1, 1, 0))
+    return s
+
+
+def build_smoke_scene(W=48, H=48, lib=None, fog=True):
+    """Volumes (programs/hitables/volume_box.cu, volume_sphere.cu + materials/isotropic.cu): Cornell
+    walls, two rotated blocks of smoke, a fog ball and (fog=True) a thin fog filling the room."""
+    def extra(s, texs, mats):
+        base = len(texs)
+        texs.extend([tex_const(0.0), tex_const(1.0), tex_const(0.2, 0.4, 0.9)])
+        mats.extend([material(pt.MAT_ISOTROPIC, base), material(pt.MAT_ISOTROPIC, base + 1),
+                     material(pt.MAT_ISOTROPIC, base + 2)])
+    s = pt.Scene(lib)
+    texs = [tex_const(0.65, 0.05, 0.05), tex_const(0.73), tex_const(0.12, 0.45, 0.15), tex_const(7.0)]
+    mats = [material(pt.MAT_LAMBERTIAN, 0), material(pt.MAT_LAMBERTIAN, 1), material(pt.MAT_LAMBERTIAN, 2),
+            material(pt.MAT_DIFFUSE_LIGHT, 3)]
+    extra(s, texs, mats)
+    s.set_textures(texs)
+    s.set_materials(mats)
+    rects = [pt.Rect(0, 555, 0, 555, 555, pt.X_AXIS, 1), pt.Rect(0, 555, 0, 555, 0, pt.X_AXIS, 0),
+             pt.Rect(113, 443, 127, 432, 554, pt.Y_AXIS, 1), pt.Rect(0, 555, 0, 555, 555, pt.Y_AXIS, 1),
+             pt.Rect(0, 555, 0, 555, 0, pt.Y_AXIS, 0), pt.Rect(0, 555, 0, 555, 555, pt.Z_AXIS, 1)]
+    s.add_rects(rects, [0, 2, 3, 1, 1, 1])
+    xf0 = mat_translate([265.0, 0.0, 295.0]) @ mat_rotate(15.0, pt.Y_AXIS)
+    xf1 = mat_translate([130.0, 0.0, 65.0]) @ mat_rotate(-18.0, pt.Y_AXIS)
+    s.add_volume_boxes([pt.VolumeBox(pt.F3(0, 0, 0), pt.F3(165, 330, 165), 0.01),
+                        pt.VolumeBox(pt.F3(0, 0, 0), pt.F3(165, 165, 165), 0.01)], [4, 5],
+                       xforms=np.stack([m34(xf0), m34(xf1)]))
+    vs = [pt.VolumeSphere(pt.F3(400, 420, 150), 70.0, 0.02)]
+    vm = [6]
+    if fog:
+        vs.append(pt.VolumeSphere(pt.F3(0, 0, 0), 5000.0, 0.0001))
+        vm.append(5)
+    s.add_volume_spheres(vs, vm)
+    s.set_lights([pt.Light(0, pt.Y_AXIS, 113, 443, 127, 432, 554, pt.F3(7, 7, 7))])
+    s.set_camera(make_camera([278, 278, -800], [278, 278, 0], [0, 1, 0], 40.0, W / H, 0.0, 10.0))
+    s.set_miss(pt.Miss(pt.MISS_CONSTANT, pt.F3(0, 0, 0), pt.F3(0, 0, 0), -1, 1, 0))
+    return s
+
+
 def build_spheres(n_small=22, seed=0, W=64, H=64, lib=None, lights=False):
     """RTOW-style scene (host_includes/scenes.hpp:17-93): ground + grid of small spheres
     (Lambertian / metal / dielectric) + three big ones, gradient sky."""

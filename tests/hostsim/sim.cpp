@@ -50,6 +50,11 @@ Sim* sim_create(const pt_scene_desc* desc, int refine) {
   in.spheres = desc->spheres;
   in.rects = desc->rects;
   in.boxes = desc->boxes;
+  in.moving_spheres = desc->moving_spheres;
+  in.volume_spheres = desc->volume_spheres;
+  in.volume_boxes = desc->volume_boxes;
+  in.cam_time0 = desc->camera.time0;
+  in.cam_time1 = desc->camera.time1;
   in.tri_v = desc->tri_v;
   in.xforms = desc->xforms;
   in.materials = desc->materials;
@@ -182,6 +187,7 @@ Sim* sim_create(const pt_scene_desc* desc, int refine) {
   d.env_n = desc->env_n;
   d.env_w = desc->env_n ? desc->images[desc->miss.image].width : 0;
   d.env_h = desc->env_n ? desc->images[desc->miss.image].height : 0;
+  d.special_mask = (desc->n_moving_spheres ? 1 : 0) | (desc->n_volume_spheres || desc->n_volume_boxes ? 2 : 0);
   d.n_prims = n;
   d.n_materials = desc->n_materials;
   d.n_textures = desc->n_textures;
@@ -257,7 +263,7 @@ int sim_trace(const Sim* s, const pt_ray* rays, long long n, pt_hit* hits, unsig
     uint32_t a = 0, b = 0;
     if (r.tmax > r.tmin) {
       bvh8_closest<true>(s->sc, f3(r.origin[0], r.origin[1], r.origin[2]), f3(r.dir[0], r.dir[1], r.dir[2]), r.tmin,
-                         r.tmax, h, a, b);
+                         r.tmax, h, a, b, RayAux{s->sc.camera.time0, (uint32_t)i});
     } else {
       h.t = r.tmax;
       h.prim = -1;
@@ -287,7 +293,7 @@ int sim_render(const Sim* s, int W, int H, int first_frame, int nframes, int max
         uint32_t seed;
         float3 o, d;
         camera_ray(sc.camera, W, H, x, y, f, seed, o, d);
-        (void)pt_rnd(seed);
+        const float time = sc.camera.time0 + pt_rnd(seed) * (sc.camera.time1 - sc.camera.time0);
         float3 thr = f3(1.f), rad = f3(0.f);
         float last_pdf = 0.f;
         bool spec = false;
@@ -297,9 +303,9 @@ int sim_render(const Sim* s, int W, int H, int first_frame, int nframes, int max
         while (alive) {
           TraceHit h;
           uint32_t a = 0, b = 0;
-          bvh8_closest<false>(sc, o, d, depth == 0 ? 1e-6f : 1e-3f, PT_RAY_MAX, h, a, b);
+          bvh8_closest<false>(sc, o, d, depth == 0 ? 1e-6f : 1e-3f, PT_RAY_MAX, h, a, b, RayAux{time, seed});
           PathIn in;
-          in.o = o; in.d = d; in.thr = thr; in.rad = rad; in.seed = seed; in.depth = depth; in.prev_specular = spec; in.last_pdf = last_pdf;
+          in.o = o; in.d = d; in.thr = thr; in.rad = rad; in.seed = seed; in.depth = depth; in.prev_specular = spec; in.last_pdf = last_pdf; in.time = time;
           if (h.leaf < 0) {
             col = shade_miss(sc, in);
             break;
@@ -316,7 +322,7 @@ int sim_render(const Sim* s, int W, int H, int first_frame, int nframes, int max
           bool nspec = out.specular;
           if (out.kind == SH_SHADOW) {
             TraceHit sh;
-            bvh8_closest<false>(sc, out.P, out.WiL, 1e-3f, PT_RAY_MAX, sh, a, b);
+            bvh8_closest<false>(sc, out.P, out.WiL, 1e-3f, PT_RAY_MAX, sh, a, b, RayAux{time, out.seedShadow});
             bool vis = out.env_shadow ? sh.leaf < 0
                                       : (sh.leaf >= 0 && (pt_f2u(sc.leaves[sh.leaf].c.w) >> 24) == PT_MAT_DIFFUSE_LIGHT);
             if (vis) { nd = out.dir; nthr = out.thr; nrad = out.rad; nseed = out.seed; }

@@ -75,9 +75,36 @@ def test_other_scenes_build(host_so, tmp_path):
     c4 = dump(host_so, 6, 64, 64, 16, tmp_path, "mine")       # 16x16 grid through OBJ + .hdr files
     assert len(c4["tri_v"]) == 16 * 16 * 2 * 9 and c4["n_images"] == 1 and c4["miss"][0] == pt.MISS_HDR
     fnw = dump(host_so, 3, 64, 64, 0, tmp_path, "mine")
-    assert len(fnw["prims"]) // 4 == 400 + 1 + 6 + 1000 and len(fnw["xforms"]) // 24 == 1000
+    assert len(fnw["prims"]) // 4 == 400 + 1 + 6 + 2 + 1000 and len(fnw["xforms"]) // 24 == 1000
+    # the two Volumetric_Spheres (blue fog inside the glass ball, thin white fog everywhere) + Isotropic
+    vs = fnw["volume_spheres"].reshape(-1, 5)
+    assert vs.shape[0] == 2 and np.allclose(vs[0], [360, 150, 45, 70, 0.2]) and np.allclose(vs[1], [0, 0, 0, 5000, 1e-4])
+    assert (fnw["materials"].reshape(-1, 6)[:, 0] == pt.MAT_ISOTROPIC).sum() == 2
     ms = dump(host_so, 1, 64, 64, 0, tmp_path, "mine")
     assert len(ms["prims"]) // 4 == 1 + 484 + 3 + 1 and len(ms["lights"]) // 10 == 1
+
+
+def test_motion_blur_and_smoke_scenes_through_the_facade(host_so, tmp_path):
+    """Moving_Sphere / Volumetric_Box / Volumetric_Sphere / Isotropic host classes: constructor argument
+    order, per-element transform chains and material registration as in the reference."""
+    mb = dump(host_so, 9, 96, 64, 0, tmp_path, "mine")
+    ms = mb["moving_spheres"].reshape(-1, 9)
+    prims = mb["prims"].reshape(-1, 4)
+    assert len(ms) == (prims[:, 0] == pt.PRIM_MOVING_SPHERE).sum() > 50
+    assert (ms[:, 7] == 0).all() and (ms[:, 8] == 1).all()                        # time0, time1
+    assert (ms[:-1, 6] == np.float32(0.2)).all() and ms[-1, 6] == 1.0             # radius
+    assert (ms[:-1, 4] >= ms[:-1, 1]).all() and (ms[:, [0, 2]] == ms[:, [3, 5]])[:-1].all()   # bounce along +y only
+    assert np.allclose(ms[-1], [-3, 1, 0, -3, 1, 1.5, 1, 0, 1])
+    smoke = dump(host_so, 10, 64, 64, 0, tmp_path, "mine")
+    hand = h.build_smoke_scene(64, 64, fog=False)
+    want = facade_dump.desc_arrays(hand.desc())
+    for k in ("rects", "volume_boxes", "volume_spheres", "lights", "camera", "miss"):
+        assert np.array_equal(smoke[k], want[k]), k
+    assert np.allclose(smoke["xforms"], want["xforms"], atol=1e-5)
+    ptypes = smoke["prims"].reshape(-1, 4)[:, 0]
+    assert list(ptypes) == [pt.PRIM_RECT] * 6 + [pt.PRIM_VOLUME_BOX] * 2 + [pt.PRIM_VOLUME_SPHERE]
+    mt = smoke["materials"].reshape(-1, 6)
+    assert list(mt[smoke["prims"].reshape(-1, 4)[6:, 2], 0]) == [pt.MAT_ISOTROPIC] * 3
 
 
 def test_sphere_pdf_light_through_the_facade(host_so, tmp_path):
