@@ -392,6 +392,17 @@ int pt_renderer_sync(pt_renderer* r);
  * width*height float4, row 0 = top image row, .w = number of samples. */
 int pt_read_accum(pt_renderer* r, float* host_rgba);
 int pt_accum_device_ptr(pt_renderer* r, void** d_ptr);
+/* replaces display_buffer + make_Color (programs/raygen.cu:136-146,167) and its map() in the
+ * progressive loop (main.cpp:268-272): width*height RGBA8 preview of the accumulation buffer,
+ * (int)(255.99 * clamp(sqrt(rgb / samples), 0, 1)), alpha 255, converted on the device (4 B per
+ * pixel cross PCIe instead of 16).  The divisor is the pixel's own sample count (.w), which is
+ * `frame + 1` in the reference's one-launch-per-sample loop. */
+int pt_read_display(pt_renderer* r, uint8_t* host_rgba8);
+/* checkpoint / resume of a progressive render: overwrites the accumulation buffer with one saved
+ * by pt_read_accum (same layout).  Continue with pt_render(first_frame = samples already in the
+ * buffer, ..., clear_accum = 0).  The reference's loop cannot resume (main.cpp:264-293 restarts at
+ * sample 0 and raygen.cu:154 clears on frame 0); SURVEY.md 8f rank 4. */
+int pt_write_accum(pt_renderer* r, const float* host_rgba);
 
 typedef struct pt_stats {
   uint64_t samples;        /* camera paths finished                          */

@@ -163,7 +163,7 @@ ABI_SYMBOLS = [
     "pt_scene_commit", "pt_scene_get_desc", "pt_scene_bvh_info", "pt_trace_rays",
     "pt_trace_rays_device", "pt_renderer_create", "pt_renderer_destroy", "pt_render",
     "pt_renderer_sync", "pt_read_accum", "pt_accum_device_ptr", "pt_get_stats",
-    "pt_renderer_set_flags", "pt_renderer_set_pool",
+    "pt_renderer_set_flags", "pt_renderer_set_pool", "pt_read_display", "pt_write_accum",
 ]
 
 
@@ -216,6 +216,8 @@ def load(path: Optional[str] = None) -> C.CDLL:
         "pt_renderer_sync": [vp],
         "pt_read_accum": [vp, vp],
         "pt_accum_device_ptr": [vp, P(vp)],
+        "pt_read_display": [vp, vp],
+        "pt_write_accum": [vp, vp],
         "pt_get_stats": [vp, P(Stats)],
         "pt_renderer_set_flags": [vp, i32],
         "pt_renderer_set_pool": [vp, i64],
@@ -410,6 +412,17 @@ class Renderer:
         out = np.empty((self.H, self.W, 4), dtype=np.float32)
         _check(self.lib, self.lib.pt_read_accum(self.h, _ptr(out)))
         return out
+
+    def read_display(self) -> np.ndarray:
+        """RGBA8 preview (display_buffer of the reference), converted on the device."""
+        out = np.empty((self.H, self.W, 4), dtype=np.uint8)
+        _check(self.lib, self.lib.pt_read_display(self.h, _ptr(out)))
+        return out
+
+    def write_accum(self, accum: np.ndarray):
+        """Restore a checkpointed accumulation buffer (continue with render(first_frame=samples done))."""
+        a = _f32(accum, (self.H, self.W, 4))
+        _check(self.lib, self.lib.pt_write_accum(self.h, _ptr(a)))
 
     def accum_device_ptr(self) -> int:
         p = C.c_void_p()

@@ -43,6 +43,7 @@ static int Scene_Config(App_State& app) {
 int main(int ac, char** av) {
   App_State app;
   int batch = 0;
+  std::string checkpoint, resume, preview;  // progressive-render extras
   for (int i = 1; i < ac; i++) {
     auto arg = [&](const char* n) { return !strcmp(av[i], n) && i + 1 < ac; };
     if (arg("--width")) app.W = atoi(av[++i]);
@@ -55,9 +56,15 @@ int main(int ac, char** av) {
     else if (arg("--file")) app.fileName = av[++i];
     else if (arg("--type")) app.fileType = atoi(av[++i]);
     else if (arg("--batch")) batch = atoi(av[++i]);
+    else if (arg("--checkpoint")) checkpoint = av[++i];
+    else if (arg("--resume")) resume = av[++i];
+    else if (arg("--preview")) preview = av[++i];
     else {
       printf("usage: %s [--width W] [--height H] [--samples N] [--scene 0..10] [--model M] [--depth D]\n"
-             "          [--russian 0|1] [--file name] [--type 0(PNG)|1(HDR)] [--batch frames-per-launch]\n", av[0]);
+             "          [--russian 0|1] [--file name] [--type 0(PNG)|1(HDR)] [--batch frames-per-launch]\n"
+             "          [--checkpoint file: save the accumulation buffer after every batch]\n"
+             "          [--resume file: continue a checkpointed render] [--preview file.png: display buffer after every batch]\n",
+             av[0]);
       return 1;
     }
   }
@@ -65,13 +72,44 @@ int main(int ac, char** av) {
     Scene_Config(app);
     auto t0 = std::chrono::system_clock::now();
     if (batch <= 0) batch = app.samples;  // default: the whole job in one wavefront run
-    for (app.currentSample = 0; app.currentSample < app.samples; app.currentSample += batch) {
+    int first = 0;
+    if (!resume.empty()) {  // header: W H samples-done, then W*H float4
+      FILE* f = fopen(resume.c_str(), "rb");
+      int hdr[3] = {0, 0, 0};
+      std::vector<float> acc((size_t)app.W * app.H * 4);
+      if (!f || fread(hdr, 4, 3, f) != 3 || hdr[0] != app.W || hdr[1] != app.H ||
+          fread(acc.data(), 16, (size_t)app.W * app.H, f) != (size_t)app.W * app.H)
+        throw "cannot resume: checkpoint missing or of another resolution";
+      fclose(f);
+      app.accBuffer->restore(acc.data(), app.W, app.H);
+      first = hdr[2];
+      printf("Resumed at sample %d\n", first);
+    }
+    for (app.currentSample = first; app.currentSample < app.samples; app.currentSample += batch) {
       int n = std::min(batch, app.samples - app.currentSample);
       if (batch == 1) {  // the reference's loop: one launch per sample (main.cpp:264-293)
         app.context["frame"]->setInt(app.currentSample);
         app.context->launch(0, app.W, app.H);
       } else {
         app.context->launchFrames(app.currentSample, n, app.W, app.H);
+      }
+      if (!preview.empty()) {  // the reference's showProgress copy of the display buffer (main.cpp:268-272)
+        const unsigned char* px = (const unsigned char*)app.displayBuffer->map();
+        std::vector<unsigned char> rgb((size_t)app.W * app.H * 3);
+        for (size_t i = 0; i < (size_t)app.W * app.H; i++)
+          for (int k = 0; k < 3; k++) rgb[3 * i + k] = px[4 * i + k];
+        app.displayBuffer->unmap();
+        ptio::write_png(preview.c_str(), app.W, app.H, rgb.data());
+      }
+      if (!checkpoint.empty()) {
+        const float* acc = (const float*)app.accBuffer->map();
+        FILE* f = fopen(checkpoint.c_str(), "wb");
+        if (!f) throw "cannot write the checkpoint";
+        int hdr[3] = {app.W, app.H, app.currentSample + n};
+        fwrite(hdr, 4, 3, f);
+        fwrite(acc, 16, (size_t)app.W * app.H, f);
+        fclose(f);
+        app.accBuffer->unmap();
       }
     }
     float renderTime = std::chrono::duration<float>(std::chrono::system_clock::now() - t0).count();

@@ -404,6 +404,19 @@ __global__ void __launch_bounds__(PT_TRACE_THREADS) k_trace_rays(SceneDev sc, co
   }
 }
 
+// make_Color (raygen.cu:136-146): the preview pixel of the display buffer
+__global__ void k_display(const float4* __restrict__ accum, uchar4* __restrict__ out, int n) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float4 c = accum[i];
+    const float inv = 1.0f / (c.w > 0.f ? c.w : 1.f);  // float3 / (frame + 1) = float3 * (1 / s)
+    const float r = fminf(fmaxf(sqrtf(c.x * inv), 0.f), 1.f);
+    const float g = fminf(fmaxf(sqrtf(c.y * inv), 0.f), 1.f);
+    const float b = fminf(fmaxf(sqrtf(c.z * inv), 0.f), 1.f);
+    out[i] = make_uchar4((unsigned char)(int)(255.99 * (double)r), (unsigned char)(int)(255.99 * (double)g),
+                         (unsigned char)(int)(255.99 * (double)b), (unsigned char)(int)(255.99 * 1.0));
+  }
+}
+
 int g_sm_count = 0;
 int sm_count() {
   if (!g_sm_count) {
@@ -471,7 +484,7 @@ struct pt_renderer {
   int flags = 0;
   long long pool_req = 0;
   int pool = 0;
-  DevBuf accum_own;
+  DevBuf accum_own, display;
   float4* accum = nullptr;
   // all per-path arrays live in one slab; array k starts at a skewed offset so that the same
   // path index in different arrays never maps to the same DRAM/L2 partition (arrays of exactly
@@ -800,6 +813,25 @@ int pt_read_accum(pt_renderer* r, float* host_rgba) {
   if (!r || !host_rgba) return PT_ERR_INVALID;
   PT_CUDA(cudaMemcpyAsync(host_rgba, r->accum, (size_t)r->W * r->H * 16, cudaMemcpyDeviceToHost, r->stream));
   PT_CUDA(cudaStreamSynchronize(r->stream));
+  return PT_OK;
+}
+
+int pt_read_display(pt_renderer* r, uint8_t* host_rgba8) {
+  if (!r || !host_rgba8) return PT_ERR_INVALID;
+  const int n = r->W * r->H;
+  if (!r->display.p) PT_CUDA(r->display.alloc((size_t)n * 4));
+  k_display<<<sm_count() * 4, 256, 0, r->stream>>>(r->accum, r->display.as<uchar4>(), n);
+  PT_CUDA(cudaGetLastError());
+  PT_CUDA(cudaMemcpyAsync(host_rgba8, r->display.p, (size_t)n * 4, cudaMemcpyDeviceToHost, r->stream));
+  PT_CUDA(cudaStreamSynchronize(r->stream));
+  return PT_OK;
+}
+
+int pt_write_accum(pt_renderer* r, const float* host_rgba) {
+  if (!r || !host_rgba) return PT_ERR_INVALID;
+  PT_CUDA(cudaMemcpyAsync(r->accum, host_rgba, (size_t)r->W * r->H * 16, cudaMemcpyHostToDevice, r->stream));
+  PT_CUDA(cudaStreamSynchronize(r->stream));
+  r->started = true;  // a restored buffer must not be cleared by the next pt_render(first_frame = 0)
   return PT_OK;
 }
 

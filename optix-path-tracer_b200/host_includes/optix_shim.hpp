@@ -150,6 +150,9 @@ struct BufferObj {  // accumulation (float4) or display (uchar4) buffer bound to
   std::vector<unsigned char> host8;
   void* map();
   void unmap() {}
+  // B200-first extension (checkpoint / resume): overwrite the device accumulation buffer with
+  // W*H float4 saved from an earlier map(); needs a launch (e.g. launch(0,0,0) + renderer) first
+  void restore(const float* rgba, int Wr, int Hr);
 };
 struct Buffer {
   std::shared_ptr<BufferObj> p;
@@ -326,18 +329,21 @@ inline void VariableObj::set(Group) {
   if (name == "world") ctx->has_world = true;
 }
 inline void VariableObj::set(Buffer b) { b->ctx = ctx; }
+inline void BufferObj::restore(const float* rgba, int Wr, int Hr) {
+  if (!ctx || !is_accum) throw "Buffer::restore: not an accumulation buffer bound to a context";
+  ctx->ensureRenderer(Wr, Hr);
+  ContextObj::check(pt_write_accum(ctx->renderer, rgba));
+}
 inline void* BufferObj::map() {
   if (!ctx || !ctx->renderer) throw "Buffer::map before the first launch";
-  host.resize((size_t)W * H * 4);
-  ContextObj::check(pt_read_accum(ctx->renderer, host.data()));
-  if (is_accum) return host.data();
-  // display buffer: make_Color of raygen.cu:136-146 on the host
-  host8.resize((size_t)W * H * 4);
-  for (size_t i = 0; i < (size_t)W * H; i++) {
-    float n = host[4 * i + 3] > 0 ? host[4 * i + 3] : 1.f;
-    for (int k = 0; k < 3; k++) host8[4 * i + k] = (unsigned char)(int)(255.99 * clamp(sqrtf(host[4 * i + k] / n), 0.f, 1.f));
-    host8[4 * i + 3] = 255;
+  if (is_accum) {
+    host.resize((size_t)W * H * 4);
+    ContextObj::check(pt_read_accum(ctx->renderer, host.data()));
+    return host.data();
   }
+  // display buffer: make_Color of raygen.cu:136-146, converted on the device
+  host8.resize((size_t)W * H * 4);
+  ContextObj::check(pt_read_display(ctx->renderer, host8.data()));
   return host8.data();
 }
 

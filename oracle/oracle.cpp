@@ -1854,6 +1854,20 @@ int orc_tonemap_png8(const float* accum, int W, int H, int samples, uint8_t* rgb
 
 uint32_t orc_tea64(uint32_t v0, uint32_t v1) { return tea<64>(v0, v1); }
 float orc_rnd(uint32_t* seed) { return rnd(*seed); }
+// P/raygen.cu:136-146 make_Color with (frame + 1) = the pixel's sample count
+int orc_display_rgba8(const float* accum, int W, int H, uint8_t* rgba) {
+  for (size_t i = 0; i < (size_t)W * H; i++) {
+    const float* c = accum + 4 * i;
+    f3 temp = mk(c[0], c[1], c[2]) / (c[3] > 0.f ? c[3] : 1.f);
+    temp = clamp3(mk(sqrtf(temp.x), sqrtf(temp.y), sqrtf(temp.z)), 0.f, 1.f);
+    rgba[4 * i + 0] = (uint8_t)int(255.99 * temp.x);
+    rgba[4 * i + 1] = (uint8_t)int(255.99 * temp.y);
+    rgba[4 * i + 2] = (uint8_t)int(255.99 * temp.z);
+    rgba[4 * i + 3] = (uint8_t)int(255.99 * 1.f);
+  }
+  return 0;
+}
+
 void orc_random_in_unit_disk(uint32_t* seed, float* o) { st3(o, random_in_unit_disk(*seed)); }
 void orc_random_in_unit_sphere(uint32_t* seed, float* o) { st3(o, random_in_unit_sphere(*seed)); }
 void orc_random_on_unit_sphere(uint32_t* seed, float* o) { st3(o, random_on_unit_sphere(*seed)); }

@@ -70,6 +70,9 @@ int orc_render_pixel(const orc_scene* s, int W, int H, int x, int y, int frame, 
 /* host_includes/image_save.hpp:13-29: 8-bit RGB, W*H*3 */
 int orc_tonemap_png8(const float* accum, int W, int H, int samples, uint8_t* rgb);
 
+/* programs/raygen.cu:136-146 make_Color: RGBA8 preview of an accumulation buffer */
+int orc_display_rgba8(const float* accum, int W, int H, uint8_t* rgba);
+
 /* ---- unit entry points (golden vectors / reference-header probes) -------- */
 uint32_t orc_tea64(uint32_t v0, uint32_t v1);            /* programs/random.cuh:33-47 */
 float orc_rnd(uint32_t* seed);                           /* programs/random.cuh:63-65 */

@@ -81,6 +81,7 @@ def oracle():
     o.orc_render.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, P(OrcStats)]
     o.orc_render_pixel.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]
     o.orc_tonemap_png8.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp]
+    o.orc_display_rgba8.argtypes = [vp, C.c_int, C.c_int, vp]
     o.orc_tea64.restype = C.c_uint32
     o.orc_tea64.argtypes = [C.c_uint32, C.c_uint32]
     o.orc_rnd.restype = C.c_float
