@@ -19,11 +19,11 @@ pt = h.pt
 REF_SCENES = "/root/reference/OptiX-Path-Tracer/host_includes/scenes.hpp"
 
 
-def dump(so, scene_id, W, H, model, tmp_path, tag):
+def dump(so, scene_id, W, H, model, tmp_path, tag, cwd=None):
     out = str(tmp_path / f"{tag}_{scene_id}.pkl")
     env = dict(os.environ, PYTHONPATH=os.path.join(h.ROOT, "tests"))
     r = subprocess.run([sys.executable, os.path.join(h.ROOT, "tests", "facade_dump.py"), so, str(scene_id), str(W), str(H),
-                        str(model), out], capture_output=True, text=True, env=env)
+                        str(model), out], capture_output=True, text=True, env=env, cwd=cwd)
     assert r.returncode == 0, r.stderr + r.stdout
     return pickle.load(open(out, "rb"))
 
@@ -165,6 +165,32 @@ def test_reference_scenes_header_drops_in(host_so, tmp_path):
             ra, rb = mr[a[2]], mm[b[2]]
             assert ra[0] == rb[0] and ra[3] == rb[3] and ra[4] == rb[4]        # type and parameters
             assert np.array_equal(tr[ra[1]][:4], tm[rb[1]][:4])                # albedo
+    # MovingSpheres and Final_Next_Week load "../../../assets/other_textures/map.jpg" relative to the working
+    # directory (the reference is run from its build tree): give them a JPEG there and run from three levels down.
+    from PIL import Image as PIL
+    (tmp_path / "assets" / "other_textures").mkdir(parents=True)
+    yy, xx = np.mgrid[0:32, 0:64]
+    earth = np.stack([xx * 4, yy * 8, 255 - xx * 2], axis=-1).astype(np.uint8)
+    PIL.fromarray(earth).save(tmp_path / "assets" / "other_textures" / "map.jpg", "JPEG", quality=95, subsampling=0)
+    run_dir = tmp_path / "build" / "bin" / "Release"
+    run_dir.mkdir(parents=True)
+    fnw = dump(so, 3, 64, 64, 0, tmp_path, "ref", cwd=str(run_dir))
+    mine = dump(host_so, 3, 64, 64, 0, tmp_path, "mine")
+    # same geometry: 400 boxes, light, 6 spheres, the two Volumetric_Spheres, 1000 instanced spheres
+    for k in ("boxes", "spheres", "rects", "volume_spheres", "xforms", "lights", "camera", "miss"):
+        assert np.array_equal(fnw[k], mine[k]), k
+    assert np.array_equal(fnw["prims"].reshape(-1, 4)[:, [0, 1, 3]], mine["prims"].reshape(-1, 4)[:, [0, 1, 3]])
+    mr = fnw["materials"].reshape(-1, 6)
+    assert (mr[:, 0] == pt.MAT_ISOTROPIC).sum() == 2 and fnw["n_images"] == 1       # the earth JPEG was decoded
+    tex = fnw["textures"].reshape(-1, 6)
+    assert (tex[:, 0] == pt.TEX_IMAGE).sum() == 1 and (tex[:, 0] == pt.TEX_NOISE).sum() == 1
+    ms = dump(so, 1, 64, 64, 0, tmp_path, "ref", cwd=str(run_dir))
+    assert len(ms["prims"]) // 4 == 1 + 484 + 3 + 1 and ms["n_images"] == 1
+    # without the asset the reference exits (textures.hpp:123-127); the facade reports the same failure
+    r = subprocess.run([sys.executable, os.path.join(h.ROOT, "tests", "facade_dump.py"), so, "3", "64", "64", "0",
+                        str(tmp_path / "x.pkl")], capture_output=True, text=True,
+                       env=dict(os.environ, PYTHONPATH=os.path.join(h.ROOT, "tests")), cwd=str(tmp_path))
+    assert r.returncode != 0 and "cannot load" in (r.stderr + r.stdout)
 
 
 def test_png_and_hdr_roundtrip(tmp_path):
