@@ -204,8 +204,11 @@ struct ClosestPolicy {
   }
 };
 
+#ifndef PT_TRACE_MINBLOCKS
+#define PT_TRACE_MINBLOCKS 8  // 64 registers: measured best (9 and 10 CTAs/SM at 56 / 48 registers were 2-5 % slower)
+#endif
 template <bool COUNT, bool SPECIAL>
-__global__ void __launch_bounds__(PT_TRACE_THREADS) k_trace(SceneDev sc, Ctrl* c, PathBuf cur, float4* hits,
+__global__ void __launch_bounds__(PT_TRACE_THREADS, PT_TRACE_MINBLOCKS) k_trace(SceneDev sc, Ctrl* c, PathBuf cur, float4* hits,
                                                             uint32_t* bin_q, int pool, SchedParams sched) {
   __shared__ uint2 s_stack[PT_SMEM_STACK * PT_TRACE_THREADS];
   ClosestPolicy pol{sc, c, cur, hits, bin_q, pool};
@@ -341,7 +344,7 @@ struct ShadowPolicy {
 };
 
 template <bool COUNT, bool SPECIAL>
-__global__ void __launch_bounds__(PT_TRACE_THREADS) k_shadow(SceneDev sc, Params p, Ctrl* c, PathBuf next, ShadowBuf sb,
+__global__ void __launch_bounds__(PT_TRACE_THREADS, PT_TRACE_MINBLOCKS) k_shadow(SceneDev sc, Params p, Ctrl* c, PathBuf next, ShadowBuf sb,
                                                              SchedParams sched) {
   __shared__ uint2 s_stack[PT_SMEM_STACK * PT_TRACE_THREADS];
   ShadowPolicy pol{sc, p, c, next, sb};
@@ -386,7 +389,7 @@ struct RaySetPolicy {
 };
 
 template <bool COUNT, bool SPECIAL>
-__global__ void __launch_bounds__(PT_TRACE_THREADS) k_trace_rays(SceneDev sc, const pt_ray* rays, int n, pt_hit* hits,
+__global__ void __launch_bounds__(PT_TRACE_THREADS, PT_TRACE_MINBLOCKS) k_trace_rays(SceneDev sc, const pt_ray* rays, int n, pt_hit* hits,
                                                                  unsigned long long* counters, SchedParams sched) {
   __shared__ uint2 s_stack[PT_SMEM_STACK * PT_TRACE_THREADS];
   RaySetPolicy pol{rays, hits, sc.camera.time0};

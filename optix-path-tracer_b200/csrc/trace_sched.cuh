@@ -26,7 +26,9 @@
 #pragma once
 #include "traverse.h"
 
+#ifndef PT_SMEM_STACK
 #define PT_SMEM_STACK 12
+#endif
 #define PT_TRACE_THREADS 128
 
 struct SchedParams {

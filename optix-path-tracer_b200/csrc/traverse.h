@@ -265,14 +265,19 @@ PT_HD uint32_t pt_byte(uint32_t v, int i) { return (v >> (8 * i)) & 0xffu; }
 // Folding rounds the addend at magnitude 2^15*s, an error of at most 2^-10 quantisation steps;
 // the builder quantises child boxes with a 2^-8-step guard band (bvh_core.h), so the test stays
 // conservative.  The host build converts exactly.
+// SASS PRMT takes ONE immediate.  With the 0x47000000 operand a compile-time constant ptxas keeps it
+// as the immediate and puts the four selectors in registers, which under the kernels' register
+// cap are re-materialised before most of the 48 PRMTs of a node test (the first ncu source view:
+// 62 of 320 node-step instructions were such moves).  Passing the constant in as a run-time value
+// (SceneDev::qbias) makes it the register operand and the selector the immediate.
 #ifdef __CUDA_ARCH__
 #define PT_QBIAS 32768.0f
-PT_HD float pt_byte_to_float(uint32_t w, int j) {
-  return __uint_as_float(__byte_perm(w, 0x47000000u, 0x7404u | ((uint32_t)j << 4)));
+PT_HD float pt_byte_to_float(uint32_t w, int j, uint32_t qbias) {
+  return __uint_as_float(__byte_perm(w, qbias, 0x7404u | ((uint32_t)j << 4)));
 }
 #else
 #define PT_QBIAS 0.0f
-PT_HD float pt_byte_to_float(uint32_t w, int j) { return (float)pt_byte(w, j); }
+PT_HD float pt_byte_to_float(uint32_t w, int j, uint32_t) { return (float)pt_byte(w, j); }
 #endif
 
 struct RayCtx {
@@ -330,6 +335,7 @@ PT_HD void bvh8_node_step(const SceneDev& sc, const RayCtx& r, float tbest, uint
   const float by = XFMA(-PT_QBIAS, sy, (pt_u2f(n0.y) - r.o.y) * r.idy);
   const float bz = XFMA(-PT_QBIAS, sz, (pt_u2f(n0.z) - r.o.z) * r.idz);
   const uint32_t octinv4 = r.octinv * 0x01010101u;
+  const uint32_t qb = sc.qbias;
 
   uint32_t hitmask = 0;
 #pragma unroll
@@ -346,12 +352,12 @@ PT_HD void bvh8_node_step(const SceneDev& sc, const RayCtx& r, float tbest, uint
     const uint32_t nz = r.idz < 0.f ? qhiz : qloz, fz = r.idz < 0.f ? qloz : qhiz;
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-      const float t0x = XFMA(pt_byte_to_float(nx, j), sx, bx);
-      const float t0y = XFMA(pt_byte_to_float(ny, j), sy, by);
-      const float t0z = XFMA(pt_byte_to_float(nz, j), sz, bz);
-      const float t1x = XFMA(pt_byte_to_float(fx, j), sx, bx);
-      const float t1y = XFMA(pt_byte_to_float(fy, j), sy, by);
-      const float t1z = XFMA(pt_byte_to_float(fz, j), sz, bz);
+      const float t0x = XFMA(pt_byte_to_float(nx, j, qb), sx, bx);
+      const float t0y = XFMA(pt_byte_to_float(ny, j, qb), sy, by);
+      const float t0z = XFMA(pt_byte_to_float(nz, j, qb), sz, bz);
+      const float t1x = XFMA(pt_byte_to_float(fx, j, qb), sx, bx);
+      const float t1y = XFMA(pt_byte_to_float(fy, j, qb), sy, by);
+      const float t1z = XFMA(pt_byte_to_float(fz, j, qb), sz, bz);
       const float cmin = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, r.tmin));
       const float cmax = fminf(fminf(t1x, t1y), fminf(t1z, tbest));
       if (cmin <= cmax) hitmask |= pt_byte(child_bits4, j) << pt_byte(bit_index4, j);
