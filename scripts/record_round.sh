@@ -4,6 +4,7 @@ R=${1:-r01}
 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${R}_bench_c2_reference.json 2>/dev/null
 python bench.py > gpurun_out/${R}_bench_c2.json 2>/dev/null
 for w in c1 c3 c4; do python bench.py --workload $w --steps 3 --warmup 3 > gpurun_out/${R}_bench_$w.json 2>/dev/null; done
+python bench.py --workload c4_10m --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/${R}_bench_c4_10m.json 2>/dev/null
 # launch list of the default bench command (first 800 launches after warm-up launches)
 ncu --metrics gpu__time_duration.sum --clock-control none -s 200 -c 800 --csv --log-file gpurun_out/${R}_launches_c2.csv python bench.py --steps 1 --warmup 1 --spp 16 --no-cpu-baseline > /dev/null 2>&1
 # full captures of the dominant kernel on large launches

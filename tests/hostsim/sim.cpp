@@ -255,6 +255,25 @@ int sim_validate(const Sim* s) {
   return 0;
 }
 
+// children per BVH8 node, primitives per leaf child, and how many nodes have an empty upper half (slots 4..7)
+void sim_child_hist(const Sim* s, int* children /*9*/, int* leaf_prims /*4*/, int* upper_empty) {
+  for (int i = 0; i < 9; i++) children[i] = 0;
+  for (int i = 0; i < 4; i++) leaf_prims[i] = 0;
+  *upper_empty = 0;
+  for (int ni = 0; ni < s->n_nodes8; ni++) {
+    const uint4* np = s->nodes8.data() + (size_t)ni * 5;
+    int c = 0;
+    for (int k = 0; k < 8; k++) {
+      uint32_t m = ((k < 4 ? np[1].z : np[1].w) >> (8 * (k & 3))) & 0xff;
+      if (!m) continue;
+      c++;
+      if (!((np[0].w >> 24) & (1u << k))) leaf_prims[pt_popc(m >> 5)]++;
+    }
+    children[c]++;
+    if (np[1].w == 0) ++*upper_empty;
+  }
+}
+
 int sim_trace(const Sim* s, const pt_ray* rays, long long n, pt_hit* hits, unsigned long long* counters) {
   unsigned long long cn = 0, cl = 0;
 #pragma omp parallel for schedule(dynamic, 256) reduction(+ : cn, cl)
