@@ -35,15 +35,48 @@ constexpr int NBINS = PT_MAT_TYPE_COUNT + 1;  // PT_MAT_* + miss
 constexpr int BIN_MISS = PT_MAT_TYPE_COUNT;
 constexpr int NSHADOW = 8;
 
-struct PathBuf {  // 64 B / path
-  float4* o_seed;  // origin.xyz, seed
-  float4* d_pack;  // dir.xyz, pix | depth<<23 | prevSpecular<<31
-  float4* thr;     // throughput.xyz, -
-  float4* rad;     // radiance.xyz, prd.time (shutter time of the sample, raygen.cu:69)
+// Path state: 64 B / path = 4 x float4
+//   0 o_seed  origin.xyz, seed
+//   1 d_pack  dir.xyz, pix | depth<<23 | prevSpecular<<31
+//   2 thr     throughput.xyz, BSDF pdf of this ray (env NEE MIS)
+//   3 rad     radiance.xyz, prd.time (shutter time of the sample, raygen.cu:69)
+// Shadow request: 7 float4 (+ an 8th, s[7] = (prd.time, seed at shadow time), only in scenes with
+// moving / volumetric primitives).
+// Layout (measured, profiles/r01_layout_ab.md): the path state is one 64-byte record per path (AoS of
+// float4) - appends by consecutive slots stay coalesced either way, and the material-sorted shade
+// kernels, which GATHER by path index, touch two full 32-byte sectors per path instead of a half-used
+// sector in each of four arrays (C2 +5 %, C3 +2 %).  Shadow requests stay one array per float4: they are
+// written once by consecutive slots and most of a 128-byte record would be a partial-line write
+// (AoS requests: C1 -9 %).  -DPT_PATH_SOA / -DPT_SHADOW_AOS build the other layouts.
+#ifndef PT_SHADOW_AOS
+#define PT_SHADOW_SOA
+#endif
+#ifdef PT_PATH_SOA
+struct PathBuf {
+  float4* a[4];
+  __device__ __forceinline__ float4& f(int k, int i) const { return a[k][i]; }
 };
-struct ShadowBuf {  // 112 B / shadow request (+16 B: s[7].x = prd.time, only in scenes with moving/volumetric primitives)
-  float4* s[NSHADOW];
+#else
+struct PathBuf {
+  float4* base;
+  __device__ __forceinline__ float4& f(int k, int i) const { return base[(size_t)i * 4 + k]; }
 };
+#endif
+#ifdef PT_SHADOW_SOA
+struct ShadowBuf {
+  float4* a[NSHADOW];
+  __device__ __forceinline__ float4& s(int k, int i) const { return a[k][i]; }
+};
+#else
+struct ShadowBuf {
+  float4* base;
+  __device__ __forceinline__ float4& s(int k, int i) const { return base[(size_t)i * NSHADOW + k]; }
+};
+#endif
+#define P_OSEED 0
+#define P_DPACK 1
+#define P_THR 2
+#define P_RAD 3
 
 // Device control block.  Every atomically updated counter sits on its own 128-byte line: queue
 // tails, bin counters and fetch cursors are hammered by warp-aggregated atomics from all SMs while
@@ -121,10 +154,10 @@ __device__ __forceinline__ void finish_bounce(const Params& p, Ctrl* c, const Pa
     return;
   }
   int slot = push_slot(&c->n_next);
-  next.o_seed[slot] = make_float4(o.x, o.y, o.z, __uint_as_float(seed));
-  next.d_pack[slot] = make_float4(d.x, d.y, d.z, __uint_as_float(pack_state(pix, depth, specular)));
-  next.thr[slot] = make_float4(thr.x, thr.y, thr.z, pdf);  // .w: BSDF pdf of this ray (env NEE MIS)
-  next.rad[slot] = make_float4(rad.x, rad.y, rad.z, time);
+  next.f(P_OSEED, slot) = make_float4(o.x, o.y, o.z, __uint_as_float(seed));
+  next.f(P_DPACK, slot) = make_float4(d.x, d.y, d.z, __uint_as_float(pack_state(pix, depth, specular)));
+  next.f(P_THR, slot) = make_float4(thr.x, thr.y, thr.z, pdf);  // .w: BSDF pdf of this ray (env NEE MIS)
+  next.f(P_RAD, slot) = make_float4(rad.x, rad.y, rad.z, time);
 }
 
 __global__ void k_iter_begin(Ctrl* c, int pool) {
@@ -161,10 +194,10 @@ __global__ void k_generate(SceneDev sc, Params p, const Ctrl* c, PathBuf cur) {
     camera_ray(sc.camera, p.W, p.H, x, y, frame, seed, o, d);
     const float time = sc.camera.time0 + pt_rnd(seed) * (sc.camera.time1 - sc.camera.time0);  // raygen.cu:69
     int s = base + i;
-    cur.o_seed[s] = make_float4(o.x, o.y, o.z, __uint_as_float(seed));
-    cur.d_pack[s] = make_float4(d.x, d.y, d.z, __uint_as_float(pack_state(pix, 0, false)));
-    cur.thr[s] = make_float4(1.f, 1.f, 1.f, 0.f);
-    cur.rad[s] = make_float4(0.f, 0.f, 0.f, time);
+    cur.f(P_OSEED, s) = make_float4(o.x, o.y, o.z, __uint_as_float(seed));
+    cur.f(P_DPACK, s) = make_float4(d.x, d.y, d.z, __uint_as_float(pack_state(pix, 0, false)));
+    cur.f(P_THR, s) = make_float4(1.f, 1.f, 1.f, 0.f);
+    cur.f(P_RAD, s) = make_float4(0.f, 0.f, 0.f, time);
   }
 }
 
@@ -177,7 +210,7 @@ struct ClosestPolicy {
   uint32_t* bin_q;
   int pool;
   __device__ __forceinline__ bool load(int i, float3& o, float3& d, float& tmin, float& tmax) const {
-    float4 o4 = cur.o_seed[i], d4 = cur.d_pack[i];
+    float4 o4 = cur.f(P_OSEED, i), d4 = cur.f(P_DPACK, i);
     int depth = (__float_as_uint(d4.w) >> 23) & 0xff;
     o = f3(o4.x, o4.y, o4.z);
     d = f3(d4.x, d4.y, d4.z);
@@ -187,7 +220,7 @@ struct ClosestPolicy {
   }
   __device__ __forceinline__ bool any_hit(int) const { return false; }
   __device__ __forceinline__ RayAux aux(int i) const {
-    return RayAux{cur.rad[i].w, __float_as_uint(cur.o_seed[i].w)};
+    return RayAux{cur.f(P_RAD, i).w, __float_as_uint(cur.f(P_OSEED, i).w)};
   }
   __device__ __forceinline__ void emit(int i, const TraceHit& h, unsigned fin) const {
     hits[i] = make_float4(h.t, __int_as_float(h.leaf), h.u, h.v);
@@ -236,7 +269,7 @@ __global__ void __launch_bounds__(128, PT_SHADE_MINBLOCKS) k_shade(SceneDev sc, 
   const uint32_t* q = bin_q + (size_t)MAT * p.pool;
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
     const int i = (int)q[j];
-    float4 o4 = cur.o_seed[i], d4 = cur.d_pack[i], t4 = cur.thr[i], r4 = cur.rad[i], h4 = hits[i];
+    float4 o4 = cur.f(P_OSEED, i), d4 = cur.f(P_DPACK, i), t4 = cur.f(P_THR, i), r4 = cur.f(P_RAD, i), h4 = hits[i];
     uint32_t pk = __float_as_uint(d4.w);
     PathIn in;
     in.o = f3(o4.x, o4.y, o4.z);
@@ -259,14 +292,17 @@ __global__ void __launch_bounds__(128, PT_SHADE_MINBLOCKS) k_shade(SceneDev sc, 
     } else {
       int s = push_slot(&c->n_shadow);
       uint32_t pk2 = pack_state(pix, in.depth, out.terminal);
-      sb.s[0][s] = make_float4(out.P.x, out.P.y, out.P.z, __uint_as_float(out.seed));
-      sb.s[1][s] = make_float4(out.WiL.x, out.WiL.y, out.WiL.z, __uint_as_float(out.seedS));
-      sb.s[2][s] = make_float4(out.dir.x, out.dir.y, out.dir.z, __uint_as_float(pk2));
-      sb.s[3][s] = make_float4(out.dirS.x, out.dirS.y, out.dirS.z, out.thr.x);
-      sb.s[4][s] = make_float4(out.thr.y, out.thr.z, out.rad.x, out.rad.y);
-      sb.s[5][s] = make_float4(out.rad.z, out.thrS.x, out.thrS.y, out.thrS.z);
-      sb.s[6][s] = make_float4(out.radS.x, out.radS.y, out.radS.z, out.env_shadow ? out.pdf : -1.f);
-      if (sc.special_mask) sb.s[7][s] = make_float4(in.time, __uint_as_float(out.seedShadow), 0.f, 0.f);
+      sb.s(0, s) = make_float4(out.P.x, out.P.y, out.P.z, __uint_as_float(out.seed));
+      sb.s(1, s) = make_float4(out.WiL.x, out.WiL.y, out.WiL.z, __uint_as_float(out.seedS));
+      sb.s(2, s) = make_float4(out.dir.x, out.dir.y, out.dir.z, __uint_as_float(pk2));
+      sb.s(3, s) = make_float4(out.dirS.x, out.dirS.y, out.dirS.z, out.thr.x);
+      sb.s(4, s) = make_float4(out.thr.y, out.thr.z, out.rad.x, out.rad.y);
+      sb.s(5, s) = make_float4(out.rad.z, out.thrS.x, out.thrS.y, out.thrS.z);
+      sb.s(6, s) = make_float4(out.radS.x, out.radS.y, out.radS.z, out.env_shadow ? out.pdf : -1.f);
+#if defined(PT_SHADOW_SOA) && !defined(PT_SHADOW_FULL)
+      if (sc.special_mask)
+#endif
+        sb.s(7, s) = make_float4(in.time, __uint_as_float(out.seedShadow), 0.f, 0.f);
     }
   }
 }
@@ -276,7 +312,7 @@ __global__ void __launch_bounds__(128) k_miss(SceneDev sc, Params p, Ctrl* c, Pa
   const uint32_t* q = bin_q + (size_t)BIN_MISS * p.pool;
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
     const int i = (int)q[j];
-    float4 d4 = cur.d_pack[i], t4 = cur.thr[i], r4 = cur.rad[i];
+    float4 d4 = cur.f(P_DPACK, i), t4 = cur.f(P_THR, i), r4 = cur.f(P_RAD, i);
     PathIn in;
     in.d = f3(d4.x, d4.y, d4.z);
     in.thr = f3(t4.x, t4.y, t4.z);
@@ -295,7 +331,7 @@ struct ShadowPolicy {
   PathBuf next;
   ShadowBuf sb;
   __device__ __forceinline__ bool load(int i, float3& o, float3& d, float& tmin, float& tmax) const {
-    float4 s0 = sb.s[0][i], s1 = sb.s[1][i];
+    float4 s0 = sb.s(0, i), s1 = sb.s(1, i);
     o = f3(s0.x, s0.y, s0.z);
     d = f3(s1.x, s1.y, s1.z);
     tmin = 1e-3f;
@@ -306,17 +342,17 @@ struct ShadowPolicy {
 #ifdef PT_NO_ANYHIT
   __device__ __forceinline__ bool any_hit(int) const { return false; }
 #else
-  __device__ __forceinline__ bool any_hit(int i) const { return sb.s[6][i].w >= 0.f; }
+  __device__ __forceinline__ bool any_hit(int i) const { return sb.s(6, i).w >= 0.f; }
 #endif
   // PINNED: the reference's volume programs would read prd.seed through a PerRayData_Shadow
   // payload (undefined); shadow rays use prd.seed as it is when Direct_Light traces them
   __device__ __forceinline__ RayAux aux(int i) const {
-    const float4 s7 = sb.s[7][i];
+    const float4 s7 = sb.s(7, i);
     return RayAux{s7.x, __float_as_uint(s7.y)};
   }
   __device__ __forceinline__ void emit(int i, const TraceHit& h, unsigned) const {
-    float4 s0 = sb.s[0][i], s1 = sb.s[1][i], s2 = sb.s[2][i], s3 = sb.s[3][i], s4 = sb.s[4][i], s5 = sb.s[5][i],
-           s6 = sb.s[6][i];
+    float4 s0 = sb.s(0, i), s1 = sb.s(1, i), s2 = sb.s(2, i), s3 = sb.s(3, i), s4 = sb.s(4, i), s5 = sb.s(5, i),
+           s6 = sb.s(6, i);
     const bool env = s6.w >= 0.f;  // shadow ray towards the environment: visible <=> nothing hit
     bool visible = env ? h.leaf < 0 : false;
     if (!env && h.leaf >= 0) visible = (__float_as_uint(__ldg(&sc.leaves[h.leaf].c.w)) >> 24) == PT_MAT_DIFFUSE_LIGHT;
@@ -339,7 +375,7 @@ struct ShadowPolicy {
     }
     if (terminal) accumulate(p, pix, rad);
     else finish_bounce(p, c, next, pix, depth, f3(s0.x, s0.y, s0.z), dir, thr, rad, seed, false, env ? s6.w : 0.f,
-                       sc.special_mask ? sb.s[7][i].x : 0.f);
+                       sc.special_mask ? sb.s(7, i).x : 0.f);
   }
 };
 
@@ -493,7 +529,7 @@ struct pt_renderer {
   // path index in different arrays never maps to the same DRAM/L2 partition (arrays of exactly
   // 2^26 bytes allocated back to back alias badly: measured -30 % on NEE scenes)
   DevBuf slab, ctrl;
-  float4 *pathA[4] = {}, *pathB[4] = {}, *shadow[NSHADOW] = {}, *hits = nullptr;
+  float4 *pathA[4] = {}, *pathB[4] = {}, *shadow[NSHADOW] = {}, *hits = nullptr;  // AoS: element [0] is the base
   uint32_t* bin_q = nullptr;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -532,9 +568,18 @@ static int ensure_pool(pt_renderer* r, long long want) {
     k++;
     return p;
   };
+#ifdef PT_PATH_SOA
   for (int i = 0; i < 4; i++) r->pathA[i] = (float4*)carve(arr);
   for (int i = 0; i < 4; i++) r->pathB[i] = (float4*)carve(arr);
+#else
+  r->pathA[0] = (float4*)carve(arr * 4);
+  r->pathB[0] = (float4*)carve(arr * 4);
+#endif
+#ifdef PT_SHADOW_SOA
   for (int i = 0; i < NSHADOW; i++) r->shadow[i] = (float4*)carve(arr);
+#else
+  r->shadow[0] = (float4*)carve(arr * NSHADOW);
+#endif
   r->hits = (float4*)carve(arr);
   r->bin_q = (uint32_t*)(base + off);
   return PT_OK;
@@ -644,12 +689,21 @@ int pt_render(pt_renderer* r, int32_t first_frame, int32_t nframes, int32_t max_
   p.pool = r->pool;
   p.accum = r->accum;
   PathBuf A, B;
-  A.o_seed = r->pathA[0]; A.d_pack = r->pathA[1];
-  A.thr = r->pathA[2]; A.rad = r->pathA[3];
-  B.o_seed = r->pathB[0]; B.d_pack = r->pathB[1];
-  B.thr = r->pathB[2]; B.rad = r->pathB[3];
   ShadowBuf sb;
-  for (int k = 0; k < NSHADOW; k++) sb.s[k] = r->shadow[k];
+#ifdef PT_PATH_SOA
+  for (int k = 0; k < 4; k++) {
+    A.a[k] = r->pathA[k];
+    B.a[k] = r->pathB[k];
+  }
+#else
+  A.base = r->pathA[0];
+  B.base = r->pathB[0];
+#endif
+#ifdef PT_SHADOW_SOA
+  for (int k = 0; k < NSHADOW; k++) sb.a[k] = r->shadow[k];
+#else
+  sb.base = r->shadow[0];
+#endif
   Ctrl* c = r->ctrl.as<Ctrl>();
   float4* hits = r->hits;
   uint32_t* bq = r->bin_q;
