@@ -111,7 +111,25 @@ struct alignas(PT_CTR_STRIDE) Ctrl {
 struct Params {
   int W, H, max_depth, russian, pool;  // (the first frame index lives in Ctrl so captured graphs stay valid)
   float4* accum;
+  uint32_t c16, c1;  // the constants 16 and 1 as run-time values, see pt_tea64_balanced
 };
+
+// tea<64> (programs/random.cuh:33-47) is 64 rounds of shift / add / xor: as written every operation
+// lands on the ALU pipe (LEA, LEA.HI, VIADD, LOP3 - 9 of 10 instructions per round) while the FMA
+// pipe idles, and one seed per camera ray made k_generate 6-7 % of the headline run.  `(v << 4) + k`
+// and `v + s` are integer multiply-adds; with 16 and 1 passed in as run-time values ptxas cannot
+// turn them back into shifts, so they issue as IMAD on the FMA pipe and the two pipes carry
+// 2.5 operations per half-round each.  Integer arithmetic: bit-identical to pt_tea64.
+__device__ __forceinline__ uint32_t pt_tea64_balanced(uint32_t val0, uint32_t val1, uint32_t c16, uint32_t c1) {
+  uint32_t v0 = val0, v1 = val1, s0 = 0;
+#pragma unroll 8
+  for (int n = 0; n < 64; n++) {
+    s0 += 0x9e3779b9u;
+    v0 += (v1 * c16 + 0xa341316cu) ^ (v1 * c1 + s0) ^ ((v1 >> 5) + 0xc8013ea4u);
+    v1 += (v0 * c16 + 0xad90777du) ^ (v0 * c1 + s0) ^ ((v0 >> 5) + 0x7e95761eu);
+  }
+  return v0;
+}
 
 __device__ __forceinline__ uint32_t pack_state(uint32_t pix, int depth, bool spec) {
   return pix | ((uint32_t)depth << 23) | (spec ? 0x80000000u : 0u);
@@ -191,7 +209,8 @@ __global__ void k_generate(SceneDev sc, Params p, const Ctrl* c, PathBuf cur) {
     int x = pix % p.W, y = pix / p.W;
     uint32_t seed;
     float3 o, d;
-    camera_ray(sc.camera, p.W, p.H, x, y, frame, seed, o, d);
+    seed = pt_tea64_balanced((uint32_t)p.W * (uint32_t)y + (uint32_t)x, (uint32_t)frame, p.c16, p.c1);
+    camera_ray_seeded(sc.camera, p.W, p.H, x, y, seed, o, d);
     const float time = sc.camera.time0 + pt_rnd(seed) * (sc.camera.time1 - sc.camera.time0);  // raygen.cu:69
     int s = base + i;
     cur.f(P_OSEED, s) = make_float4(o.x, o.y, o.z, __uint_as_float(seed));
@@ -688,6 +707,8 @@ int pt_render(pt_renderer* r, int32_t first_frame, int32_t nframes, int32_t max_
   p.russian = russian;
   p.pool = r->pool;
   p.accum = r->accum;
+  p.c16 = 16u;
+  p.c1 = 1u;
   PathBuf A, B;
   ShadowBuf sb;
 #ifdef PT_PATH_SOA

@@ -599,9 +599,14 @@ PT_HD HitRec make_hit_record(const SceneDev& sc, float3 o, float3 d, float t, in
 }
 
 // ---- camera: programs/raygen.cu:50-64,148-162 ----------------------------------------------
+// camera ray for a seed that is already computed (the device hashes with pt_tea64_balanced, integrator.cu)
+PT_HD void camera_ray_seeded(const pt_camera& c, int W, int H, int x, int y, uint32_t& seed, float3& o, float3& d);
 PT_HD void camera_ray(const pt_camera& c, int W, int H, int x, int y, int frame, uint32_t& seed, float3& o,
                       float3& d) {
   seed = pt_tea64((uint32_t)W * (uint32_t)y + (uint32_t)x, (uint32_t)frame);
+  camera_ray_seeded(c, W, H, x, y, seed, o, d);
+}
+PT_HD void camera_ray_seeded(const pt_camera& c, int W, int H, int x, int y, uint32_t& seed, float3& o, float3& d) {
   float u = float(x + pt_rnd(seed)) / W;
   float v = float(y + pt_rnd(seed)) / H;
   float3 rd = c.lens_radius * pt_random_in_unit_disk(seed);
