@@ -470,6 +470,25 @@ PT_HD void collapse_node(const Collapse& c, int ref, int dst, uint2* out_work, i
     n = 1;
   }
   for (int i = 0; i < n; i++) bvh2_child_box(t, cref[i], clo[i], chi[i], ccnt[i]);
+  // Quantisation guard: child boxes are stored on this node's 8-bit grid, whose step is the node's
+  // extent / 255.  A subtree that spans only a few steps (small objects next to a huge one: the 1000-
+  // unit ground sphere of the RTOW scenes, a fog ball around a whole scene, room walls) would have
+  // all of its children rounded out to about the same coarse box, and every ray entering it would
+  // visit all of them.  Such a subtree is not opened here: it stays ONE inner child and gets a node
+  // (and a grid) of its own.  PT_QUANT_MIN_STEPS = 0 disables the rule.
+#ifndef PT_QUANT_MIN_STEPS
+#define PT_QUANT_MIN_STEPS 16
+#endif
+  float node_ext = 0.f;
+  {
+    float3 ulo = clo[0], uhi = chi[0];
+    for (int i = 1; i < n; i++) {
+      ulo = fmin3(ulo, clo[i]);
+      uhi = fmax3(uhi, chi[i]);
+    }
+    node_ext = fmaxf(fmaxf(uhi.x - ulo.x, uhi.y - ulo.y), uhi.z - ulo.z);
+  }
+  const float min_child_ext = node_ext * ((float)PT_QUANT_MIN_STEPS / 255.0f);
   // greedy expansion by surface area: first only subtrees too big for a leaf
   // (> 3 primitives), then any inner node while slots remain
   for (int pass = 0; pass < 2; pass++) {
@@ -479,6 +498,8 @@ PT_HD void collapse_node(const Collapse& c, int ref, int dst, uint2* out_work, i
       float ba = -1.f;
       for (int i = 0; i < n; i++)
         if (cref[i] >= 0 && ccnt[i] >= minc) {
+          const float3 e = chi[i] - clo[i];
+          if (fmaxf(fmaxf(e.x, e.y), e.z) < min_child_ext && ccnt[i] > 3) continue;  // keep as one inner child
           float a = box_half_area(clo[i], chi[i]);
           if (a > ba) {
             ba = a;

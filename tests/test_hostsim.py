@@ -287,3 +287,20 @@ def test_volume_free_flight_is_exponential():
     # truncated-exponential mean of the scattering distances
     expect = 1 / sigma - D * np.exp(-sigma * D) / (1 - np.exp(-sigma * D))
     assert abs(dist.mean() - expect) < 0.3
+
+
+def test_quantisation_guard_for_huge_next_to_small():
+    """BVH8 child boxes live on the parent's 8-bit grid.  The RTOW scenes put a 1000-unit ground sphere next
+    to 0.2-unit spheres: opened into the root, the small-sphere subtrees would all be rounded out to the same
+    ~8-unit cells and every ray would visit all of them (7.5 nodes per ray before the guard in collapse_node).
+    With the guard the small spheres stay under one inner child with a grid of its own."""
+    sc = h.build_spheres(22)
+    sim = h.SimScene(sc)
+    assert sim.validate() == 0
+    orc = h.OracleScene(sc, mode=1)
+    rays = orc.camera_rays(64, 64, 0)
+    rays = np.concatenate([rays, orc.bounce_rays(rays, 7)])
+    hs, cnt = sim.trace(rays)
+    ho, _ = orc.trace(rays)
+    assert same_hits(ho, hs).all()
+    assert cnt[0] / len(rays) < 5.5, cnt[0] / len(rays)
