@@ -201,11 +201,16 @@ __global__ void k_iter_begin(Ctrl* c, int pool) {
 __global__ void k_generate(SceneDev sc, Params p, const Ctrl* c, PathBuf cur) {
   const int n = c->gen_n, base = c->gen_base;
   const unsigned long long sbase = c->sample_base;
-  const unsigned long long npix = (unsigned long long)p.W * p.H;
+  const uint32_t npix = (uint32_t)p.W * (uint32_t)p.H;
+  // sample id -> (frame, pixel): one 64-bit division per thread; inside the loop the offset from the
+  // first sample of this launch is < npix + pool < 2^26, so 32-bit arithmetic does
+  const int frame0 = c->first_frame + (int)(sbase / npix);
+  const uint32_t rem0 = (uint32_t)(sbase % npix);
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    unsigned long long sid = sbase + (unsigned long long)i;
-    int frame = c->first_frame + (int)(sid / npix);
-    uint32_t pix = (uint32_t)(sid % npix);
+    const uint32_t t = rem0 + (uint32_t)i;
+    const uint32_t fr = t / npix;
+    int frame = frame0 + (int)fr;
+    uint32_t pix = t - fr * npix;
     int x = pix % p.W, y = pix / p.W;
     uint32_t seed;
     float3 o, d;
@@ -265,7 +270,8 @@ __global__ void __launch_bounds__(PT_TRACE_THREADS, PT_TRACE_MINBLOCKS) k_trace(
   __shared__ uint2 s_stack[PT_SMEM_STACK * PT_TRACE_THREADS];
   ClosestPolicy pol{sc, c, cur, hits, bin_q, pool};
   uint32_t cn = 0, cl = 0;
-  trace_persistent<COUNT, SPECIAL>(sc, c->n_cur, &c->fetch_closest, pol, s_stack, sched, &c->error, cn, cl);
+  if (sched.flat) trace_flat<COUNT, SPECIAL>(sc, c->n_cur, pol, cl);
+  else trace_persistent<COUNT, SPECIAL>(sc, c->n_cur, &c->fetch_closest, pol, s_stack, sched, &c->error, cn, cl);
   if (COUNT) {
     for (int o = 16; o > 0; o >>= 1) {
       cn += __shfl_xor_sync(0xffffffffu, cn, o);
@@ -404,7 +410,8 @@ __global__ void __launch_bounds__(PT_TRACE_THREADS, PT_TRACE_MINBLOCKS) k_shadow
   __shared__ uint2 s_stack[PT_SMEM_STACK * PT_TRACE_THREADS];
   ShadowPolicy pol{sc, p, c, next, sb};
   uint32_t cn = 0, cl = 0;
-  trace_persistent<COUNT, SPECIAL>(sc, c->n_shadow, &c->fetch_shadow, pol, s_stack, sched, &c->error, cn, cl);
+  if (sched.flat) trace_flat<COUNT, SPECIAL>(sc, c->n_shadow, pol, cl);
+  else trace_persistent<COUNT, SPECIAL>(sc, c->n_shadow, &c->fetch_shadow, pol, s_stack, sched, &c->error, cn, cl);
   if (COUNT) {
     for (int o = 16; o > 0; o >>= 1) {
       cn += __shfl_xor_sync(0xffffffffu, cn, o);
@@ -449,7 +456,8 @@ __global__ void __launch_bounds__(PT_TRACE_THREADS, PT_TRACE_MINBLOCKS) k_trace_
   __shared__ uint2 s_stack[PT_SMEM_STACK * PT_TRACE_THREADS];
   RaySetPolicy pol{rays, hits, sc.camera.time0};
   uint32_t cn = 0, cl = 0;
-  trace_persistent<COUNT, SPECIAL>(sc, n, (int*)(counters + 2), pol, s_stack, sched, (int*)(counters + 3), cn, cl);
+  if (sched.flat) trace_flat<COUNT, SPECIAL>(sc, n, pol, cl);
+  else trace_persistent<COUNT, SPECIAL>(sc, n, (int*)(counters + 2), pol, s_stack, sched, (int*)(counters + 3), cn, cl);
   if (COUNT) {
     for (int o = 16; o > 0; o >>= 1) {
       cn += __shfl_xor_sync(0xffffffffu, cn, o);
@@ -487,14 +495,27 @@ int sm_count() {
 }
 
 // scheduler knobs; PTB200_REFILL_MIN / PTB200_LEAF_THRESH override the tuned defaults (dev only)
-SchedParams sched_params() {
+// scenes with at most this many primitives are traversed flat (trace_flat); PTB200_FLAT_MAX overrides (dev)
+int flat_max() {
+  static int v = [] {
+    const char* e = getenv("PTB200_FLAT_MAX");
+    return e ? atoi(e) : 16;
+  }();
+  return v;
+}
+SchedParams sched_params_base() {
   static SchedParams p = [] {
-    SchedParams q{12, 8, 0};
+    SchedParams q{12, 8, 0, 0};
     if (const char* e = getenv("PTB200_REFILL_MIN")) q.refill_min = std::max(1, atoi(e));
     if (const char* e = getenv("PTB200_LEAF_THRESH")) q.leaf_thresh = std::max(1, atoi(e));
     if (const char* e = getenv("PTB200_FETCH_CHUNK")) q.fetch_chunk = std::max(0, atoi(e));
     return q;
   }();
+  return p;
+}
+SchedParams sched_params(const SceneDev& sc) {
+  SchedParams p = sched_params_base();
+  p.flat = sc.n_prims <= flat_max() ? 1 : 0;
   return p;
 }
 
@@ -735,7 +756,15 @@ int pt_render(pt_renderer* r, int32_t first_frame, int32_t nframes, int32_t max_
   const bool special = sc.special_mask != 0;
   const int g_trace = sms * trace_blocks_per_sm(special), g_shade = sms * 8, g_gen = sms * 4;
   const uint32_t mask = s->material_type_mask;
-  const SchedParams sched = sched_params();
+  const SchedParams sched = sched_params(sc);
+  // shadow rays keep the BVH walk even in tiny scenes: they start on a surface and aim at a light, the one
+  // node test culls most primitives, and testing all of them flat was 7 % slower end to end (C1, C3);
+  // closest-hit rays are 25-45 % faster flat.  PTB200_FLAT_SHADOW=1 overrides (dev)
+  SchedParams sched_shadow = sched;
+  {
+    static const int fs = getenv("PTB200_FLAT_SHADOW") ? atoi(getenv("PTB200_FLAT_SHADOW")) : 0;
+    sched_shadow.flat = sched.flat && fs != 0;
+  }
   const bool need_shadow = (mask & ((1u << PT_MAT_LAMBERTIAN) | (1u << PT_MAT_OREN_NAYAR) | (1u << PT_MAT_DIFFUSE_LIGHT) |
                                     (1u << PT_MAT_ISOTROPIC))) &&
                            (s->lights.size() > 0 || sc.env_n > 0);
@@ -785,7 +814,7 @@ int pt_render(pt_renderer* r, int32_t first_frame, int32_t nframes, int32_t max_
     if (timed) cudaEventRecord(e[3], st);
     n++;
     if (need_shadow) {
-      PT_LAUNCH_TRACE(k_shadow, count, special, g_trace, st, sc, p, c, nxt, sb, sched);
+      PT_LAUNCH_TRACE(k_shadow, count, special, g_trace, st, sc, p, c, nxt, sb, sched_shadow);
       n++;
     }
     if (timed) {
@@ -941,7 +970,7 @@ int pt_trace_rays_device(pt_scene* scene, const void* d_rays, int64_t n, void* d
   PT_CUDA(cudaMemsetAsync(dc, 0, 32, st));
   const bool special = scene->dev.special_mask != 0;
   PT_LAUNCH_TRACE(k_trace_rays, false, special, sm_count() * trace_blocks_per_sm(special), st, scene->dev,
-                  (const pt_ray*)d_rays, (int)n, (pt_hit*)d_hits, dc, sched_params());
+                  (const pt_ray*)d_rays, (int)n, (pt_hit*)d_hits, dc, sched_params(scene->dev));
   PT_CUDA(cudaGetLastError());
   PT_CUDA(cudaFreeAsync(dc, st));
   return PT_OK;
@@ -967,7 +996,7 @@ int pt_trace_rays(pt_scene* scene, const pt_ray* rays, int64_t n, pt_hit* hits, 
   const bool special = scene->dev.special_mask != 0;
   const int grid = sm_count() * trace_blocks_per_sm(special);
   PT_LAUNCH_TRACE(k_trace_rays, counters != nullptr, special, grid, (cudaStream_t)0, scene->dev, dr.as<pt_ray>(), (int)n,
-                  dh.as<pt_hit>(), dc.as<unsigned long long>(), sched_params());
+                  dh.as<pt_hit>(), dc.as<unsigned long long>(), sched_params(scene->dev));
   PT_CUDA(cudaGetLastError());
   PT_CUDA(cudaMemcpy(hits, dh.p, (size_t)n * sizeof(pt_hit), cudaMemcpyDeviceToHost));
   unsigned long long hc[4];

@@ -35,6 +35,7 @@ struct SchedParams {
   int refill_min;   // refill when at least this many lanes are idle (or the whole warp is)
   int leaf_thresh;  // run a leaf step when >= this many lanes have a pending leaf (or leaf lanes are the majority)
   int fetch_chunk;  // rays a warp claims from the queue per atomic (surplus stays warp-private); 0 = exactly the idle lanes
+  int flat;         // tiny scene: skip the BVH, every lane tests every leaf record (trace_flat)
 };
 
 template <class Policy, bool SPECIAL>
@@ -151,5 +152,58 @@ __device__ __forceinline__ void trace_persistent(const SceneDev& sc, int n, int*
         }
       }
     }
+  }
+}
+
+// ---- flat traversal for tiny scenes --------------------------------------------------------------
+// Cornell-type scenes hold 7..16 primitives in ONE BVH8 node.  Walking that node through the
+// vote-scheduled machinery costs a 320-instruction node test, a handful of scheduler rounds and leaf
+// tests that run with 2-8 active lanes.  Here every lane tests every leaf record in the same order:
+// the record address is warp-uniform (one broadcast load), the primitive kind is warp-uniform (no
+// divergence), there is no stack and no scheduling.  Same closest hit as the BVH walk: exact tests,
+// open interval, ties to the lowest primitive id; any-hit rays stop at their first hit.
+template <bool COUNT, bool SPECIAL, class Policy>
+__device__ __forceinline__ void trace_flat(const SceneDev& sc, int n, Policy& pol, uint32_t& cl) {
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int stride = gridDim.x * blockDim.x;
+  const int n_leaves = sc.n_prims;
+  for (int i0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31); i0 < n; i0 += stride) {  // warp-uniform trip count
+    const int i = i0 + lane;
+    const bool act = i < n;
+    TraceHit hit;
+    hit_reset(hit, 0.f);
+    if (act) {
+      float3 o, d;
+      float tmin, tmax;
+      const bool ok = pol.load(i, o, d, tmin, tmax);
+      const bool anyhit = pol.any_hit(i);
+      hit_reset(hit, tmax);
+      if (ok) {
+        const PolicyAux<Policy, SPECIAL> aux{pol, i};
+        for (int k = 0; k < n_leaves; k++) {
+          const float4* lp = (const float4*)(sc.leaves + k);
+          LeafRec L;
+          L.a = __ldg(lp + 0);
+          L.b = __ldg(lp + 1);
+          L.c = __ldg(lp + 2);
+          float t, u, v;
+          if (isect_leaf(sc, L, o, d, tmin, tmax, hit.t, t, u, v, aux)) {
+            const int prim = (int)pt_f2u(L.a.w);
+            if (t < hit.t || (t == hit.t && (hit.prim < 0 || prim < hit.prim))) {
+              hit.t = t;
+              hit.leaf = k;
+              hit.prim = prim;
+              hit.u = u;
+              hit.v = v;
+            }
+            if (anyhit) break;
+          }
+        }
+        if (COUNT) cl += (uint32_t)n_leaves;
+      }
+    }
+    const unsigned m = __ballot_sync(FULL, act);
+    if (act) pol.emit(i, hit, m);
   }
 }

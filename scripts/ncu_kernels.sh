@@ -10,7 +10,8 @@ rows=[l for l in open(sys.argv[1]) if l.startswith('"')]
 agg=collections.defaultdict(lambda: collections.defaultdict(float)); cnt=collections.Counter()
 for r in csv.DictReader(rows):
     name=re.sub(r"\(.*","",r["Kernel Name"]).replace("<unnamed>::","").replace("void ","")
-    v=float(r["Metric Value"].replace(",",""))
+    try: v=float(r["Metric Value"].replace(",",""))
+    except ValueError: continue
     agg[name][r["Metric Name"]]+=v
     if r["Metric Name"]=="gpu__time_duration.sum": cnt[name]+=1
 tot=sum(m["gpu__time_duration.sum"] for m in agg.values())
