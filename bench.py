@@ -394,6 +394,9 @@ def main():
                 "frac": ach / peak, "traffic": traffic,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "6.65 TB/s (of fallback)",
                 "bytes_per_ray": b_ray, "nodes_per_ray": n_node, "leaves_per_ray": n_leaf,
+                "traversal": ("flat: <= 16 primitives, closest-hit rays test every leaf record; a record is ONE warp-uniform "
+                              "broadcast fetch for 32 rays (counted once per warp), so this kernel is compute-bound, not on the "
+                              "memory roofline" if info.n_prims <= 16 else "bvh8"),
                 "rays_per_launch": stt.closest_rays / max(1, stt.iterations),
                 "launch_ms": stt.ms_trace_closest / max(1, stt.iterations),
                 "kernel_share": {"trace_closest": stt.ms_trace_closest / stt.ms_total,

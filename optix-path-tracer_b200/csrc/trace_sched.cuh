@@ -200,7 +200,7 @@ __device__ __forceinline__ void trace_flat(const SceneDev& sc, int n, Policy& po
             if (anyhit) break;
           }
         }
-        if (COUNT) cl += (uint32_t)n_leaves;
+        if (COUNT && lane == 0) cl += (uint32_t)n_leaves;  // one broadcast fetch per record serves the whole warp
       }
     }
     const unsigned m = __ballot_sync(FULL, act);
