@@ -292,6 +292,8 @@ __global__ void __launch_bounds__(128, PT_SHADE_MINBLOCKS) k_shade(SceneDev sc, 
                                                const float4* hits, const uint32_t* bin_q) {
   const int n = c->bin_count[MAT].v;
   const uint32_t* q = bin_q + (size_t)MAT * p.pool;
+  // (a software pipeline of this gather - queue entry read two iterations ahead, prefetch.global.L2 of the
+  // next path record and hit - was measured 4 % SLOWER on C2: the kernels are not latency-bound on it)
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
     const int i = (int)q[j];
     float4 o4 = cur.f(P_OSEED, i), d4 = cur.f(P_DPACK, i), t4 = cur.f(P_THR, i), r4 = cur.f(P_RAD, i), h4 = hits[i];
