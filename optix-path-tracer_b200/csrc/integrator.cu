@@ -247,7 +247,9 @@ struct ClosestPolicy {
     return RayAux{cur.f(P_RAD, i).w, __float_as_uint(cur.f(P_OSEED, i).w)};
   }
   __device__ __forceinline__ void emit(int i, const TraceHit& h, unsigned fin) const {
+#ifdef PT_HITS_BY_PATH
     hits[i] = make_float4(h.t, __int_as_float(h.leaf), h.u, h.v);
+#endif
     int key = BIN_MISS;
     if (h.leaf >= 0) key = (int)(__float_as_uint(__ldg(&sc.leaves[h.leaf].c.w)) >> 24);
     // material binning: finished lanes with the same key share one atomic
@@ -257,7 +259,13 @@ struct ClosestPolicy {
     int base = 0;
     if (lane == leader) base = atomicAdd(&c->bin_count[key].v, __popc(peers));
     base = __shfl_sync(peers, base, leader);
-    bin_q[(size_t)key * pool + base + __popc(peers & ((1u << lane) - 1))] = (uint32_t)i;
+    const size_t slot = (size_t)key * pool + base + __popc(peers & ((1u << lane) - 1));
+    bin_q[slot] = (uint32_t)i;
+#ifndef PT_HITS_BY_PATH
+    // the hit record goes into the BIN slot, next to the queue entry: the shade kernels then read it with
+    // coalesced loads (indexed by path it was a 16-byte gather that cost a 64-byte DRAM access per path)
+    if (key != BIN_MISS) hits[slot] = make_float4(h.t, __int_as_float(h.leaf), h.u, h.v);
+#endif
   }
 };
 
@@ -296,7 +304,12 @@ __global__ void __launch_bounds__(128, PT_SHADE_MINBLOCKS) k_shade(SceneDev sc, 
   // next path record and hit - was measured 4 % SLOWER on C2: the kernels are not latency-bound on it)
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
     const int i = (int)q[j];
-    float4 o4 = cur.f(P_OSEED, i), d4 = cur.f(P_DPACK, i), t4 = cur.f(P_THR, i), r4 = cur.f(P_RAD, i), h4 = hits[i];
+#ifdef PT_HITS_BY_PATH
+    const float4 h4 = hits[i];
+#else
+    const float4 h4 = hits[(size_t)MAT * p.pool + j];
+#endif
+    float4 o4 = cur.f(P_OSEED, i), d4 = cur.f(P_DPACK, i), t4 = cur.f(P_THR, i), r4 = cur.f(P_RAD, i);
     uint32_t pk = __float_as_uint(d4.w);
     PathIn in;
     in.o = f3(o4.x, o4.y, o4.z);
@@ -597,7 +610,7 @@ static int ensure_pool(pt_renderer* r, long long want) {
   const size_t arr = (size_t)pool * 16;
   const size_t skew = 33 * 256;  // odd multiple of 256 B
   const size_t gap = 64 * 1024;
-  const int n_arr = 4 + 4 + NSHADOW + 1;
+  const int n_arr = 4 + 4 + NSHADOW + NBINS;
   const size_t total = (arr + gap + 7 * skew + 256) * n_arr + (size_t)pool * 4 * NBINS + 64 * 1024;
   PT_CUDA(r->slab.alloc(total));
   char* base = r->slab.as<char>();
@@ -622,7 +635,11 @@ static int ensure_pool(pt_renderer* r, long long want) {
 #else
   r->shadow[0] = (float4*)carve(arr * NSHADOW);
 #endif
+#ifdef PT_HITS_BY_PATH
   r->hits = (float4*)carve(arr);
+#else
+  r->hits = (float4*)carve(arr * (NBINS - 1));  // one pool-sized segment per material bin
+#endif
   r->bin_q = (uint32_t*)(base + off);
   return PT_OK;
 }
