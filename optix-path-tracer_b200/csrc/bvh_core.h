@@ -16,8 +16,12 @@
 #pragma once
 #include "scene_dev.h"
 
+#ifndef PT_TREELET
 #define PT_TREELET 64
+#endif
+#ifndef PT_SAH_BINS
 #define PT_SAH_BINS 8
+#endif
 
 struct BuildIn {  // device copies of the flat scene arrays
   const pt_prim_ref* prim_ref;
@@ -501,6 +505,9 @@ PT_HD void collapse_node(const Collapse& c, int ref, int dst, uint2* out_work, i
           const float3 e = chi[i] - clo[i];
           if (fmaxf(fmaxf(e.x, e.y), e.z) < min_child_ext && ccnt[i] > 3) continue;  // keep as one inner child
           float a = box_half_area(clo[i], chi[i]);
+          // (tried: dissolving 4..6-primitive subtrees before flattening big ones - 15-25 % fewer BVH8 nodes but
+          // the same node visits per ray within 1 %, the visits are at the upper levels; likewise treelets of
+          // 32..256 leaves and 8 vs 16 SAH bins move nodes/ray by < 3 %)
           if (a > ba) {
             ba = a;
             bi = i;
