@@ -565,8 +565,10 @@ def build_mesh_scene(grid=32, W=64, H=64, lib=None, normals=False, mat_kind=None
     return s
 
 
-def build_random_prims(seed=0, n_sph=40, n_rect=30, n_box=30, n_tri=200, xforms=True, lib=None, W=32, H=32):
-    """Random soup of all four primitive kinds, some with rotate/scale/translate chains."""
+def build_random_prims(seed=0, n_sph=40, n_rect=30, n_box=30, n_tri=200, xforms=True, lib=None, W=32, H=32,
+                       n_moving=0, n_vsph=0, n_vbox=0):
+    """Random soup of all primitive kinds, some with rotate/scale/translate chains (n_moving / n_vsph / n_vbox
+    add Moving_Spheres and volumes; they come last so the ids of the other primitives do not change)."""
     rng = np.random.default_rng(seed)
     s = pt.Scene(lib)
     s.set_textures([tex_const(0.6, 0.6, 0.6)])
@@ -599,7 +601,24 @@ def build_random_prims(seed=0, n_sph=40, n_rect=30, n_box=30, n_tri=200, xforms=
         c = rng.uniform(-5, 5, (n_tri, 1, 3))
         v = (c + rng.uniform(-0.7, 0.7, (n_tri, 3, 3))).astype(np.float32).reshape(n_tri, 9)
         s.add_mesh(v, 0)
-    s.set_camera(make_camera([0, 1, -14], [0, 0, 0], [0, 1, 0], 50.0, W / H, 0.0, 10.0))
+    if n_moving:
+        ms = []
+        for _ in range(n_moving):
+            c0 = rng.uniform(-5, 5, 3)
+            ms.append(pt.MovingSphere(pt.F3(*c0), pt.F3(*(c0 + rng.uniform(-1.5, 1.5, 3))), float(rng.uniform(0.2, 0.8)),
+                                      float(rng.uniform(-0.5, 0.2)), float(rng.uniform(0.8, 1.5))))
+        s.add_moving_spheres(ms, rng.integers(0, 2, n_moving), xforms=np.stack([rand_xf() for _ in range(n_moving)]))
+    if n_vsph:
+        vs = [pt.VolumeSphere(pt.F3(*rng.uniform(-5, 5, 3)), float(rng.uniform(0.5, 2.0)), float(rng.uniform(0.2, 3.0)))
+              for _ in range(n_vsph)]
+        s.add_volume_spheres(vs, rng.integers(0, 2, n_vsph), xforms=np.stack([rand_xf() for _ in range(n_vsph)]))
+    if n_vbox:
+        vb = []
+        for _ in range(n_vbox):
+            lo = rng.uniform(-5, 4, 3)
+            vb.append(pt.VolumeBox(pt.F3(*lo), pt.F3(*(lo + rng.uniform(0.5, 2.5, 3))), float(rng.uniform(0.2, 3.0))))
+        s.add_volume_boxes(vb, rng.integers(0, 2, n_vbox), xforms=np.stack([rand_xf() for _ in range(n_vbox)]))
+    s.set_camera(make_camera([0, 1, -14], [0, 0, 0], [0, 1, 0], 50.0, W / H, 0.0, 10.0, 0.0, 1.0))
     s.set_miss(pt.Miss(pt.MISS_CONSTANT, pt.F3(0.1, 0.2, 0.3), pt.F3(0, 0, 0), -1, 1, 0))
     return s
 

@@ -304,3 +304,21 @@ def test_quantisation_guard_for_huge_next_to_small():
     ho, _ = orc.trace(rays)
     assert same_hits(ho, hs).all()
     assert cnt[0] / len(rays) < 5.5, cnt[0] / len(rays)
+
+
+def test_soup_with_moving_and_volumetric_primitives():
+    """Random soup of every primitive kind incl. transformed Moving_Spheres / volumes: BVH structure valid, hit ids
+    and t bit-identical to the oracle's brute-force loop on the CPU, Normal_Shader images identical."""
+    sc = h.build_random_prims(21, n_sph=30, n_rect=20, n_box=20, n_tri=150, n_moving=25, n_vsph=12, n_vbox=12)
+    sim, orc = h.SimScene(sc), h.OracleScene(sc, mode=1)
+    assert sim.validate() == 0
+    rays = np.concatenate([orc.camera_rays(48, 48, 0), h.random_rays(4000, 11)])
+    rays = np.concatenate([rays, orc.bounce_rays(rays, 5)])
+    ho, _ = orc.trace(rays)
+    hs, _ = sim.trace(rays)
+    assert same_hits(ho, hs).all()
+    kinds = np.array([sc.desc().prims[i].type for i in range(sc.desc().n_prims)])
+    hit_kinds = set(kinds[ho["prim"][ho["prim"] >= 0]])
+    assert {pt.PRIM_MOVING_SPHERE, pt.PRIM_VOLUME_SPHERE, pt.PRIM_VOLUME_BOX} <= hit_kinds
+    a, _ = orc.render(32, 32, 0, 3)
+    assert np.array_equal(a, sim.render(32, 32, 0, 3))
