@@ -146,6 +146,18 @@ def scene_host_bytes(d):
     return n
 
 
+_JSON_FD = None
+
+
+def emit_json(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    sys.stdout.flush()
+    if _JSON_FD is None:
+        os.write(1, line)
+    else:
+        os.write(_JSON_FD, line)
+
+
 def run_reference(args, rank, world):
     """Reference arm: the reference's algorithm on the host CPU cores (the oracle)."""
     if rank != 0:
@@ -171,7 +183,7 @@ def run_reference(args, rank, world):
     samples = W * H * spp_step * args.steps
     val = samples / tot_s / 1e6
     sample = f"{W}x{H} @ {spp_step} spp per step (of {spp}), all {st.threads} host threads, OpenMP over scanlines"
-    print(json.dumps({
+    emit_json({
         "impl": "reference", "metric": "Msamples/s", "value": val, "unit": "Msamples/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": tot_s / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -180,7 +192,7 @@ def run_reference(args, rank, world):
         "cpu_baseline": {"value": val, "unit": "Msamples/s", "cores": st.threads, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "reference needs OptiX 6 + GPU and has no CPU path; this is the oracle (CPU restatement of its programs)",
-    }), flush=True)
+    })
 
 
 def main():
@@ -194,6 +206,13 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--pool", type=int, default=0, help="path-pool size (dev only; 0 = library default)")
     args = ap.parse_args()
+    # stdout carries exactly ONE line: the JSON.  Libraries write there on their own (NCCL prints its version
+    # banner at communicator creation, the facade's scene functions printf progress like the reference), so
+    # file descriptor 1 points at stderr for the whole run and the JSON goes to the saved descriptor.
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -439,7 +458,7 @@ def main():
             "roofline": roof, "cpu_baseline": cpu_base,
             "bvh": {"build_ms": info.build_ms, "sah_lbvh": info.sah_cost_lbvh, "sah_refined": info.sah_cost_refined},
         }
-        print(json.dumps(out), flush=True)
+        emit_json(out)
     if world > 1:
         dist.destroy_process_group()
 
