@@ -347,6 +347,9 @@ __global__ void __launch_bounds__(128, PT_SHADE_MINBLOCKS) k_shade(SceneDev sc, 
   }
 }
 
+// (evaluating cheap miss programs - gradient, constant - in k_trace's epilogue instead was measured SLOWER:
+// C2 -3 %, C3 -12 %, and C4 -4 % although its HDR background does not even take that branch; the traversal
+// kernel sits at its 64-register budget and pays for every instruction added to it)
 __global__ void __launch_bounds__(128) k_miss(SceneDev sc, Params p, Ctrl* c, PathBuf cur, const uint32_t* bin_q) {
   const int n = c->bin_count[BIN_MISS].v;
   const uint32_t* q = bin_q + (size_t)BIN_MISS * p.pool;
