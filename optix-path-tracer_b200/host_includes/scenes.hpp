@@ -7,7 +7,11 @@
 // rnd() draws inside one argument list are taken right-to-left, which is what g++
 // (and MSVC x64, the reference's toolchain) do for the reference's expressions.
 #pragma once
+#include <sys/stat.h>
+#include <unistd.h>
+
 #include <chrono>
+#include <cstdio>
 
 #include "camera.hpp"
 #include "hitables.hpp"
@@ -15,6 +19,16 @@
 #include "pdfs.hpp"
 
 namespace scene_detail {
+// procedural assets are written to a directory of this PROCESS: with one process per GPU all ranks build the
+// same scene at the same time, and a shared path had one rank reading a file another was still writing
+inline std::string scratch_dir() {
+  static const std::string dir = [] {
+    std::string p = "/tmp/ptb200_" + std::to_string((long)getpid());
+    mkdir(p.c_str(), 0700);
+    return p;
+  }();
+  return dir;
+}
 inline Group beginScene(App_State& app, Light_Sampler& lights) {
   setRayGenerationProgram(app.context, lights);
   setExceptionProgram(app.context);
@@ -324,7 +338,7 @@ inline void Test_Scene(App_State& app) {
   setMissProgram(app.context, GRADIENT, make_float3(1.f), make_float3(0.5f, 0.7f, 1.f));
   Group group = beginScene(app, lights);
   int n = app.model == 0 ? 708 : (app.model == 1 ? 2237 : app.model);
-  std::string obj = write_heightfield_obj("/tmp/ptb200_heightfield_" + std::to_string(n) + ".obj", n);
+  std::string obj = write_heightfield_obj(scene_detail::scratch_dir() + "/heightfield_" + std::to_string(n) + ".obj", n);
   BRDF* whiteMt = new Lambertian(new Constant_Texture(0.73f));
   Mesh model(obj, whiteMt, app.RTX);
   model.scale(make_float3(100.f));
@@ -469,8 +483,8 @@ inline void Textured_Mesh(App_State& app) {
   addRectLight(lights, app, -2.f, 2.f, -2.f, 2.f, 6.f, Y_AXIS, 6.f);
   setMissProgram(app.context, GRADIENT, make_float3(1.f), make_float3(0.5f, 0.7f, 1.f));
   Group group = beginScene(app, lights);
-  const std::string dir = "/tmp/";
-  Mesh model(write_textured_obj("/tmp", app.model > 0 ? app.model : 24), dir, app.RTX);  // no given material: MTL path
+  const std::string dir = scratch_dir() + "/";
+  Mesh model(write_textured_obj(scratch_dir(), app.model > 0 ? app.model : 24), dir, app.RTX);  // no given material: MTL path
   model.addTo(group, app.context);
   Hitable_List list;
   list.push(new AARect(-2.f, 2.f, -2.f, 2.f, 6.f, true, Y_AXIS, new Diffuse_Light(new Constant_Texture(6.f))));
@@ -484,11 +498,12 @@ inline void Mesh_HDRI(App_State& app) {
   using namespace scene_detail;
   auto t0 = std::chrono::system_clock::now();
   Light_Sampler lights;
-  setMissProgram(app.context, HDR, write_synthetic_hdri("/tmp/ptb200_sky.hdr"), true);
+  setMissProgram(app.context, HDR, write_synthetic_hdri(scene_detail::scratch_dir() + "/sky.hdr"), true);
   Group group = beginScene(app, lights);
   int n = app.model == 0 ? 708 : (app.model == 1 ? 2237 : app.model);
-  std::string obj = write_heightfield_obj("/tmp/ptb200_heightfield_" + std::to_string(n) + ".obj", n);
+  std::string obj = write_heightfield_obj(scene_detail::scratch_dir() + "/heightfield_" + std::to_string(n) + ".obj", n);
   Mesh model(obj, new Lambertian(new Constant_Texture(0.7f)), app.RTX);
   model.addTo(group, app.context);
+  std::remove(obj.c_str());  // loaded: a 1 M-triangle OBJ is 60 MB per process
   finishScene(app, group, make_float3(0.f, 4.5f, -9.f), make_float3(0.f), 40.f, 0.f, 10.f, t0);
 }
