@@ -506,6 +506,8 @@ int pt_scene_commit(pt_scene* s) {
   d.env_n = (int)s->env_alias_prob.size();
   d.env_w = d.env_n ? s->images[s->miss.image].width : 0;
   d.env_h = d.env_n ? s->images[s->miss.image].height : 0;
+  d.tex_need_uv = 0;
+  for (const pt_texture& t : s->textures) d.tex_need_uv |= t.type == PT_TEX_IMAGE;
   d.qbias = 0x47000000u;
   d.special_mask = (s->moving_spheres.empty() ? 0 : 1) | (s->volume_spheres.empty() && s->volume_boxes.empty() ? 0 : 2);
   d.n_prims = (int)s->prims.size();

@@ -776,7 +776,11 @@ int pt_render(pt_renderer* r, int32_t first_frame, int32_t nframes, int32_t max_
   const bool timing = (r->flags & 2) != 0;
   const int sms = sm_count();
   const bool special = sc.special_mask != 0;
-  const int g_trace = sms * trace_blocks_per_sm(special), g_shade = sms * 8, g_gen = sms * 4;
+  const int g_trace = sms * trace_blocks_per_sm(special), g_shade = sms * PT_SHADE_MINBLOCKS, g_gen = sms * 4;
+#ifndef PT_MISS_BLOCKS
+#define PT_MISS_BLOCKS 8
+#endif
+  const int g_miss = sms * PT_MISS_BLOCKS;
   const uint32_t mask = s->material_type_mask;
   const SchedParams sched = sched_params(sc);
   // shadow rays keep the BVH walk even in tiny scenes: they start on a surface and aim at a light, the one
@@ -832,7 +836,7 @@ int pt_render(pt_renderer* r, int32_t first_frame, int32_t nframes, int32_t max_
     LAUNCH_SHADE(PT_MAT_ASHIKHMIN_SHIRLEY, 0)
     LAUNCH_SHADE(PT_MAT_NORMAL, 0)
 #undef LAUNCH_SHADE
-    k_miss<<<g_shade, 128, 0, st>>>(sc, p, c, cur, bq);
+    k_miss<<<g_miss, 128, 0, st>>>(sc, p, c, cur, bq);
     if (timed) cudaEventRecord(e[3], st);
     n++;
     if (need_shadow) {

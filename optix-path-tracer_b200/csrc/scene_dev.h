@@ -58,6 +58,7 @@ struct SceneDev {
   const int* env_alias_idx;
   const float* env_texel_pdf;
   int env_n, env_w, env_h;
+  int tex_need_uv;   // some texture is an image: hit records must carry (u, v)
   uint32_t qbias;    // 0x47000000, deliberately a run-time value: see pt_byte_to_float (traverse.h)
   int special_mask;  // bit0: moving spheres present (rays carry prd.time), bit1: volumes present (rays carry a seed)
   int n_prims, n_materials, n_textures, n_texvec, n_texdata, n_images, n_lights;

@@ -552,6 +552,9 @@ PT_HD HitRec make_hit_record(const SceneDev& sc, float3 o, float3 d, float t, in
   }
   float3 hp = o + t * d;
   rec.P = o2w ? xf_point(o2w, hp) : hp;
+  // texture coordinates of analytic primitives cost an atan2f + asinf (sphere) or two IEEE divisions (rect) per
+  // hit and are read by image textures only: a scene without image textures skips them (same colours, exactly)
+  const bool need_uv = sc.tex_need_uv != 0;
   float3 n;
   rec.u = rec.v = 0.f;
   if (kind == PT_PRIM_VOLUME_SPHERE || kind == PT_PRIM_VOLUME_BOX) {
@@ -564,26 +567,33 @@ PT_HD HitRec make_hit_record(const SceneDev& sc, float3 o, float3 d, float t, in
     }
     float3 T = (hp - ctr) / L.b.x;
     n = T;
-    float phi = atan2f(T.z, T.x);
-    float theta = asinf(T.y);
-    rec.u = 1.f - (phi + PT_PI_F) / (2.f * PT_PI_F);
-    rec.v = (theta + PT_PI_F / 2.f) / PT_PI_F;
+    if (need_uv) {  // sphere.cu:85-90; only image textures read (u, v): skipped when the scene has none
+      float phi = atan2f(T.z, T.x);
+      float theta = asinf(T.y);
+      rec.u = 1.f - (phi + PT_PI_F) / (2.f * PT_PI_F);
+      rec.v = (theta + PT_PI_F / 2.f) / PT_PI_F;
+    }
   } else if (kind == PT_PRIM_RECT) {  // aarect.cu:71-115
     const float a0 = L.a.x, a1 = L.a.y, b0 = L.a.z, b1 = L.b.x;
     const uint32_t af = pt_f2u(L.b.z);
     const int axis = af & 3;
+    float pa, pb;
     if (axis == PT_X_AXIS) {
       n = f3(1.f, 0.f, 0.f);
-      rec.u = (hp.y - a0) / (a1 - a0);
-      rec.v = (hp.z - b0) / (b1 - b0);
+      pa = hp.y;
+      pb = hp.z;
     } else if (axis == PT_Y_AXIS) {
       n = f3(0.f, 1.f, 0.f);
-      rec.u = (hp.x - a0) / (a1 - a0);
-      rec.v = (hp.z - b0) / (b1 - b0);
+      pa = hp.x;
+      pb = hp.z;
     } else {
       n = f3(0.f, 0.f, 1.f);
-      rec.u = (hp.x - a0) / (a1 - a0);
-      rec.v = (hp.y - b0) / (b1 - b0);
+      pa = hp.x;
+      pb = hp.y;
+    }
+    if (need_uv) {
+      rec.u = (pa - a0) / (a1 - a0);
+      rec.v = (pb - b0) / (b1 - b0);
     }
     if (af & 4u) n = -n;
   } else {  // box.cu:24-33,56-81

@@ -187,6 +187,8 @@ Sim* sim_create(const pt_scene_desc* desc, int refine) {
   d.env_n = desc->env_n;
   d.env_w = desc->env_n ? desc->images[desc->miss.image].width : 0;
   d.env_h = desc->env_n ? desc->images[desc->miss.image].height : 0;
+  d.tex_need_uv = 0;
+  for (int i = 0; i < desc->n_textures; i++) d.tex_need_uv |= desc->textures[i].type == PT_TEX_IMAGE;
   d.qbias = 0x47000000u;
   d.special_mask = (desc->n_moving_spheres ? 1 : 0) | (desc->n_volume_spheres || desc->n_volume_boxes ? 2 : 0);
   d.n_prims = n;
