@@ -944,8 +944,32 @@ int pt_renderer_sync(pt_renderer* r) {
 
 int pt_read_accum(pt_renderer* r, float* host_rgba) {
   if (!r || !host_rgba) return PT_ERR_INVALID;
-  PT_CUDA(cudaMemcpyAsync(host_rgba, r->accum, (size_t)r->W * r->H * 16, cudaMemcpyDeviceToHost, r->stream));
+  const size_t bytes = (size_t)r->W * r->H * 16;
+  // The caller's buffer is usually pageable, and a pageable device-to-host copy is staged by the driver at
+  // ~2 GB/s (7.4 ms for the 15 MB of a 1200x800 image).  Copy into a pinned buffer of the renderer's own at
+  // link speed (0.35 ms) and memcpy from there; a caller that passes pinned memory gets the direct copy.
+  cudaPointerAttributes at{};
+  const bool caller_pinned = cudaPointerGetAttributes(&at, host_rgba) == cudaSuccess && at.type == cudaMemoryTypeHost;
+  cudaGetLastError();  // unregistered host pointers make cudaPointerGetAttributes report an error on old drivers
+  if (caller_pinned) {
+    PT_CUDA(cudaMemcpyAsync(host_rgba, r->accum, bytes, cudaMemcpyDeviceToHost, r->stream));
+    PT_CUDA(cudaStreamSynchronize(r->stream));
+    return PT_OK;
+  }
+  // one grow-only staging buffer per process (pinning 15 MB costs ~7 ms: not something to pay per renderer);
+  // the library is driven by one host thread, like the reference
+  static float* g_stage = nullptr;
+  static size_t g_stage_bytes = 0;
+  if (g_stage_bytes < bytes) {
+    if (g_stage) cudaFreeHost(g_stage);
+    g_stage = nullptr;
+    g_stage_bytes = 0;
+    PT_CUDA(cudaMallocHost((void**)&g_stage, bytes));
+    g_stage_bytes = bytes;
+  }
+  PT_CUDA(cudaMemcpyAsync(g_stage, r->accum, bytes, cudaMemcpyDeviceToHost, r->stream));
   PT_CUDA(cudaStreamSynchronize(r->stream));
+  memcpy(host_rgba, g_stage, bytes);
   return PT_OK;
 }
 
