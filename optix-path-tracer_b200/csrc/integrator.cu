@@ -602,6 +602,14 @@ struct pt_renderer {
   Ctrl* h_ctrl = nullptr;  // pinned
 };
 
+// Process-level caches (the library is driven by one host thread, like the reference).
+//  * the path-pool slab of a destroyed renderer is parked here and handed to the next one: creating a
+//    renderer per job otherwise frees and re-allocates 2-3 GB each time, and the stream-ordered allocator
+//    answered that churn with re-mapping stalls of 100-700 ms (seen as e2e C4 1346 -> 1053 Msamples/s);
+//  * one pinned control-block mirror for all renderers (pinning / unpinning synchronises the device).
+static DevBuf g_slab_cache;
+static Ctrl* g_hctrl = nullptr;
+
 static int ensure_pool(pt_renderer* r, long long want) {
   long long npix = (long long)r->W * r->H;
   long long pool = r->pool_req > 0 ? r->pool_req : (1ll << 22);
@@ -615,7 +623,12 @@ static int ensure_pool(pt_renderer* r, long long want) {
   const size_t gap = 64 * 1024;
   const int n_arr = 4 + 4 + NSHADOW + NBINS;
   const size_t total = (arr + gap + 7 * skew + 256) * n_arr + (size_t)pool * 4 * NBINS + 64 * 1024;
-  PT_CUDA(r->slab.alloc(total));
+  if (g_slab_cache.p && g_slab_cache.bytes >= total && !r->slab.p) {
+    std::swap(r->slab.p, g_slab_cache.p);
+    std::swap(r->slab.bytes, g_slab_cache.bytes);
+  } else {
+    PT_CUDA(r->slab.alloc(total));
+  }
   char* base = r->slab.as<char>();
   size_t off = 0;
   int k = 0;
@@ -679,21 +692,28 @@ int pt_renderer_create(pt_scene* scene, int32_t width, int32_t height, void* d_a
   if (cudaMemset(r->accum, 0, (size_t)width * height * 16) != cudaSuccess ||
       r->ctrl.alloc(sizeof(Ctrl)) != cudaSuccess || cudaStreamCreate(&r->stream) != cudaSuccess ||
       cudaEventCreate(&r->ev0) != cudaSuccess || cudaEventCreate(&r->ev1) != cudaSuccess ||
-      cudaMallocHost((void**)&r->h_ctrl, sizeof(Ctrl)) != cudaSuccess) {
+      (!g_hctrl && cudaMallocHost((void**)&g_hctrl, sizeof(Ctrl)) != cudaSuccess)) {
     pt_set_error("renderer setup failed: %s", cudaGetErrorString(cudaGetLastError()));
     delete r;
     return PT_ERR_CUDA;
   }
+  r->h_ctrl = g_hctrl;  // only read inside pt_render, which is synchronous
   *out = r;
   return PT_OK;
 }
 
 int pt_renderer_destroy(pt_renderer* r) {
   if (!r) return PT_OK;
-  if (r->stream) cudaStreamDestroy(r->stream);
+  if (r->stream) {
+    cudaStreamSynchronize(r->stream);
+    cudaStreamDestroy(r->stream);
+  }
   if (r->ev0) cudaEventDestroy(r->ev0);
   if (r->ev1) cudaEventDestroy(r->ev1);
-  if (r->h_ctrl) cudaFreeHost(r->h_ctrl);
+  if (r->slab.p && r->slab.bytes > g_slab_cache.bytes) {  // park the larger slab, free the smaller
+    std::swap(r->slab.p, g_slab_cache.p);
+    std::swap(r->slab.bytes, g_slab_cache.bytes);
+  }
   for (auto& g : r->gexec)
     if (g) cudaGraphExecDestroy(g);
   delete r;
