@@ -20,6 +20,7 @@
 #include "materials/torrance_sparrow.cuh"
 #include "materials/ashikhmin_shirley.cuh"
 #include "materials/diffuse_light.cuh"
+#include "materials/isotropic.cuh"
 
 static float3 ld(const float* p) { return make_float3(p[0], p[1], p[2]); }
 static void st(float* p, const float3& v) { p[0] = v.x; p[1] = v.y; p[2] = v.z; }
@@ -48,6 +49,7 @@ void ref_bsdf_sample(int mat, const float* color, const float* color2, float p0,
     case 5: { Torrance_Sparrow_Parameters s; s.color = ld(color); s.nu = p0; s.nv = p1; wi = Sample(s, ld(P), ld(Wo), ld(N), *seed); break; }
     case 6: { Ashikhmin_Shirley_Parameters s; s.diffuse_color = ld(color); s.specular_color = ld(color2); s.nu = p0; s.nv = p1; wi = Sample(s, ld(P), ld(Wo), ld(N), *seed); break; }
     case 3: { Diffuse_Light_Parameters s; s.color = ld(color); wi = Sample(s, ld(P), ld(Wo), ld(N), *seed); break; }
+    case 8: { Isotropic_Parameters s; s.color = ld(color); wi = Sample(s, ld(P), ld(Wo), ld(N), *seed); break; }
   }
   st(out, wi);
 }
@@ -62,6 +64,7 @@ void ref_bsdf_eval(int mat, const float* color, const float* color2, float p0, f
     case 5: { Torrance_Sparrow_Parameters s; s.color = ld(color); s.nu = p0; s.nv = p1; v = Evaluate(s, ld(P), ld(Wo), ld(Wi), ld(N), pd); break; }
     case 6: { Ashikhmin_Shirley_Parameters s; s.diffuse_color = ld(color); s.specular_color = ld(color2); s.nu = p0; s.nv = p1; v = Evaluate(s, ld(P), ld(Wo), ld(Wi), ld(N), pd); break; }
     case 3: { Diffuse_Light_Parameters s; s.color = ld(color); v = Evaluate(s, ld(P), ld(Wo), ld(Wi), ld(N), pd); break; }
+    case 8: { Isotropic_Parameters s; s.color = ld(color); v = Evaluate(s, ld(P), ld(Wo), ld(Wi), ld(N), pd); break; }
   }
   st(f, v);
   *pdf = pd;

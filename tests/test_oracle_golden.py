@@ -73,8 +73,13 @@ def test_bsdf_eval_golden(orc, gold):
 def test_bsdf_sample_golden(orc, gold):
     l2r = gold["arg_order_l2r"]
     for c in gold["bsdf_sample"]:
-        if c["mat"] == pt.MAT_DIFFUSE_LIGHT:
-            continue  # covered by sampling golden (random_on_unit_sphere)
+        if c["mat"] in (pt.MAT_DIFFUSE_LIGHT, pt.MAT_ISOTROPIC):
+            # diffuse_light.cuh / isotropic.cuh: Sample = random_on_unit_sphere(seed), three draws
+            s = C.c_uint32(c["seed"])
+            wi = F3()
+            orc.orc_random_on_unit_sphere(C.byref(s), wi)
+            assert b(list(wi)) == c["Wi"] and s.value == c["seed_after"], c
+            continue
         p = f(c["p"])
         s = C.c_uint32(c["seed"])
         d1 = orc.orc_rnd(C.byref(s))
