@@ -1925,5 +1925,36 @@ int orc_intersect_prim(const orc_scene* s, int prim, const pt_ray* ray, float* t
   Ray r = {ld3(ray->origin), ld3(ray->dir), ray->tmin, ray->tmax};
   return intersect_prim(*s, prim, r, *t, *u, *v) ? 1 : 0;
 }
+// the same with the per-ray data moving spheres (time) and volumes (seed) read, plus the hit record
+// (P, geometric normal, shading normal, u, v, Wo) and the UNPADDED-by-the-BVH reference bounds check
+int orc_intersect_prim_ex(const orc_scene* s, int prim, const pt_ray* ray, float time, uint32_t seed,
+                          float* hit3, float* rec14) {
+  Ray r = {ld3(ray->origin), ld3(ray->dir), ray->tmin, ray->tmax, time, seed};
+  float t, u, v;
+  if (!intersect_prim(*s, prim, r, t, u, v)) return 0;
+  hit3[0] = t;
+  hit3[1] = u;
+  hit3[2] = v;
+  Hit h = {t, prim, u, v};
+  HitRecord rec = get_hit_record(*s, r, h);
+  st3(rec14, rec.P);
+  st3(rec14 + 3, rec.geometric_normal);
+  st3(rec14 + 6, rec.shading_normal);
+  rec14[9] = rec.u;
+  rec14[10] = rec.v;
+  st3(rec14 + 11, rec.Wo);
+  return 1;
+}
+void orc_prim_bounds(const orc_scene* s, int prim, float* lo_hi6) {
+  Box3 b = prim_bounds(*s, prim);
+  st3(lo_hi6, b.lo);
+  st3(lo_hi6 + 3, b.hi);
+}
+// light sampling / pdf for either light kind; the sample consumes its draws from *seed
+void orc_light_sample(const pt_light* l, const float* P, uint32_t* seed, float* Wi_out) {
+  st3(Wi_out, Light_Sample(*l, ld3(P), *seed));
+}
+float orc_light_pdf(const pt_light* l, const float* P, const float* Wi) { return Light_PDF(*l, ld3(P), ld3(Wi)); }
+uint32_t orc_volume_seed(uint32_t ray_seed, uint32_t prim) { return tea<4>(ray_seed, prim); }
 
 }  // extern "C"

@@ -98,6 +98,14 @@ void orc_rect_sample(const pt_light* l, const float* P, float u1, float u2, floa
 float orc_rect_pdf(const pt_light* l, const float* P, const float* Wi);
 /* single primitive intersection: returns 1 and *t when hit in (tmin,tmax) */
 int orc_intersect_prim(const orc_scene* s, int prim, const pt_ray* ray, float* t, float* u, float* v);
+/* ... with prd.time / ray seed, returning hit3 = (t, u, v) and the hit record
+ * rec14 = P, geometric normal, shading normal, u, v, Wo (compared with the reference's own .cu programs) */
+int orc_intersect_prim_ex(const orc_scene* s, int prim, const pt_ray* ray, float time, uint32_t seed,
+                          float* hit3, float* rec14);
+void orc_prim_bounds(const orc_scene* s, int prim, float* lo_hi6);
+void orc_light_sample(const pt_light* l, const float* P, uint32_t* seed, float* Wi_out);
+float orc_light_pdf(const pt_light* l, const float* P, const float* Wi);
+uint32_t orc_volume_seed(uint32_t ray_seed, uint32_t prim); /* tea<4>: the pinned volume uniform's seed */
 
 #ifdef __cplusplus
 }

@@ -102,6 +102,13 @@ def oracle():
     o.orc_rect_pdf.restype = fl
     o.orc_rect_pdf.argtypes = [P(pt.Light), F3, F3]
     o.orc_intersect_prim.argtypes = [vp, C.c_int, P(pt.Ray), P(fl), P(fl), P(fl)]
+    o.orc_intersect_prim_ex.argtypes = [vp, C.c_int, P(pt.Ray), fl, C.c_uint32, vp, vp]
+    o.orc_prim_bounds.argtypes = [vp, C.c_int, vp]
+    o.orc_light_sample.argtypes = [P(pt.Light), F3, P(C.c_uint32), F3]
+    o.orc_light_pdf.restype = fl
+    o.orc_light_pdf.argtypes = [P(pt.Light), F3, F3]
+    o.orc_volume_seed.restype = C.c_uint32
+    o.orc_volume_seed.argtypes = [C.c_uint32, C.c_uint32]
     for n in ("orc_random_in_unit_disk", "orc_random_in_unit_sphere", "orc_random_on_unit_sphere"):
         getattr(o, n).argtypes = [P(C.c_uint32), F3]
     _oracle = o
@@ -178,6 +185,27 @@ def ref_probe():
     r.ref_ggx_g.argtypes = [F3, F3, fl, fl]
     for n in ("ref_random_in_unit_disk", "ref_random_in_unit_sphere", "ref_random_on_unit_sphere"):
         getattr(r, n).argtypes = [P(C.c_uint32), F3]
+    return r
+
+
+def ref_cu_probe():
+    """The reference's hitables/*.cu and pdfs/*.cu compiled unmodified as host code
+    (oracle/_ref/libref_cu.so, oracle/ref_cu_probe.cpp) or None."""
+    so = os.path.join(ORACLE_DIR, "_ref", "libref_cu.so")
+    if not os.path.exists(so) and os.path.isdir("/root/reference/OptiX-Path-Tracer/programs"):
+        _run(["make", "ref"], ORACLE_DIR)
+    if not os.path.exists(so):
+        return None
+    r = C.CDLL(so)
+    vp, fl = C.c_void_p, C.c_float
+    for kind in ("sphere", "rect", "box", "triangle", "moving_sphere", "volume_sphere", "volume_box"):
+        getattr(r, "refcu_" + kind).argtypes = [vp, vp, fl, C.c_uint32, vp, vp, vp]
+    r.refcu_rect_pdf.restype = fl
+    r.refcu_rect_pdf.argtypes = [vp, C.c_int, pt.F3, pt.F3]
+    r.refcu_rect_sample.argtypes = [vp, C.c_int, pt.F3, C.POINTER(C.c_uint32), pt.F3]
+    r.refcu_spherelight_pdf.restype = fl
+    r.refcu_spherelight_pdf.argtypes = [vp, pt.F3, pt.F3]
+    r.refcu_spherelight_sample.argtypes = [vp, pt.F3, C.POINTER(C.c_uint32), pt.F3]
     return r
 
 
