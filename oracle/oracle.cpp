@@ -47,6 +47,22 @@
 #include <cstring>
 #include <vector>
 
+// Two uniforms drawn inside ONE argument list (cosine_sample_hemisphere(rnd(seed), rnd(seed), ..),
+// make_float3(k, a0 + rnd(seed) * .., b0 + rnd(seed) * ..)): device code evaluates left to right - the
+// pinned order.  -DORC_ARGS_R2L builds the variant in which they are taken right to left, which is what g++
+// does: oracle/_ref/libref_mat.so is the reference's closest-hit programs compiled by g++, and
+// liboracle_r2l.so is what must reproduce THEM bit for bit (tests/test_oracle_mat_golden.py).  The two oracle
+// builds differ in nothing else.
+#ifdef ORC_ARGS_R2L
+#define ORC_DRAW2(seed, a, b) \
+  float b = rnd(seed);        \
+  float a = rnd(seed)
+#else
+#define ORC_DRAW2(seed, a, b) \
+  float a = rnd(seed);        \
+  float b = rnd(seed)
+#endif
+
 namespace {
 
 // ---------------------------------------------------------------------------
@@ -398,15 +414,15 @@ inline f3 Sample(const Surface& s, f3 /*P*/, f3 Wo, f3 N, uint32_t& seed) {
   switch (s.type) {
     case PT_MAT_LAMBERTIAN:
     case PT_MAT_OREN_NAYAR: {
-      float u1 = rnd(seed), u2 = rnd(seed);
+      ORC_DRAW2(seed, u1, u2);
       return Sample_cosine(N, u1, u2);
     }
     case PT_MAT_TORRANCE_SPARROW: {
-      float u1 = rnd(seed), u2 = rnd(seed);
+      ORC_DRAW2(seed, u1, u2);
       return Sample_TS(s, Wo, N, u1, u2);
     }
     case PT_MAT_ASHIKHMIN_SHIRLEY: {
-      float u1 = rnd(seed), u2 = rnd(seed);
+      ORC_DRAW2(seed, u1, u2);
       return Sample_AS(s, Wo, N, u1, u2);
     }
     case PT_MAT_DIFFUSE_LIGHT:  // P/materials/diffuse_light.cuh:7-13
@@ -617,8 +633,7 @@ inline float SphereL_PDF(const pt_light& l, f3 P, f3 Wi) {
 }
 inline f3 Light_Sample(const pt_light& l, f3 P, uint32_t& seed) {
   if (l.type == PT_LIGHT_SPHERE) return SphereL_Sample(l, P, seed);
-  float ua = rnd(seed);
-  float ub = rnd(seed);
+  ORC_DRAW2(seed, ua, ub);
   return Rect_Sample(l, P, ua, ub);
 }
 inline float Light_PDF(const pt_light& l, f3 P, f3 Wi) {
@@ -1338,6 +1353,9 @@ struct PerRayData {  // P/prd.cuh:45-57
 };
 struct Counters {
   uint64_t closest = 0, shadow = 0, bounces = 0, nodes = 0, prims = 0;
+  // probe support (orc_closest_hit_probe): the last shadow ray Direct_Light traced and its outcome
+  int shadow_traced = 0, shadow_blocked = 0;
+  float shadow_ray[6] = {0, 0, 0, 0, 0, 0};
 };
 
 f3 miss_color(const orc_scene& s, f3 d);
@@ -1366,6 +1384,10 @@ f3 Direct_Light(const orc_scene& s, const Surface& surface, f3 P, f3 Wo, f3 N, b
     const pt_material& m = s.d.materials[s.d.prims[h.prim].material];
     if (m.type == PT_MAT_DIFFUSE_LIGHT && dot(N, Wi) > 0.f) inShadow = false;
   }
+  cn.shadow_traced++;
+  cn.shadow_blocked = inShadow ? 1 : 0;
+  st3(cn.shadow_ray, P);
+  st3(cn.shadow_ray + 3, Wi);
   if (inShadow) return mk(0.f);
   if (lightPDF != 0.f && !isNull(emission)) {
     float matPDF = 0.f;
@@ -1944,6 +1966,37 @@ int orc_intersect_prim_ex(const orc_scene* s, int prim, const pt_ray* ray, float
   rec14[10] = rec.v;
   st3(rec14 + 11, rec.Wo);
   return 1;
+}
+// One closest-hit program invocation (P/materials/*.cu closest_hit) on the hit (prim, t, u, v) of `ray`.
+// prd_io: seed (bit pattern), time, throughput.xyz, radiance.xyz on entry; on return seed, time, throughput,
+// radiance, origin.xyz, direction.xyz, scatterEvent, isSpecular (16 floats).  shadow4: number of shadow rays
+// traced, then the last one's origin.xyz direction.xyz and whether it was blocked (8 floats).
+void orc_closest_hit_probe(const orc_scene* s, const pt_ray* ray, int prim, float t, float u, float v,
+                           float* prd_io, float* shadow8) {
+  PerRayData prd;
+  memcpy(&prd.seed, prd_io, 4);
+  prd.time = prd_io[1];
+  prd.throughput = ld3(prd_io + 2);
+  prd.radiance = ld3(prd_io + 5);
+  prd.origin = prd.direction = mk(0.f);
+  prd.scatterEvent = rayGotBounced;
+  prd.isSpecular = false;
+  prd.last_pdf = 0.f;
+  Ray r = {ld3(ray->origin), ld3(ray->dir), ray->tmin, ray->tmax, prd.time, prd.seed};
+  Hit h = {t, prim, u, v};
+  Counters cn;
+  closest_hit_program(*s, r, h, prd, cn);
+  memcpy(prd_io, &prd.seed, 4);
+  prd_io[1] = prd.time;
+  st3(prd_io + 2, prd.throughput);
+  st3(prd_io + 5, prd.radiance);
+  st3(prd_io + 8, prd.origin);
+  st3(prd_io + 11, prd.direction);
+  prd_io[14] = (float)(int)prd.scatterEvent;
+  prd_io[15] = prd.isSpecular ? 1.f : 0.f;
+  shadow8[0] = (float)cn.shadow_traced;
+  memcpy(shadow8 + 1, cn.shadow_ray, 24);
+  shadow8[7] = (float)cn.shadow_blocked;
 }
 void orc_prim_bounds(const orc_scene* s, int prim, float* lo_hi6) {
   Box3 b = prim_bounds(*s, prim);

@@ -102,6 +102,9 @@ int orc_intersect_prim(const orc_scene* s, int prim, const pt_ray* ray, float* t
  * rec14 = P, geometric normal, shading normal, u, v, Wo (compared with the reference's own .cu programs) */
 int orc_intersect_prim_ex(const orc_scene* s, int prim, const pt_ray* ray, float time, uint32_t seed,
                           float* hit3, float* rec14);
+/* one closest-hit program invocation (programs/materials/<x>.cu closest_hit); see oracle.cpp for the layout */
+void orc_closest_hit_probe(const orc_scene* s, const pt_ray* ray, int prim, float t, float u, float v,
+                           float* prd_io16, float* shadow8);
 void orc_prim_bounds(const orc_scene* s, int prim, float* lo_hi6);
 void orc_light_sample(const pt_light* l, const float* P, uint32_t* seed, float* Wi_out);
 float orc_light_pdf(const pt_light* l, const float* P, const float* Wi);

@@ -29,12 +29,13 @@ using namespace optix;
 #define rtDeclareVariable(type, name, semantic, annotation) static type name
 
 template <class T, int N = 1>
-struct rtBuffer {
+struct shim_buffer {
   std::vector<T> v;
   T& operator[](size_t i) { return v[i]; }
   const T& operator[](size_t i) const { return v[i]; }
   size_t size() const { return v.size(); }
 };
+#define rtBuffer static shim_buffer  // `rtBuffer<float3> Light_Emissions;` -> a buffer private to this translation unit
 
 enum RTtransformkind { RT_WORLD_TO_OBJECT = 0, RT_OBJECT_TO_WORLD = 1 };
 static inline float3 rtTransformPoint(RTtransformkind, const float3& p) { return p; }
@@ -76,3 +77,37 @@ static inline bool rtReportIntersection(unsigned) {
 }
 static inline int rtGetPrimitiveIndex() { return 0; }
 static inline float2 rtGetTriangleBarycentrics() { return make_float2(0.f); }
+
+// ---- closest-hit programs (programs/materials/*.cu) ------------------------------------------------
+//   rtCallableProgramId<R(A...)> / rtCallableProgramX<R(A...)>  -> std::function the probe fills in
+//   rtTrace(world, shadowRay, prdShadow)                         -> records the ray and answers with the
+//        visibility the probe was GIVEN (the shadow test itself is the oracle's pinned rule; what is
+//        compared is everything the program does before and after it)
+#include <functional>
+template <class R, class... A>
+struct rtCallableProgramId<R(A...)> {
+  std::function<R(A...)> f;
+  R operator()(A... a) const { return f(a...); }
+};
+template <class R, class... A>
+struct rtCallableProgramX<R(A...)> {
+  std::function<R(A...)> f;
+  R operator()(A... a) const { return f(a...); }
+};
+typedef int rtObject;
+struct ShimShadow {
+  int answer_in_shadow;  // set by the probe's caller
+  int traced;
+  Ray ray;
+};
+static ShimShadow g_shadow;
+template <class PRD>
+static inline void shim_trace(const Ray& r, PRD& prd) {
+  g_shadow.traced++;
+  g_shadow.ray = r;
+  prd.inShadow = g_shadow.answer_in_shadow != 0;
+}
+// a macro, so that the `world` argument never reaches the compiler: light_sample.cuh's Direct_Light template
+// names it before any .cu declares it (accepted by nvcc, rejected by g++'s two-phase lookup)
+#define rtTrace(world_, ray_, prd_) shim_trace(ray_, prd_)
+static inline void rtTerminateRay() {}

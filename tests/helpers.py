@@ -59,17 +59,18 @@ class OrcStats(C.Structure):
                 ("seconds", C.c_double), ("threads", C.c_int32)]
 
 
-_oracle = None
+_oracles = {}
 
 
-def oracle():
-    global _oracle
-    if _oracle is not None:
-        return _oracle
-    so = os.path.join(ORACLE_DIR, "liboracle.so")
+def oracle(variant=""):
+    """liboracle.so, or (variant="_r2l") the build whose two-draws-in-one-argument-list are taken right to left
+    like g++ does with the reference's source (only for replaying vectors recorded from that build)."""
+    if variant in _oracles:
+        return _oracles[variant]
+    so = os.path.join(ORACLE_DIR, f"liboracle{variant}.so")
     src_m = max(os.path.getmtime(os.path.join(ORACLE_DIR, f)) for f in ("oracle.cpp", "oracle.h"))
     if not os.path.exists(so) or os.path.getmtime(so) < src_m:
-        _run(["make", "liboracle.so"], ORACLE_DIR)
+        _run(["make", f"liboracle{variant}.so"], ORACLE_DIR)
     o = C.CDLL(so)
     vp, P = C.c_void_p, C.POINTER
     o.orc_scene_create.restype = vp
@@ -103,6 +104,7 @@ def oracle():
     o.orc_rect_pdf.argtypes = [P(pt.Light), F3, F3]
     o.orc_intersect_prim.argtypes = [vp, C.c_int, P(pt.Ray), P(fl), P(fl), P(fl)]
     o.orc_intersect_prim_ex.argtypes = [vp, C.c_int, P(pt.Ray), fl, C.c_uint32, vp, vp]
+    o.orc_closest_hit_probe.argtypes = [vp, P(pt.Ray), C.c_int, fl, fl, fl, vp, vp]
     o.orc_prim_bounds.argtypes = [vp, C.c_int, vp]
     o.orc_light_sample.argtypes = [P(pt.Light), F3, P(C.c_uint32), F3]
     o.orc_light_pdf.restype = fl
@@ -111,15 +113,15 @@ def oracle():
     o.orc_volume_seed.argtypes = [C.c_uint32, C.c_uint32]
     for n in ("orc_random_in_unit_disk", "orc_random_in_unit_sphere", "orc_random_on_unit_sphere"):
         getattr(o, n).argtypes = [P(C.c_uint32), F3]
-    _oracle = o
+    _oracles[variant] = o
     return o
 
 
 class OracleScene:
     """orc_scene over a pt.Scene's flat description (keeps the Scene alive)."""
 
-    def __init__(self, scene, mode: int = 0):
-        self.o = oracle()
+    def __init__(self, scene, mode: int = 0, variant: str = ""):
+        self.o = oracle(variant)
         self.scene = scene
         self.desc = scene.desc()
         self.h = self.o.orc_scene_create(C.byref(self.desc), mode)
@@ -186,6 +188,25 @@ def ref_probe():
     for n in ("ref_random_in_unit_disk", "ref_random_in_unit_sphere", "ref_random_on_unit_sphere"):
         getattr(r, n).argtypes = [P(C.c_uint32), F3]
     return r
+
+
+def ref_mat_probe():
+    """The reference's materials/*.cu closest-hit programs (with light_sample.cuh) compiled unmodified as host
+    code (oracle/_ref/libref_mat.so, oracle/ref_mat_probe.cpp) or None."""
+    so = os.path.join(ORACLE_DIR, "_ref", "libref_mat.so")
+    if not os.path.exists(so) and os.path.isdir("/root/reference/OptiX-Path-Tracer/programs"):
+        _run(["make", "ref"], ORACLE_DIR)
+    if not os.path.exists(so):
+        return None
+    r = C.CDLL(so)
+    vp = C.c_void_p
+    for name in MAT_PROGRAMS.values():
+        getattr(r, "refmat_" + name).argtypes = [vp, vp, C.c_float, vp, vp, vp, C.c_int, vp, vp]
+    return r
+
+
+MAT_PROGRAMS = {0: "lambertian", 1: "metal", 2: "dielectric", 3: "diffuse_light", 4: "oren_nayar",
+                5: "torrance_sparrow", 6: "ashikhmin_shirley", 7: "normal_shader", 8: "isotropic"}
 
 
 def ref_cu_probe():
