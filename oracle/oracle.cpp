@@ -1566,6 +1566,29 @@ void closest_hit_program(const orc_scene& s, const Ray& ray, const Hit& h, PerRa
   }
 }
 
+// texture coordinates of the image backgrounds — P/miss.cu:51-55 (image_background), :64-91 (environmental_mapping)
+inline void miss_uv(const pt_miss& ms, f3 d, float& u, float& v) {
+  if (ms.type == PT_MISS_IMG) {
+    float theta = atan2f(d.x, d.z);
+    float phi = OPTIX_PIf * 0.5f - acosf(d.y);
+    u = (theta + OPTIX_PIf) * (0.5f * OPTIX_1_PIf);
+    v = 0.5f * (1.f + sinf(phi));
+  } else if (ms.spherical) {
+    float r = length(d);
+    float lon = atan2f(d.z, d.x);
+    float lat = acosf(d.y / r);
+    float rx = 1.f / (PI_F * 2.f), ry = 1.f / PI_F;
+    u = lon * rx;
+    v = lat * ry;
+  } else {
+    float theta = atan2f(d.x, d.z);
+    theta = theta < 0.f ? theta + (2.f * PI_F) : theta;
+    float phi = acosf(d.y);
+    u = 1.f - (theta / (2.f * PI_F));
+    v = phi / PI_F;
+  }
+}
+
 // miss programs — P/miss.cu:30-95: background radiance factor for direction d
 f3 miss_color(const orc_scene& s, f3 d) {
   const pt_miss& ms = s.d.miss;
@@ -1580,28 +1603,13 @@ f3 miss_color(const orc_scene& s, f3 d) {
     case PT_MISS_CONSTANT:
       return ld3(ms.color1);
     case PT_MISS_IMG: {
-      float theta = atan2f(d.x, d.z);
-      float phi = OPTIX_PIf * 0.5f - acosf(d.y);
-      float u = (theta + OPTIX_PIf) * (0.5f * OPTIX_1_PIf);
-      float v = 0.5f * (1.f + sinf(phi));
+      float u, v;
+      miss_uv(ms, d, u, v);
       return (ms.image >= 0 && ms.image < s.d.n_images) ? image_lookup(s.d.images[ms.image], u, v) : mk(0.f);
     }
     default: {  // HDR environmental_mapping
       float u, v;
-      if (ms.spherical) {
-        float r = length(d);
-        float lon = atan2f(d.z, d.x);
-        float lat = acosf(d.y / r);
-        float rx = 1.f / (PI_F * 2.f), ry = 1.f / PI_F;
-        u = lon * rx;
-        v = lat * ry;
-      } else {
-        float theta = atan2f(d.x, d.z);
-        theta = theta < 0.f ? theta + (2.f * PI_F) : theta;
-        float phi = acosf(d.y);
-        u = 1.f - (theta / (2.f * PI_F));
-        v = phi / PI_F;
-      }
+      miss_uv(ms, d, u, v);
       f3 c = (ms.image >= 0 && ms.image < s.d.n_images) ? image_lookup(s.d.images[ms.image], u, v) : mk(0.f);
       return 2.f * c;
     }
@@ -1997,6 +2005,44 @@ void orc_closest_hit_probe(const orc_scene* s, const pt_ray* ray, int prim, floa
   shadow8[0] = (float)cn.shadow_traced;
   memcpy(shadow8 + 1, cn.shadow_ray, 24);
   shadow8[7] = (float)cn.shadow_blocked;
+}
+// One rtTrace of a radiance ray as OptiX performs it: closest hit -> that material's closest-hit program, or
+// the miss program (P/raygen.cu:77).  prd16 as in orc_closest_hit_probe.  The reference's own color() loop
+// (compiled from raygen.cu, oracle/ref_ray_probe.cpp) is driven through this entry point.
+void orc_trace_radiance(const orc_scene* s, const float* ray8, float* prd16) {
+  PerRayData prd;
+  memcpy(&prd.seed, prd16, 4);
+  prd.time = prd16[1];
+  prd.throughput = ld3(prd16 + 2);
+  prd.radiance = ld3(prd16 + 5);
+  prd.origin = ld3(prd16 + 8);
+  prd.direction = ld3(prd16 + 11);
+  prd.scatterEvent = (ScatterEvent)(int)prd16[14];
+  prd.isSpecular = prd16[15] != 0.f;
+  prd.last_pdf = 0.f;
+  Ray r = {ld3(ray8), ld3(ray8 + 4), ray8[3], ray8[7], prd.time, prd.seed};
+  Counters cn;
+  Hit h = closest_hit(*s, r, &cn.nodes, &cn.prims);
+  if (h.prim >= 0) closest_hit_program(*s, r, h, prd, cn);
+  else miss_program(*s, r, prd);
+  memcpy(prd16, &prd.seed, 4);
+  prd16[1] = prd.time;
+  st3(prd16 + 2, prd.throughput);
+  st3(prd16 + 5, prd.radiance);
+  st3(prd16 + 8, prd.origin);
+  st3(prd16 + 11, prd.direction);
+  prd16[14] = (float)(int)prd.scatterEvent;
+  prd16[15] = prd.isSpecular ? 1.f : 0.f;
+}
+// miss program on a throughput; also the (u, v) an image background samples at
+void orc_miss_probe(const orc_scene* s, const float* dir, const float* thr_in, float* thr_out, float* uv2) {
+  PerRayData prd;
+  prd.throughput = ld3(thr_in);
+  Ray r = {mk(0.f), ld3(dir), 1e-3f, RT_DEFAULT_MAX};
+  miss_program(*s, r, prd);
+  st3(thr_out, prd.throughput);
+  uv2[0] = uv2[1] = 0.f;
+  if (s->d.miss.type == PT_MISS_IMG || s->d.miss.type == PT_MISS_HDR) miss_uv(s->d.miss, ld3(dir), uv2[0], uv2[1]);
 }
 void orc_prim_bounds(const orc_scene* s, int prim, float* lo_hi6) {
   Box3 b = prim_bounds(*s, prim);

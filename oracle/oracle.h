@@ -105,6 +105,9 @@ int orc_intersect_prim_ex(const orc_scene* s, int prim, const pt_ray* ray, float
 /* one closest-hit program invocation (programs/materials/<x>.cu closest_hit); see oracle.cpp for the layout */
 void orc_closest_hit_probe(const orc_scene* s, const pt_ray* ray, int prim, float t, float u, float v,
                            float* prd_io16, float* shadow8);
+/* one rtTrace of a radiance ray (closest hit + its closest-hit program, or the miss program) on a payload */
+void orc_trace_radiance(const orc_scene* s, const float* ray8, float* prd16);
+void orc_miss_probe(const orc_scene* s, const float* dir, const float* thr_in, float* thr_out, float* uv2);
 void orc_prim_bounds(const orc_scene* s, int prim, float* lo_hi6);
 void orc_light_sample(const pt_light* l, const float* P, uint32_t* seed, float* Wi_out);
 float orc_light_pdf(const pt_light* l, const float* P, const float* Wi);

@@ -31,8 +31,10 @@ using namespace optix;
 template <class T, int N = 1>
 struct shim_buffer {
   std::vector<T> v;
+  int w = 0;  // row length of a 2-D buffer
   T& operator[](size_t i) { return v[i]; }
   const T& operator[](size_t i) const { return v[i]; }
+  T& operator[](const uint2& i) { return v[(size_t)i.y * w + i.x]; }
   size_t size() const { return v.size(); }
 };
 #define rtBuffer static shim_buffer  // `rtBuffer<float3> Light_Emissions;` -> a buffer private to this translation unit

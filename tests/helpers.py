@@ -105,6 +105,8 @@ def oracle(variant=""):
     o.orc_intersect_prim.argtypes = [vp, C.c_int, P(pt.Ray), P(fl), P(fl), P(fl)]
     o.orc_intersect_prim_ex.argtypes = [vp, C.c_int, P(pt.Ray), fl, C.c_uint32, vp, vp]
     o.orc_closest_hit_probe.argtypes = [vp, P(pt.Ray), C.c_int, fl, fl, fl, vp, vp]
+    o.orc_trace_radiance.argtypes = [vp, vp, vp]
+    o.orc_miss_probe.argtypes = [vp, F3, F3, F3, vp]
     o.orc_prim_bounds.argtypes = [vp, C.c_int, vp]
     o.orc_light_sample.argtypes = [P(pt.Light), F3, P(C.c_uint32), F3]
     o.orc_light_pdf.restype = fl
@@ -187,6 +189,24 @@ def ref_probe():
     r.ref_ggx_g.argtypes = [F3, F3, fl, fl]
     for n in ("ref_random_in_unit_disk", "ref_random_in_unit_sphere", "ref_random_on_unit_sphere"):
         getattr(r, n).argtypes = [P(C.c_uint32), F3]
+    return r
+
+
+RADIANCE_HOOK = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p)
+
+
+def ref_ray_probe():
+    """The reference's raygen.cu and miss.cu compiled unmodified as host code (oracle/_ref/libref_ray.so,
+    oracle/ref_ray_probe.cpp) or None."""
+    so = os.path.join(ORACLE_DIR, "_ref", "libref_ray.so")
+    if not os.path.exists(so) and os.path.isdir("/root/reference/OptiX-Path-Tracer/programs"):
+        _run(["make", "ref"], ORACLE_DIR)
+    if not os.path.exists(so):
+        return None
+    r = C.CDLL(so)
+    vp, ci = C.c_void_p, C.c_int
+    r.refray_render.argtypes = [vp, ci, ci, ci, ci, ci, ci, RADIANCE_HOOK, vp, vp]
+    r.refmiss.argtypes = [ci, ci, pt.F3, pt.F3, pt.F3, pt.F3, pt.F3, pt.F3, vp, C.POINTER(ci)]
     return r
 
 
