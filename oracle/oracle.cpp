@@ -1,5 +1,8 @@
 // oracle.cpp — CPU oracle: host C++/OpenMP restatement of the reference's
 // device programs.  TEST INFRASTRUCTURE ONLY (see oracle.h).
+// Pinned bit for bit against the reference's own source compiled as host code
+// (oracle/ref_*probe.cpp, tests/test_oracle_*golden.py): headers, intersection /
+// hit-record / light / closest-hit / ray-generation / miss / texture programs.
 //
 // Citations use P/ = /root/reference/OptiX-Path-Tracer/programs/ and
 // H/ = /root/reference/OptiX-Path-Tracer/host_includes/.
@@ -2043,6 +2046,10 @@ void orc_miss_probe(const orc_scene* s, const float* dir, const float* thr_in, f
   st3(thr_out, prd.throughput);
   uv2[0] = uv2[1] = 0.f;
   if (s->d.miss.type == PT_MISS_IMG || s->d.miss.type == PT_MISS_HDR) miss_uv(s->d.miss, ld3(dir), uv2[0], uv2[1]);
+}
+// texture program `tex` of the scene at (u, v, P, index) — P/textures/*.cu sample_texture
+void orc_sample_texture(const orc_scene* s, int tex, float u, float v, const float* P, int index, float* rgb) {
+  st3(rgb, sample_texture(*s, tex, u, v, ld3(P), index));
 }
 void orc_prim_bounds(const orc_scene* s, int prim, float* lo_hi6) {
   Box3 b = prim_bounds(*s, prim);

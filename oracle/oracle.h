@@ -9,15 +9,20 @@
  * (optix-path-tracer_b200/, libptb200.so) never links, imports or calls it.
  *
  * Parity pinning: the reference has no tests and cannot run here (needs the
- * proprietary OptiX 6 SDK + a GPU).  What IS pinned against the real
- * reference: RNG, sampling, BSDF Sample/Evaluate/PDF, microfacet helpers and
- * Fresnel/refraction helpers — the reference's own header code
- * (programs/ .cuh headers) is compiled unmodified into oracle/_ref/libref_probe.so by
- * oracle/Makefile and compared with this restatement (tests/test_oracle_ref.py,
- * golden vectors in tests/golden/).  The .cu glue (intersection programs,
- * closest-hit programs, raygen loop, miss programs) cannot be compiled without
- * OptiX and is restated only: for those parts parity is UNPINNED by reference
- * outputs and the oracle defines it.
+ * proprietary OptiX 6 SDK + a GPU), but its device code compiles UNMODIFIED as
+ * host C++ once the OptiX device-program environment is emulated
+ * (oracle/ref_shim/).  oracle/Makefile builds, from the sources where they lie
+ * under /root/reference, oracle/_ref/libref_{probe,cu,mat,ray,tex}.so: the BSDF /
+ * RNG headers, the intersection + bounds + hit-record programs of all seven
+ * primitive kinds, both light programs, all nine closest-hit programs with
+ * Direct_Light, the ray-generation program (camera, color() loop, accumulation,
+ * display pixel), the miss programs and the texture programs.  This restatement
+ * reproduces every one of them bit for bit (tests/test_oracle_*golden.py; vectors
+ * recorded by tests/golden/make_golden*.py so the tests also run without the tree).
+ * Pinned by decision, not by reference output (OptiX runtime behaviour): the open
+ * ray interval, what a shadow ray answers (hit.cu leaves it undefined on a miss),
+ * traversal order / tie-breaking, the per-(ray, primitive) uniform of the volumes,
+ * hit records of transformed primitives, hardware texture filtering.
  *
  * It consumes the same flat scene description as the product
  * (include/ptb200.h: pt_scene_desc), so both sides see identical inputs.
@@ -108,6 +113,7 @@ void orc_closest_hit_probe(const orc_scene* s, const pt_ray* ray, int prim, floa
 /* one rtTrace of a radiance ray (closest hit + its closest-hit program, or the miss program) on a payload */
 void orc_trace_radiance(const orc_scene* s, const float* ray8, float* prd16);
 void orc_miss_probe(const orc_scene* s, const float* dir, const float* thr_in, float* thr_out, float* uv2);
+void orc_sample_texture(const orc_scene* s, int tex, float u, float v, const float* P, int index, float* rgb);
 void orc_prim_bounds(const orc_scene* s, int prim, float* lo_hi6);
 void orc_light_sample(const pt_light* l, const float* P, uint32_t* seed, float* Wi_out);
 float orc_light_pdf(const pt_light* l, const float* P, const float* Wi);

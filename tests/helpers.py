@@ -106,6 +106,7 @@ def oracle(variant=""):
     o.orc_intersect_prim_ex.argtypes = [vp, C.c_int, P(pt.Ray), fl, C.c_uint32, vp, vp]
     o.orc_closest_hit_probe.argtypes = [vp, P(pt.Ray), C.c_int, fl, fl, fl, vp, vp]
     o.orc_trace_radiance.argtypes = [vp, vp, vp]
+    o.orc_sample_texture.argtypes = [vp, C.c_int, fl, fl, F3, C.c_int, F3]
     o.orc_miss_probe.argtypes = [vp, F3, F3, F3, vp]
     o.orc_prim_bounds.argtypes = [vp, C.c_int, vp]
     o.orc_light_sample.argtypes = [P(pt.Light), F3, P(C.c_uint32), F3]
@@ -207,6 +208,19 @@ def ref_ray_probe():
     vp, ci = C.c_void_p, C.c_int
     r.refray_render.argtypes = [vp, ci, ci, ci, ci, ci, ci, RADIANCE_HOOK, vp, vp]
     r.refmiss.argtypes = [ci, ci, pt.F3, pt.F3, pt.F3, pt.F3, pt.F3, pt.F3, vp, C.POINTER(ci)]
+    return r
+
+
+def ref_tex_probe():
+    """The reference's textures/*.cu compiled unmodified as host code (oracle/_ref/libref_tex.so) or None."""
+    so = os.path.join(ORACLE_DIR, "_ref", "libref_tex.so")
+    if not os.path.exists(so) and os.path.isdir("/root/reference/OptiX-Path-Tracer/programs"):
+        _run(["make", "ref"], ORACLE_DIR)
+    if not os.path.exists(so):
+        return None
+    r = C.CDLL(so)
+    for name in ("constant", "checker", "gradient", "vector", "noise"):
+        getattr(r, "reftex_" + name).argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_float, pt.F3, C.c_int, pt.F3]
     return r
 
 
