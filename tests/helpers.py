@@ -340,26 +340,44 @@ def _v(x, y, z):
     return np.array([x, y, z], dtype=np.float32)
 
 
+_libm = C.CDLL("libm.so.6")
+_libm.tanf.restype = C.c_float
+_libm.tanf.argtypes = [C.c_float]
+
+
+def _dot(a, b):
+    return f32(f32(f32(a[0] * b[0]) + f32(a[1] * b[1])) + f32(a[2] * b[2]))
+
+
+def _cross(a, b):
+    return np.array([f32(f32(a[1] * b[2]) - f32(a[2] * b[1])), f32(f32(a[2] * b[0]) - f32(a[0] * b[2])),
+                     f32(f32(a[0] * b[1]) - f32(a[1] * b[0]))], dtype=np.float32)
+
+
 def _unit(v):
-    return (v / f32(np.sqrt(np.dot(v, v), dtype=np.float32))).astype(np.float32)
+    """programs/vec.hpp unit_vector: v / length(v) with optix's float3 / float = v * (1 / s)"""
+    inv = f32(1.0) / f32(np.sqrt(_dot(v, v), dtype=np.float32))
+    return (v * inv).astype(np.float32)
 
 
 def make_camera(lookfrom, lookat, vup, vfov, aspect, aperture, focus_dist, t0=0.0, t1=1.0):
-    """host_includes/camera.hpp:16-38"""
+    """host_includes/camera.hpp:16-38, operation for operation in binary32 (pinned bit-exactly against the reference's
+    own camera.hpp by tests/test_oracle_host_golden.py)"""
     lookfrom, lookat, vup = (np.asarray(a, dtype=np.float32) for a in (lookfrom, lookat, vup))
-    theta = f32(vfov) * PI_F / f32(180.0)
-    half_height = f32(math.tan(float(theta / f32(2.0))))
-    half_width = f32(aspect) * half_height
-    w = _unit(lookfrom - lookat)
-    u = _unit(np.cross(vup, w).astype(np.float32))
-    v = np.cross(w, u).astype(np.float32)
+    theta = f32(f32(f32(vfov) * PI_F) / f32(180.0))
+    half_height = f32(_libm.tanf(float(f32(theta / f32(2.0)))))
+    half_width = f32(f32(aspect) * half_height)
+    w = _unit((lookfrom - lookat).astype(np.float32))
+    u = _unit(_cross(vup, w))
+    v = _cross(w, u)
     fd = f32(focus_dist)
-    llc = lookfrom - half_width * fd * u - half_height * fd * v - fd * w
+    llc = (((lookfrom - f32(half_width * fd) * u).astype(np.float32) - f32(half_height * fd) * v).astype(np.float32)
+           - fd * w).astype(np.float32)
     cam = pt.Camera()
     cam.origin = pt.F3(*lookfrom)
-    cam.lower_left_corner = pt.F3(*llc.astype(np.float32))
-    cam.horizontal = pt.F3(*(f32(2.0) * half_width * fd * u).astype(np.float32))
-    cam.vertical = pt.F3(*(f32(2.0) * half_height * fd * v).astype(np.float32))
+    cam.lower_left_corner = pt.F3(*llc)
+    cam.horizontal = pt.F3(*(f32(f32(f32(2.0) * half_width) * fd) * u).astype(np.float32))
+    cam.vertical = pt.F3(*(f32(f32(f32(2.0) * half_height) * fd) * v).astype(np.float32))
     cam.u, cam.v, cam.w = pt.F3(*u), pt.F3(*v), pt.F3(*w)
     cam.lens_radius = f32(aperture) / f32(2.0)
     cam.time0, cam.time1 = t0, t1
