@@ -153,3 +153,18 @@ extern "C" void refcu_spherelight_sample(const float* prm, const float* P, unsig
   st(Wi, Sample(ld(P), z, z, *seed));
 }
 #endif
+
+#if defined(PROBE_ANY_HIT)
+#include "hit.cu"
+// the per-hit rule of the shadow any-hit program (hit.cu:16-24): returns prd_shadow.inShadow after any_hit() ran on a
+// hit of a material with `is_light` = light, for shading normal N and shadow-ray direction d.  WHICH hit OptiX hands
+// to it is traversal-order dependent and stays the oracle's pin (the closest one).
+extern "C" int refcu_any_hit(int light, const float* N, const float* d) {
+  is_light = light;
+  prd_shadow.normal = ld(N);
+  prd_shadow.inShadow = false;
+  ray = make_Ray(make_float3(0.f), ld(d), 1, 1e-3f, RT_DEFAULT_MAX);
+  any_hit();
+  return prd_shadow.inShadow ? 1 : 0;
+}
+#endif

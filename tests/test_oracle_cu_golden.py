@@ -168,3 +168,20 @@ def test_oracle_reproduces_reference_cu_programs_live():
     n = check_prims(cases, lambda c: G.run_reference(r, c))
     assert n >= 200
     check_lights(G.light_cases(rng, 64), lambda c: G.run_light_reference(r, c), int(h.ref_probe().ref_arg_order()))
+
+
+def test_shadow_any_hit_rule_live():
+    """hit.cu any_hit, compiled unmodified: a hit un-shadows the ray iff its material is a light AND the shading
+    normal faces along the shadow ray (dot(N, d) > 0) - the per-hit rule inside the oracle's Direct_Light
+    (`m.type == PT_MAT_DIFFUSE_LIGHT && dot(N, Wi) > 0`); which hit is asked is the oracle's pin (the closest)."""
+    r = h.ref_cu_probe()
+    if r is None or not hasattr(r, "refcu_any_hit"):
+        pytest.skip("reference tree not present")
+    r.refcu_any_hit.argtypes = [C.c_int, pt.F3, pt.F3]
+    rng = np.random.default_rng(1)
+    for _ in range(200):
+        N, d = rng.normal(size=3).astype(np.float32), rng.normal(size=3).astype(np.float32)
+        dot = np.float32(np.float32(np.float32(N[0] * d[0]) + np.float32(N[1] * d[1])) + np.float32(N[2] * d[2]))
+        for light in (0, 1):
+            want_shadow = 0 if (light and dot > 0) else 1
+            assert r.refcu_any_hit(light, pt.F3(*N), pt.F3(*d)) == want_shadow
