@@ -523,7 +523,9 @@ int flat_max() {
 }
 SchedParams sched_params_base() {
   static SchedParams p = [] {
-    SchedParams q{12, 8, 0, 0};
+    // refill threshold re-tuned for the final kernels (profiles/r01_sched_sweep3.txt): 12 -> 20 is +4 % on C2 / C3,
+    // neutral on the triangle scene; 28 costs it 9 %
+    SchedParams q{20, 8, 0, 0};
     if (const char* e = getenv("PTB200_REFILL_MIN")) q.refill_min = std::max(1, atoi(e));
     if (const char* e = getenv("PTB200_LEAF_THRESH")) q.leaf_thresh = std::max(1, atoi(e));
     if (const char* e = getenv("PTB200_FETCH_CHUNK")) q.fetch_chunk = std::max(0, atoi(e));
@@ -612,7 +614,7 @@ static Ctrl* g_hctrl = nullptr;
 
 static int ensure_pool(pt_renderer* r, long long want) {
   long long npix = (long long)r->W * r->H;
-  long long pool = r->pool_req > 0 ? r->pool_req : (1ll << 22);
+  long long pool = r->pool_req > 0 ? r->pool_req : (1ll << 23);  // 8 Mi paths (3.5 GB of state): +5 % over 4 Mi on C1 / C3 / C4
   pool = std::min<long long>(pool, std::max<long long>(want, 1024));
   (void)npix;
   pool = std::min<long long>(pool, 1ll << 25);
@@ -807,6 +809,7 @@ int pt_render(pt_renderer* r, int32_t first_frame, int32_t nframes, int32_t max_
   // node test culls most primitives, and testing all of them flat was 7 % slower end to end (C1, C3);
   // closest-hit rays are 25-45 % faster flat.  PTB200_FLAT_SHADOW=1 overrides (dev)
   SchedParams sched_shadow = sched;
+  if (!getenv("PTB200_REFILL_MIN")) sched_shadow.refill_min = 28;  // shadow rays are short: larger retire batches pay (C3 +3 %)
   {
     static const int fs = getenv("PTB200_FLAT_SHADOW") ? atoi(getenv("PTB200_FLAT_SHADOW")) : 0;
     sched_shadow.flat = sched.flat && fs != 0;
