@@ -7,7 +7,8 @@ lib = pt.load()
 which = sys.argv[1:] or ["c1", "c2", "c4"]
 cfg = {"c1": (lambda: h.build_cornell(512, 512, lib), 512, 512, 64),
        "c2": (lambda: h.build_spheres(22, W=1200, H=800, lib=lib), 1200, 800, 256),
-       "c4": (lambda: h.build_mesh_scene(708, 1920, 1080, lib), 1920, 1080, 64)}
+       "c4": (lambda: h.build_mesh_scene(708, 1920, 1080, lib), 1920, 1080, 64),
+       "c4_10m": (lambda: h.build_mesh_scene(2237, 1920, 1080, lib), 1920, 1080, 64)}
 for name in which:
     build, W, H, spp = cfg[name]
     pin = torch.empty(H, W, 4, pin_memory=True)
