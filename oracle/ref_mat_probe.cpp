@@ -14,6 +14,17 @@
 
 static float3 ld(const float* p) { return make_float3(p[0], p[1], p[2]); }
 static void st(float* p, const float3& v) { p[0] = v.x; p[1] = v.y; p[2] = v.z; }
+// a texture callable: the given constant colour, or - in the emulated pipeline - texture program tex[0] of the scene
+static std::function<float3(float, float, float3, int)> tex_fn(const float* tex) {
+  return [=](float u, float v, float3 p, int idx) {
+    if (refshim_texture_hook) {
+      float o[3];
+      refshim_texture_hook((int)tex[0], u, v, &p.x, idx, o);
+      return ld(o);
+    }
+    return ld(tex);
+  };
+}
 
 // light programs live in their own translation units (ref_cu_probe.cpp)
 extern "C" float refcu_rect_pdf(const float* prm, int axis, const float* P, const float* Wi);
@@ -25,13 +36,13 @@ extern "C" void refcu_spherelight_sample(const float* prm, const float* P, unsig
 #include "materials/lambertian.cu"
 #define NAME lambertian
 #define USES_LIGHTS 1
-static void set_params(const float* tex, const float*) { sample_texture.f = [=](float, float, float3, int) { return ld(tex); }; }
+static void set_params(const float* tex, const float*) { sample_texture.f = tex_fn(tex); }
 #elif defined(PROBE_MAT_METAL)
 #include "materials/metal.cu"
 #define NAME metal
 #define USES_LIGHTS 0
 static void set_params(const float* tex, const float* mp) {
-  sample_texture.f = [=](float, float, float3, int) { return ld(tex); };
+  sample_texture.f = tex_fn(tex);
   fuzz = mp[0];
 }
 #elif defined(PROBE_MAT_DIELECTRIC)
@@ -39,8 +50,8 @@ static void set_params(const float* tex, const float* mp) {
 #define NAME dielectric
 #define USES_LIGHTS 0
 static void set_params(const float* tex, const float* mp) {
-  base_texture.f = [=](float, float, float3, int) { return ld(tex); };
-  extinction_texture.f = [=](float, float, float3, int) { return ld(tex + 3); };
+  base_texture.f = tex_fn(tex);
+  extinction_texture.f = tex_fn(tex + 3);
   ref_idx = mp[0];
   density = mp[1];
 }
@@ -48,13 +59,13 @@ static void set_params(const float* tex, const float* mp) {
 #include "materials/diffuse_light.cu"
 #define NAME diffuse_light
 #define USES_LIGHTS 1
-static void set_params(const float* tex, const float*) { sample_texture.f = [=](float, float, float3, int) { return ld(tex); }; }
+static void set_params(const float* tex, const float*) { sample_texture.f = tex_fn(tex); }
 #elif defined(PROBE_MAT_OREN_NAYAR)
 #include "materials/oren_nayar.cu"
 #define NAME oren_nayar
 #define USES_LIGHTS 1
 static void set_params(const float* tex, const float* mp) {
-  sample_texture.f = [=](float, float, float3, int) { return ld(tex); };
+  sample_texture.f = tex_fn(tex);
   rA = mp[0];
   rB = mp[1];
 }
@@ -63,7 +74,7 @@ static void set_params(const float* tex, const float* mp) {
 #define NAME torrance_sparrow
 #define USES_LIGHTS 1
 static void set_params(const float* tex, const float* mp) {
-  sample_texture.f = [=](float, float, float3, int) { return ld(tex); };
+  sample_texture.f = tex_fn(tex);
   nu = mp[0];
   nv = mp[1];
 }
@@ -72,8 +83,8 @@ static void set_params(const float* tex, const float* mp) {
 #define NAME ashikhmin_shirley
 #define USES_LIGHTS 1
 static void set_params(const float* tex, const float* mp) {
-  diffuse_color.f = [=](float, float, float3, int) { return ld(tex); };
-  specular_color.f = [=](float, float, float3, int) { return ld(tex + 3); };
+  diffuse_color.f = tex_fn(tex);
+  specular_color.f = tex_fn(tex + 3);
   nu = mp[0];
   nv = mp[1];
 }
@@ -86,7 +97,7 @@ static void set_params(const float*, const float* mp) { useShadingNormal = (int)
 #include "materials/isotropic.cu"
 #define NAME isotropic
 #define USES_LIGHTS 1
-static void set_params(const float* tex, const float*) { sample_texture.f = [=](float, float, float3, int) { return ld(tex); }; }
+static void set_params(const float* tex, const float*) { sample_texture.f = tex_fn(tex); }
 #endif
 
 #define CAT2(a, b) a##b

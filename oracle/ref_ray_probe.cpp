@@ -51,8 +51,8 @@ static inline void shim_trace(const Ray& r, PerRayData& p) {  // preferred over 
 // cam: origin, lower_left_corner, horizontal, vertical, u, v (3 floats each), lens_radius, time0, time1
 // renders frames [first, first + n) of a W x H image with the reference's renderPixel; acc: W*H float4,
 // disp: W*H uchar4 (both row 0 = top, raygen.cu:153)
-extern "C" void refray_render(const float* cam, int W, int H, int first, int n, int max_depth, int russian_,
-                              radiance_hook_t hook, float* acc, unsigned char* disp) {
+extern "C" void refray_render_rows(const float* cam, int W, int H, int y0, int y1, int first, int n, int max_depth,
+                                   int russian_, radiance_hook_t hook, float* acc, unsigned char* disp) {
   camera_origin = ld(cam);
   camera_lower_left_corner = ld(cam + 3);
   camera_horizontal = ld(cam + 6);
@@ -73,7 +73,7 @@ extern "C" void refray_render(const float* cam, int W, int H, int first, int n, 
   for (size_t i = 0; i < (size_t)W * H; i++) acc_buffer.v[i] = {acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]};
   for (int f = first; f < first + n; f++) {
     frame = f;
-    for (int y = 0; y < H; y++)
+    for (int y = y0; y < y1; y++)  // pixelID.y counts from the bottom row (raygen.cu:153)
       for (int x = 0; x < W; x++) {
         pixelID = make_uint2((unsigned)x, (unsigned)y);
         renderPixel();
@@ -85,6 +85,10 @@ extern "C" void refray_render(const float* cam, int W, int H, int first, int n, 
     const uchar4 d = display_buffer.v[i];
     disp[4 * i] = d.x; disp[4 * i + 1] = d.y; disp[4 * i + 2] = d.z; disp[4 * i + 3] = d.w;
   }
+}
+extern "C" void refray_render(const float* cam, int W, int H, int first, int n, int max_depth, int russian_,
+                              radiance_hook_t hook, float* acc, unsigned char* disp) {
+  refray_render_rows(cam, W, H, 0, H, first, n, max_depth, russian_, hook, acc, disp);
 }
 #endif
 

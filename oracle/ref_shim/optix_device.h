@@ -103,10 +103,23 @@ struct ShimShadow {
   Ray ray;
 };
 static ShimShadow g_shadow;
+// Hooks of the emulated pipeline (oracle/ref_render.cpp); null in the unit probes.  Weak, so that every translation
+// unit of one library shares them.
+extern "C" {
+typedef int (*refshim_shadow_hook_t)(const float* ray8, const float* normal3);
+typedef void (*refshim_texture_hook_t)(int tex, float u, float v, const float* p3, int index, float* rgb3);
+__attribute__((weak)) refshim_shadow_hook_t refshim_shadow_hook = nullptr;
+__attribute__((weak)) refshim_texture_hook_t refshim_texture_hook = nullptr;
+}
 template <class PRD>
 static inline void shim_trace(const Ray& r, PRD& prd) {
   g_shadow.traced++;
   g_shadow.ray = r;
+  if (refshim_shadow_hook) {
+    const float ray8[8] = {r.origin.x, r.origin.y, r.origin.z, r.tmin, r.direction.x, r.direction.y, r.direction.z, r.tmax};
+    prd.inShadow = refshim_shadow_hook(ray8, &prd.normal.x) != 0;
+    return;
+  }
   prd.inShadow = g_shadow.answer_in_shadow != 0;
 }
 // a macro, so that the `world` argument never reaches the compiler: light_sample.cuh's Direct_Light template

@@ -211,6 +211,50 @@ def ref_ray_probe():
     return r
 
 
+class ReferenceRenderer:
+    """The reference itself on the CPU: its own programs (compiled unmodified) inside an emulated OptiX pipeline
+    (oracle/ref_render.cpp -> oracle/_ref/libref_render.so).  One rendering thread per process."""
+
+    @staticmethod
+    def lib():
+        so = os.path.join(ORACLE_DIR, "_ref", "libref_render.so")
+        if not os.path.exists(so) and os.path.isdir("/root/reference/OptiX-Path-Tracer/programs"):
+            _run(["make", "ref"], ORACLE_DIR)
+        if not os.path.exists(so):
+            return None
+        r = C.CDLL(so)
+        ci, vp = C.c_int, C.c_void_p
+        r.refrender_create.restype = vp
+        r.refrender_create.argtypes = [C.POINTER(pt.SceneDesc)]
+        r.refrender_destroy.argtypes = [vp]
+        r.refrender_render.argtypes = [vp, ci, ci, ci, ci, ci, ci, ci, ci, vp, vp]
+        return r
+
+    def __init__(self, scene):
+        self.r = self.lib()
+        if self.r is None:
+            raise RuntimeError("oracle/_ref/libref_render.so is not built (needs /root/reference)")
+        self.scene = scene
+        self.desc = scene.desc()
+        self.h = self.r.refrender_create(C.byref(self.desc))
+
+    def render(self, W, H, first_frame, nframes, max_depth=50, russian=True, rows=None, acc=None):
+        """frames [first, first + n) of rows [y0, y1) (0 = bottom) added into acc; returns (acc, display)"""
+        if acc is None:
+            acc = np.zeros((H, W, 4), dtype=np.float32)
+        disp = np.zeros((H, W, 4), dtype=np.uint8)
+        y0, y1 = rows if rows else (0, H)
+        self.r.refrender_render(self.h, W, H, y0, y1, first_frame, nframes, max_depth, int(russian), acc.ctypes.data,
+                                disp.ctypes.data)
+        return acc, disp
+
+    def __del__(self):
+        try:
+            self.r.refrender_destroy(self.h)
+        except Exception:
+            pass
+
+
 def ref_tex_probe():
     """The reference's textures/*.cu compiled unmodified as host code (oracle/_ref/libref_tex.so) or None."""
     so = os.path.join(ORACLE_DIR, "_ref", "libref_tex.so")
