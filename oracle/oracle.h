@@ -12,11 +12,15 @@
  * proprietary OptiX 6 SDK + a GPU), but its device code compiles UNMODIFIED as
  * host C++ once the OptiX device-program environment is emulated
  * (oracle/ref_shim/).  oracle/Makefile builds, from the sources where they lie
- * under /root/reference, oracle/_ref/libref_{probe,cu,mat,ray,tex}.so: the BSDF /
+ * under /root/reference, oracle/_ref/libref_{probe,cu,mat,ray,tex,host,render}.so: the BSDF /
  * RNG headers, the intersection + bounds + hit-record programs of all seven
  * primitive kinds, both light programs, all nine closest-hit programs with
  * Direct_Light, the ray-generation program (camera, color() loop, accumulation,
- * display pixel), the miss programs and the texture programs.  This restatement
+ * display pixel), the miss programs and the texture programs — and
+ * libref_render.so (oracle/ref_render.cpp), all of those programs wired into an
+ * emulated OptiX pipeline, i.e. the reference itself rendering whole images on the
+ * CPU (tests/test_reference_render.py: bit-identical to this oracle; it is also
+ * what bench.py --impl reference times, kind "reference").  This restatement
  * reproduces every one of them bit for bit (tests/test_oracle_*golden.py; vectors
  * recorded by tests/golden/make_golden*.py so the tests also run without the tree).
  * Pinned by decision, not by reference output (OptiX runtime behaviour): the open

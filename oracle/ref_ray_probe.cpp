@@ -68,9 +68,16 @@ extern "C" void refray_render_rows(const float* cam, int W, int H, int y0, int y
   samples = first + n;
   g_hook = hook;
   acc_buffer.w = display_buffer.w = W;
-  acc_buffer.v.assign((size_t)W * H, make_float4(0.f));
-  display_buffer.v.assign((size_t)W * H, make_uchar4(0, 0, 0, 0));
-  for (size_t i = 0; i < (size_t)W * H; i++) acc_buffer.v[i] = {acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]};
+  // only the buffer rows that hold pixel rows [y0, y1) travel in and out: a band costs its own pixels, not W*H
+  const size_t n_px = (size_t)W * H, r0 = (size_t)(H - y1) * W, r1 = (size_t)(H - y0) * W;
+  if (acc_buffer.v.size() != n_px) {
+    acc_buffer.v.assign(n_px, make_float4(0.f));
+    display_buffer.v.assign(n_px, make_uchar4(0, 0, 0, 0));
+  }
+  for (size_t i = r0; i < r1; i++) {
+    acc_buffer.v[i] = {acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]};
+    display_buffer.v[i] = make_uchar4(0, 0, 0, 0);
+  }
   for (int f = first; f < first + n; f++) {
     frame = f;
     for (int y = y0; y < y1; y++)  // pixelID.y counts from the bottom row (raygen.cu:153)
@@ -79,7 +86,7 @@ extern "C" void refray_render_rows(const float* cam, int W, int H, int y0, int y
         renderPixel();
       }
   }
-  for (size_t i = 0; i < (size_t)W * H; i++) {
+  for (size_t i = r0; i < r1; i++) {
     const float4 a = acc_buffer.v[i];
     acc[4 * i] = a.x; acc[4 * i + 1] = a.y; acc[4 * i + 2] = a.z; acc[4 * i + 3] = a.w;
     const uchar4 d = display_buffer.v[i];
