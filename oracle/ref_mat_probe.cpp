@@ -107,7 +107,7 @@ extern "C" void CAT(refmat_, NAME)(const float* rec14, const float* ray8, float 
                                    const float* lights, int in_shadow, float* prd16, float* shadow8) {
   set_params(tex6, mp3);
   HitRecord rec;
-  rec.index = 0;
+  rec.index = refshim_hit_index;
   rec.P = ld(rec14);
   rec.geometric_normal = ld(rec14 + 3);
   rec.shading_normal = ld(rec14 + 6);

@@ -47,12 +47,14 @@ typedef int (*refshim_shadow_hook_t)(const float* ray8, const float* normal3);
 typedef void (*refshim_texture_hook_t)(int tex, float u, float v, const float* p3, int index, float* rgb3);
 extern refshim_shadow_hook_t refshim_shadow_hook;
 extern refshim_texture_hook_t refshim_texture_hook;
+extern int refshim_hit_index;
 }
 
 namespace {
 
 struct Prim {
   int kind, material, xform;
+  int tex_index;  // HitRecord::index: the mesh's per-triangle texture index, 0 for everything else
   std::vector<float> prm;
   float lo[3], hi[3];  // world bounds from the reference's bounds program
 };
@@ -352,7 +354,9 @@ void radiance_hook(const float* ray8, float* prd16) {
     // shadow ray: that state seeds the volumes a shadow ray meets (the payload of a shadow ray carries no seed)
     g_shadow_seed = seed;
     for (int k = 0; k < 3; k++) g_shadow_seed = 1664525u * g_shadow_seed + 1013904223u;
+    refshim_hit_index = s.prims[id].tex_index;
     material_program(m.type)(rec, ray8, h3[0], tex6, mp3, s.lights.data(), 1, prd16, sh);
+    refshim_hit_index = 0;
     return;
   }
   // miss program (miss.cu): image backgrounds sample at coordinates the program computes
@@ -397,6 +401,7 @@ void* refrender_create(const pt_scene_desc* d) {
     p.kind = r.type;
     p.material = r.material;
     p.xform = r.xform;
+    p.tex_index = (r.type == PT_PRIM_TRIANGLE && d->tri_tex) ? d->tri_tex[r.index] : 0;
     switch (r.type) {
       case PT_PRIM_TRIANGLE: {
         p.prm.assign(26, 0.f);

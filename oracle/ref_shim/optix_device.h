@@ -110,6 +110,10 @@ typedef int (*refshim_shadow_hook_t)(const float* ray8, const float* normal3);
 typedef void (*refshim_texture_hook_t)(int tex, float u, float v, const float* p3, int index, float* rgb3);
 __attribute__((weak)) refshim_shadow_hook_t refshim_shadow_hook = nullptr;
 __attribute__((weak)) refshim_texture_hook_t refshim_texture_hook = nullptr;
+// HitRecord::index of the hit being shaded: 0 for analytic primitives (their intersection programs report
+// geo_index = 0), material_buffer[primitive] for mesh triangles (hitables/triangle.cu:146).  The float record
+// that travels between the probes has no slot for it, so the emulated pipeline hands it over here.
+__attribute__((weak)) int refshim_hit_index = 0;
 }
 template <class PRD>
 static inline void shim_trace(const Ray& r, PRD& prd) {

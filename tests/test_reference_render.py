@@ -73,6 +73,50 @@ def test_reference_renderer_equals_oracle(name):
     assert np.array_equal(disp_ref, disp_orc)
 
 
+# scene functions of the C++ facade (host_includes/scenes.hpp: the reference's scene-building surface), by id:
+# 0 InOneWeekend, 1 MovingSpheres (moving spheres + checker + earth image), 2 Cornell, 4 Test_Scene (1 M-triangle
+# mesh + HDRI), 5 material zoo, 6 mesh + env map, 7 sphere light, 8 MTL-textured mesh (per-triangle texture index
+# through Vector_Texture), 9 motion blur, 10 Cornell smoke
+FACADE_SCENES = [(0, 0), (1, 0), (2, 0), (4, 0), (5, 0), (6, 8), (7, 0), (8, 8), (9, 0), (10, 0)]
+
+
+def facade_scene(scene_id, model, W, H):
+    import facade_dump
+    h.build_product()
+    if not os.path.exists(pt.HOST_LIB_PATH):
+        pytest.skip("facade library not built")
+    return facade_dump.build(pt.HOST_LIB_PATH, scene_id, W, H, model)
+
+
+@needs_ref
+@pytest.mark.parametrize("scene_id,model", FACADE_SCENES)
+def test_facade_scene_functions_render_identically(scene_id, model, capfd):
+    """scene function -> facade -> flat scene description -> {the reference's programs, the oracle}: same image,
+    bit for bit.  Covers what the hand-built scenes above do not: checker / noise / image / vector textures, the
+    facade's transforms, a million-triangle mesh under an HDR environment."""
+    W, H = 36, 24
+    sc = facade_scene(scene_id, model, W, H)
+    a, _ = h.ReferenceRenderer(sc).render(W, H, 0, 2)
+    b, _ = h.OracleScene(sc, 0, "_r2l").render(W, H, 0, 2)
+    assert b[..., :3].max() > 0
+    assert same_bits(a, b), f"scene {scene_id}: {np.count_nonzero(a != b)} of {a.size} floats differ"
+
+
+@needs_ref
+def test_final_next_week_differs_only_through_transformed_spheres(capfd):
+    """Final_Next_Week holds 1000 spheres under translate + rotate: the one pinned difference (see below); everything
+    else in it (noise and image textures, both volumes, the moving sphere, 400 boxes) must not add to it."""
+    W, H = 36, 24
+    sc = facade_scene(3, 0, W, H)
+    a, _ = h.ReferenceRenderer(sc).render(W, H, 0, 2)
+    b, _ = h.OracleScene(sc, 0, "_r2l").render(W, H, 0, 2)
+    differ = a != b
+    assert np.count_nonzero(differ) < 0.05 * a.size
+    if differ.any():   # last-bit normal differences; a path may fork on one, hence a quantile rather than the maximum
+        rel = np.abs(a - b)[differ] / np.maximum(np.abs(b)[differ], 1e-3)
+        assert np.quantile(rel, 0.9) < 1e-3
+
+
 @needs_ref
 def test_reference_renderer_row_bands_and_frame_ranges():
     """Rows and frames are independent in the reference (seed = tea<64>(W*y+x, frame)): rendering by bands and by
