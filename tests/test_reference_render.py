@@ -25,6 +25,19 @@ needs_ref = pytest.mark.skipif(h.ReferenceRenderer.lib() is None, reason="oracle
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "ref_render_vectors.json")
 
 
+def build_empty(W, H, constant=False):
+    """no primitives at all: every camera ray runs the miss program (miss.cu) and nothing else"""
+    s = pt.Scene(None)
+    s.set_textures([h.tex_const(0.5)])
+    s.set_materials([h.material(pt.MAT_LAMBERTIAN, 0)])
+    s.set_camera(h.make_camera([0, 0, -5], [0, 0, 0], [0, 1, 0], 40.0, W / H, 0.1, 5.0))
+    if constant:
+        s.set_miss(pt.Miss(pt.MISS_CONSTANT, pt.F3(0.25, 0.5, 0.75), pt.F3(0, 0, 0), -1, 1, 0))
+    else:
+        s.set_miss(pt.Miss(pt.MISS_GRADIENT, pt.F3(1, 1, 1), pt.F3(0.5, 0.7, 1.0), -1, 1, 0))
+    return s
+
+
 def scene_table():
     """name -> (builder, W, H, frames, max_depth)"""
     return {
@@ -40,6 +53,8 @@ def scene_table():
         "mesh_env": (lambda: h.build_mesh_scene(12, 32, 32), 32, 32, 2, 50),
         "mesh_normals": (lambda: h.build_mesh_scene(12, 32, 32, normals=True), 32, 32, 2, 50),
         "cornell_depth3": (lambda: h.build_cornell(32, 32), 32, 32, 2, 3),
+        "empty_gradient": (lambda: build_empty(24, 16), 24, 16, 2, 50),
+        "empty_constant": (lambda: build_empty(24, 16, True), 24, 16, 2, 50),
     }
 
 
