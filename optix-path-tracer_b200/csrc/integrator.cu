@@ -292,6 +292,29 @@ __global__ void __launch_bounds__(PT_TRACE_THREADS, PT_TRACE_MINBLOCKS) k_trace(
   }
 }
 
+// closest-hit traversal of deep trees: two node steps per vote round (trace_sched.cuh, BURST); never flat
+#ifndef PT_DEEP_BURST
+#define PT_DEEP_BURST 2
+#endif
+template <bool COUNT, bool SPECIAL>
+__global__ void __launch_bounds__(PT_TRACE_THREADS, PT_TRACE_MINBLOCKS) k_trace_deep(SceneDev sc, Ctrl* c, PathBuf cur, float4* hits,
+                                                                 uint32_t* bin_q, int pool, SchedParams sched) {
+  __shared__ uint2 s_stack[PT_SMEM_STACK * PT_TRACE_THREADS];
+  ClosestPolicy pol{sc, c, cur, hits, bin_q, pool};
+  uint32_t cn = 0, cl = 0;
+  trace_persistent<COUNT, SPECIAL, PT_DEEP_BURST>(sc, c->n_cur, &c->fetch_closest, pol, s_stack, sched, &c->error, cn, cl);
+  if (COUNT) {
+    for (int o = 16; o > 0; o >>= 1) {
+      cn += __shfl_xor_sync(0xffffffffu, cn, o);
+      cl += __shfl_xor_sync(0xffffffffu, cl, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+      atomicAdd(&c->stat_nodes, (unsigned long long)cn);
+      atomicAdd(&c->stat_leaves, (unsigned long long)cl);
+    }
+  }
+}
+
 #ifndef PT_SHADE_MINBLOCKS
 #define PT_SHADE_MINBLOCKS 8
 #endif
@@ -551,17 +574,19 @@ int g_trace_bpm[2] = {0, 0};
 int trace_blocks_per_sm(bool special) {
   int& bpm = g_trace_bpm[special ? 1 : 0];
   if (!bpm) {
-    int a = 0, b = 0, c = 0;
+    int a = 0, b = 0, c = 0, d = 0;
     if (special) {
       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_trace<false, true>, PT_TRACE_THREADS, 0);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d, k_trace_deep<false, true>, PT_TRACE_THREADS, 0);
       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_shadow<false, true>, PT_TRACE_THREADS, 0);
       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c, k_trace_rays<false, true>, PT_TRACE_THREADS, 0);
     } else {
       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_trace<false, false>, PT_TRACE_THREADS, 0);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d, k_trace_deep<false, false>, PT_TRACE_THREADS, 0);
       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_shadow<false, false>, PT_TRACE_THREADS, 0);
       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c, k_trace_rays<false, false>, PT_TRACE_THREADS, 0);
     }
-    bpm = std::max(1, std::min(a, std::min(b, c)));
+    bpm = std::max(1, std::min(std::min(a, d), std::min(b, c)));
 #ifdef PT_TRACE_BPM
     bpm = PT_TRACE_BPM;
 #endif
@@ -812,6 +837,10 @@ int pt_render(pt_renderer* r, int32_t first_frame, int32_t nframes, int32_t max_
   const int g_miss = sms * PT_MISS_BLOCKS;
   const uint32_t mask = s->material_type_mask;
   const SchedParams sched = sched_params(sc);
+  // deep trees (>= 64 Ki primitives: five or more BVH8 levels) take two node steps per vote round for closest-hit
+  // rays; PTB200_DEEP_MIN overrides the size (dev), 0 switches it off
+  static const long long deep_min = getenv("PTB200_DEEP_MIN") ? atoll(getenv("PTB200_DEEP_MIN")) : 65536;
+  const bool deep = deep_min > 0 && sc.n_prims >= deep_min && !sched.flat;
   // shadow rays keep the BVH walk even in tiny scenes: they start on a surface and aim at a light, the one
   // node test culls most primitives, and testing all of them flat was 7 % slower end to end (C1, C3);
   // closest-hit rays are 25-45 % faster flat.  PTB200_FLAT_SHADOW=1 overrides (dev)
@@ -840,7 +869,8 @@ int pt_render(pt_renderer* r, int32_t first_frame, int32_t nframes, int32_t max_
     if (timed) cudaEventRecord(e[0], st);
     k_generate<<<g_gen, 256, 0, st>>>(sc, p, c, cur);
     if (timed) cudaEventRecord(e[1], st);
-    PT_LAUNCH_TRACE(k_trace, count, special, g_trace, st, sc, c, cur, hits, bq, r->pool, sched);
+    if (deep) PT_LAUNCH_TRACE(k_trace_deep, count, special, g_trace, st, sc, c, cur, hits, bq, r->pool, sched);
+    else PT_LAUNCH_TRACE(k_trace, count, special, g_trace, st, sc, c, cur, hits, bq, r->pool, sched);
     if (timed) cudaEventRecord(e[2], st);
     n += 3;
 #define LAUNCH_SHADE(M, LK)                                                     \
