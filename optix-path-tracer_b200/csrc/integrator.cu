@@ -6,13 +6,15 @@
 //   k_iter_begin   1 thread: queue bookkeeping (counts stay on the device)
 //   k_generate     pinhole/thin-lens camera rays for the free slots
 //   k_trace        closest-hit BVH8 traversal, bins paths by material type
+//                  (k_trace_deep: the same with two node steps per vote round,
+//                  for scenes of >= 64 Ki primitives)
 //   k_shade<MAT>   one kernel per material type present (+ k_miss); writes
 //                  compacted continuing paths (warp-aggregated atomics) or a
 //                  shadow request with both continuations (see shading.h)
 //   k_shadow       shadow traversal + resolve + Russian roulette
-// Path state moves with the queue (double-buffered SoA of float4), so every
-// kernel reads coalesced 128-bit words; only the material-sorted shade kernels
-// gather.  No host synchronisation inside an iteration; the host polls the
+// Path state moves with the queue (double-buffered pool of 64-byte records, 4
+// float4 per path; shadow requests one array per float4), so appends are
+// coalesced 128-bit stores; only the material-sorted shade kernels gather.  No host synchronisation inside an iteration; the host polls the
 // control block every few iterations to detect completion.
 #include <cooperative_groups.h>
 
