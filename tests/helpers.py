@@ -332,6 +332,9 @@ def hostsim():
     s.sim_info.argtypes = [vp, P(C.c_int), P(C.c_double), P(C.c_double), P(C.c_int)]
     s.sim_trace.argtypes = [vp, vp, C.c_longlong, vp, vp]
     s.sim_render.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]
+    s.sim_perm8.restype = C.c_uint
+    s.sim_perm8.argtypes = [C.c_uint, C.c_uint]
+    s.sim_node_invariant_violations.argtypes = [vp]
     _sim = s
     return s
 

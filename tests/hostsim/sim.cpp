@@ -276,6 +276,41 @@ void sim_child_hist(const Sim* s, int* children /*9*/, int* leaf_prims /*4*/, in
   }
 }
 
+// the node step's octant table (traverse.h pt_perm8): bit s -> bit s ^ octinv
+unsigned sim_perm8(unsigned m, unsigned octinv) { return pt_perm8(m & 0xffu, octinv & 7u); }
+
+// Invariants the node step's hit-mask assembly relies on, counted over all BVH8 nodes: an empty child slot has
+// meta 0, no imask bit and the inverted box (qlo 255, qhi 0 on every axis) so that it can never pass the slab test;
+// an inner slot s has meta (1 << 5) | (24 + s); a leaf slot's records stay inside the 24-bit leaf field.
+int sim_node_invariant_violations(const Sim* s) {
+  int bad = 0;
+  for (int ni = 0; ni < s->n_nodes8; ni++) {
+    const uint4* np = s->nodes8.data() + (size_t)ni * 5;
+    const uint32_t imask = np[0].w >> 24;
+    const uint32_t q[12] = {np[2].x, np[2].y, np[2].z, np[2].w, np[3].x, np[3].y, np[3].z, np[3].w, np[4].x, np[4].y, np[4].z, np[4].w};
+    for (int k = 0; k < 8; k++) {
+      const uint32_t m = ((k < 4 ? np[1].z : np[1].w) >> (8 * (k & 3))) & 0xff;
+      const bool inner = (imask >> k) & 1u;
+      uint32_t lo[3], hi[3];
+      for (int a = 0; a < 3; a++) {
+        lo[a] = (q[2 * a + (k >> 2)] >> (8 * (k & 3))) & 0xff;
+        hi[a] = (q[6 + 2 * a + (k >> 2)] >> (8 * (k & 3))) & 0xff;
+      }
+      if (m == 0) {
+        if (inner) bad++;
+        for (int a = 0; a < 3; a++)
+          if (lo[a] != 255 || hi[a] != 0) bad++;
+      } else if (inner) {
+        if (m != ((1u << 5) | (24u + (uint32_t)k))) bad++;
+      } else {
+        const uint32_t unary = m >> 5, off = m & 31u;
+        if (!(unary == 1 || unary == 3 || unary == 7) || off + (uint32_t)pt_popc(unary) > 24u) bad++;
+      }
+    }
+  }
+  return bad;
+}
+
 int sim_trace(const Sim* s, const pt_ray* rays, long long n, pt_hit* hits, unsigned long long* counters) {
   unsigned long long cn = 0, cl = 0;
 #pragma omp parallel for schedule(dynamic, 256) reduction(+ : cn, cl)

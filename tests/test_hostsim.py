@@ -322,3 +322,28 @@ def test_soup_with_moving_and_volumetric_primitives():
     assert {pt.PRIM_MOVING_SPHERE, pt.PRIM_VOLUME_SPHERE, pt.PRIM_VOLUME_BOX} <= hit_kinds
     a, _ = orc.render(32, 32, 0, 3)
     assert np.array_equal(a, sim.render(32, 32, 0, 3))
+
+
+def test_octant_table_of_the_node_step():
+    """pt_perm8 (traverse.h): bit s of the child-slot mask goes to priority bit s ^ octinv; an involution, popcount
+    preserving, identity for octinv 0."""
+    s = h.hostsim()
+    for o in range(8):
+        for m in range(256):
+            p = s.sim_perm8(m, o)
+            assert p == sum(1 << (b ^ o) for b in range(8) if m >> b & 1)
+            assert s.sim_perm8(p, o) == m
+        assert s.sim_perm8(0xA5, 0) == 0xA5
+
+
+@pytest.mark.parametrize("builder", ["spheres", "mesh", "soup", "cornell"])
+def test_node_encoding_invariants_the_hit_mask_assembly_relies_on(builder):
+    """Empty child slots carry meta 0, no imask bit and the inverted box (they can never pass the slab test and would
+    add nothing if they did); inner slot s is encoded as (1 << 5) | (24 + s); leaf record ranges fit the 24-bit
+    field.  Checked on every node of four kinds of scene."""
+    sc = {"spheres": lambda: h.build_spheres(22, 0, 32, 32),
+          "mesh": lambda: h.build_mesh_scene(48, 32, 32),
+          "soup": lambda: h.build_random_prims(seed=5, n_moving=6, n_vsph=3, n_vbox=3),
+          "cornell": lambda: h.build_cornell(32, 32)}[builder]()
+    sim = h.SimScene(sc)
+    assert sim.s.sim_node_invariant_violations(sim.h) == 0
