@@ -713,6 +713,29 @@ def build_mesh_scene(grid=32, W=64, H=64, lib=None, normals=False, mat_kind=None
     return s
 
 
+def build_noise_scene(W=32, H=32):
+    """Spheres with Perlin-noise, gradient and checker textures on Lambertian / metal."""
+    rng = np.random.default_rng(7)
+    s = pt.Scene()
+    g = rng.normal(size=(256, 3))
+    g /= np.linalg.norm(g, axis=1, keepdims=True)
+    perms = [rng.permutation(256) for _ in range(3)]
+    data = np.concatenate([g.reshape(-1), *[p.astype(np.float64) for p in perms],
+                           [0.9, 0.1, 0.1, 0.1, 0.9, 0.1, 0.1, 0.1, 0.9]]).astype(np.float32)
+    s.set_texture_data(data)
+    texs = [pt.Texture(pt.TEX_NOISE, pt.F3(4.0, 0, 0), 0, 0), pt.Texture(pt.TEX_GRADIENT, pt.F3(0, 0, 0), 1536, 0),
+            tex_const(0.2, 0.3, 0.1), tex_const(0.9, 0.9, 0.9), pt.Texture(pt.TEX_CHECKER, pt.F3(0, 0, 0), 2, 3),
+            pt.Texture(pt.TEX_NOISE, pt.F3(0.7, 0, 0), 0, 1)]
+    s.set_textures(texs)
+    s.set_materials([material(pt.MAT_LAMBERTIAN, 0), material(pt.MAT_LAMBERTIAN, 1), material(pt.MAT_LAMBERTIAN, 4),
+                     material(pt.MAT_METAL, 5, p0=0.05)])
+    s.add_spheres([pt.Sphere(pt.F3(0, -1000, 0), 1000), pt.Sphere(pt.F3(-2.2, 1, 0), 1.0), pt.Sphere(pt.F3(0, 1, 0), 1.0),
+                   pt.Sphere(pt.F3(2.2, 1, 0), 1.0)], [2, 0, 1, 3])
+    s.set_camera(make_camera([0, 2.5, 7], [0, 1, 0], [0, 1, 0], 40, W / H, 0.0, 7.0))
+    s.set_miss(pt.Miss(pt.MISS_GRADIENT, pt.F3(1, 1, 1), pt.F3(0.5, 0.7, 1.0), -1, 1, 0))
+    return s
+
+
 def build_random_prims(seed=0, n_sph=40, n_rect=30, n_box=30, n_tri=200, xforms=True, lib=None, W=32, H=32,
                        n_moving=0, n_vsph=0, n_vbox=0):
     """Random soup of all primitive kinds, some with rotate/scale/translate chains (n_moving / n_vsph / n_vbox

@@ -172,26 +172,7 @@ def test_env_nee_converges_to_reference_estimator():
 
 
 def _noise_scene(W=32, H=32):
-    """Spheres with Perlin-noise, gradient and checker textures on Lambertian / metal."""
-    rng = np.random.default_rng(7)
-    s = pt.Scene()
-    g = rng.normal(size=(256, 3))
-    g /= np.linalg.norm(g, axis=1, keepdims=True)
-    perms = [rng.permutation(256) for _ in range(3)]
-    data = np.concatenate([g.reshape(-1), *[p.astype(np.float64) for p in perms],
-                           [0.9, 0.1, 0.1, 0.1, 0.9, 0.1, 0.1, 0.1, 0.9]]).astype(np.float32)
-    s.set_texture_data(data)
-    texs = [pt.Texture(pt.TEX_NOISE, pt.F3(4.0, 0, 0), 0, 0), pt.Texture(pt.TEX_GRADIENT, pt.F3(0, 0, 0), 1536, 0),
-            h.tex_const(0.2, 0.3, 0.1), h.tex_const(0.9, 0.9, 0.9), pt.Texture(pt.TEX_CHECKER, pt.F3(0, 0, 0), 2, 3),
-            pt.Texture(pt.TEX_NOISE, pt.F3(0.7, 0, 0), 0, 1)]
-    s.set_textures(texs)
-    s.set_materials([h.material(pt.MAT_LAMBERTIAN, 0), h.material(pt.MAT_LAMBERTIAN, 1), h.material(pt.MAT_LAMBERTIAN, 4),
-                     h.material(pt.MAT_METAL, 5, p0=0.05)])
-    s.add_spheres([pt.Sphere(pt.F3(0, -1000, 0), 1000), pt.Sphere(pt.F3(-2.2, 1, 0), 1.0), pt.Sphere(pt.F3(0, 1, 0), 1.0),
-                   pt.Sphere(pt.F3(2.2, 1, 0), 1.0)], [2, 0, 1, 3])
-    s.set_camera(h.make_camera([0, 2.5, 7], [0, 1, 0], [0, 1, 0], 40, W / H, 0.0, 7.0))
-    s.set_miss(pt.Miss(pt.MISS_GRADIENT, pt.F3(1, 1, 1), pt.F3(0.5, 0.7, 1.0), -1, 1, 0))
-    return s
+    return h.build_noise_scene(W, H)
 
 
 def test_noise_and_gradient_textures_equal_oracle():

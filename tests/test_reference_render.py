@@ -38,6 +38,19 @@ def build_empty(W, H, constant=False):
     return s
 
 
+def build_backdrop(W, H, miss_type, spherical=1):
+    """a mirror sphere and a diffuse one in front of an image background (miss.cu image_background /
+    environmental_mapping): the miss program's own (u, v) arithmetic decides every pixel"""
+    s = pt.Scene(None)
+    s.set_textures([h.tex_const(0.8, 0.6, 0.2), h.tex_const(0.9)])
+    s.set_materials([h.material(pt.MAT_LAMBERTIAN, 0), h.material(pt.MAT_METAL, 1, p0=0.0)])
+    s.add_spheres([pt.Sphere(pt.F3(-1.1, 0, 0), 1.0), pt.Sphere(pt.F3(1.1, 0, 0), 1.0)], [0, 1])
+    s.set_camera(h.make_camera([0, 0.5, -6], [0, 0, 0], [0, 1, 0], 40.0, W / H, 0.0, 6.0))
+    img = s.add_image(h.synthetic_hdri(64, 32))
+    s.set_miss(pt.Miss(miss_type, pt.F3(0, 0, 0), pt.F3(0, 0, 0), img, spherical, 0))
+    return s
+
+
 def scene_table():
     """name -> (builder, W, H, frames, max_depth)"""
     return {
@@ -53,6 +66,9 @@ def scene_table():
         "mesh_env": (lambda: h.build_mesh_scene(12, 32, 32), 32, 32, 2, 50),
         "mesh_normals": (lambda: h.build_mesh_scene(12, 32, 32, normals=True), 32, 32, 2, 50),
         "cornell_depth3": (lambda: h.build_cornell(32, 32), 32, 32, 2, 3),
+        "noise_gradient_checker": (lambda: h.build_noise_scene(32, 32), 32, 32, 2, 50),
+        "image_background": (lambda: build_backdrop(24, 16, pt.MISS_IMG), 24, 16, 2, 50),
+        "hdr_flat_background": (lambda: build_backdrop(24, 16, pt.MISS_HDR, spherical=0), 24, 16, 2, 50),
         "empty_gradient": (lambda: build_empty(24, 16), 24, 16, 2, 50),
         "empty_constant": (lambda: build_empty(24, 16, True), 24, 16, 2, 50),
     }
