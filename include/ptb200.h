@@ -30,7 +30,13 @@
 extern "C" {
 #endif
 
-#define PTB200_ABI_VERSION 2
+#define PTB200_ABI_VERSION 3
+
+/* fixed limits of the renderer (the 64-byte path record packs pixel index | depth | specular flag into 32 bits):
+ * larger images are rejected by pt_renderer_create, larger depths by pt_render (PT_ERR_INVALID).  3840x2160
+ * is 8.3 M pixels; the reference's default maxDepth is 50 (host_includes/host_common.hpp:30). */
+#define PT_MAX_PIXELS (1 << 23)
+#define PT_MAX_DEPTH 255
 
 typedef enum pt_status {
   PT_OK = 0,
@@ -417,6 +423,8 @@ typedef struct pt_stats {
   float ms_trace_shadow;
   float ms_shade;
   float ms_generate;
+  float ms_reduce;         /* ABI 3: device time of the last NCCL merge of the accumulation buffers */
+  uint32_t drained_paths;  /* ABI 3: 1 when the render ended in the single-launch drain kernel */
 } pt_stats;
 int pt_get_stats(pt_renderer* r, pt_stats* out);
 /* bit0: count node/leaf fetches (instrumented kernels); bit1: per-kernel-class
@@ -424,6 +432,42 @@ int pt_get_stats(pt_renderer* r, pt_stats* out);
 int pt_renderer_set_flags(pt_renderer* r, int32_t flags);
 /* path-pool capacity (paths in flight); 0 = default */
 int pt_renderer_set_pool(pt_renderer* r, int64_t paths);
+/* frees the process-level caches (parked path-pool slabs, BVH build arenas) of every device */
+int pt_release_caches(void);
+
+/* ---- multi-GPU (ABI 3) --------------------------------------------------------
+ * The reference renders on one GPU (one OptiX context, main.cpp:30-33, one launch per sample,
+ * main.cpp:264-293).  Samples are independent - seed = tea<64>(W*y+x, frame), programs/raygen.cu:150 -
+ * and the accumulation is a sum (raygen.cu:166), so the frames of a render can be split over devices with the
+ * scene + BVH replicated and the float4 buffers merged by ONE sum-reduce (NCCL over NVLink).  The merged
+ * buffer equals the single-device buffer up to fp32 summation order; .w sums to the sample count.
+ *
+ * (1) One process, several devices - the reference's usage model (a C++ host program):
+ *     pt_renderer_create_multi replicates the committed scene (host data copied, uploaded and its BVH built
+ *     on every other device), creates one renderer per device and returns ONE handle.  pt_render on it
+ *     renders frames [first, first+n) split as pt_split_frames does, all devices concurrently;
+ *     pt_read_accum / pt_read_display / pt_accum_device_ptr first merge the buffers into the first device's
+ *     with ncclReduce.  The list must contain the device the scene was committed on (the root of the merge).
+ * (2) One process per device (torchrun / MPI): every rank builds and commits the scene on its own device,
+ *     renders its share (pt_split_frames) with an ordinary renderer, and the ranks merge with pt_comm_reduce.
+ *     Rank 0 creates the 128-byte id with pt_comm_unique_id and hands it to the others by any means
+ *     (bench.py broadcasts it through torch.distributed; a file or MPI_Bcast do as well).
+ * NCCL is loaded at run time (libnccl.so.2); without it these calls fail with PT_ERR_STATE. */
+int pt_renderer_create_multi(pt_scene* scene, int32_t width, int32_t height, const int32_t* device_ids,
+                             int32_t n_devices, pt_renderer** out);
+/* the share of `total_frames` that participant `rank` of `world` renders: contiguous, sizes differ by at most 1 */
+int pt_split_frames(int32_t total_frames, int32_t rank, int32_t world, int32_t first_frame,
+                    int32_t* out_first, int32_t* out_n);
+
+typedef struct pt_comm pt_comm;
+#define PT_COMM_ID_BYTES 128
+int pt_comm_unique_id(uint8_t id[PT_COMM_ID_BYTES]);
+/* joins the communicator on the calling thread's current device; collective over all `world` ranks */
+int pt_comm_create(const uint8_t id[PT_COMM_ID_BYTES], int32_t rank, int32_t world, pt_comm** out);
+int pt_comm_destroy(pt_comm* comm);
+/* sum-reduce of the renderers' accumulation buffers to rank `root` (in place), on the renderer's stream;
+ * synchronous; the device time lands in pt_stats.ms_reduce.  The only collective of the path. */
+int pt_comm_reduce(pt_comm* comm, pt_renderer* r, int32_t root);
 
 #ifdef __cplusplus
 }

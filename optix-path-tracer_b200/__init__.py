@@ -145,7 +145,7 @@ class Stats(C.Structure):
                 ("iterations", C.c_uint64), ("kernel_launches", C.c_uint64),
                 ("ms_total", C.c_float), ("ms_trace_closest", C.c_float),
                 ("ms_trace_shadow", C.c_float), ("ms_shade", C.c_float),
-                ("ms_generate", C.c_float)]
+                ("ms_generate", C.c_float), ("ms_reduce", C.c_float), ("drained_paths", C.c_uint32)]
 
 
 RAY_DTYPE = np.dtype([("origin", np.float32, 3), ("tmin", np.float32),
@@ -164,7 +164,11 @@ ABI_SYMBOLS = [
     "pt_trace_rays_device", "pt_renderer_create", "pt_renderer_destroy", "pt_render",
     "pt_renderer_sync", "pt_read_accum", "pt_accum_device_ptr", "pt_get_stats",
     "pt_renderer_set_flags", "pt_renderer_set_pool", "pt_read_display", "pt_write_accum",
+    # ABI 3
+    "pt_release_caches", "pt_renderer_create_multi", "pt_split_frames", "pt_comm_unique_id", "pt_comm_create",
+    "pt_comm_destroy", "pt_comm_reduce",
 ]
+MAX_PIXELS, MAX_DEPTH, COMM_ID_BYTES = 1 << 23, 255, 128
 
 
 class PtError(RuntimeError):
@@ -221,6 +225,13 @@ def load(path: Optional[str] = None) -> C.CDLL:
         "pt_get_stats": [vp, P(Stats)],
         "pt_renderer_set_flags": [vp, i32],
         "pt_renderer_set_pool": [vp, i64],
+        "pt_release_caches": [],
+        "pt_renderer_create_multi": [vp, i32, i32, P(i32), i32, P(vp)],
+        "pt_split_frames": [i32, i32, i32, i32, P(i32), P(i32)],
+        "pt_comm_unique_id": [vp],
+        "pt_comm_create": [vp, i32, i32, P(vp)],
+        "pt_comm_destroy": [vp],
+        "pt_comm_reduce": [vp, vp, i32],
     }
     for name, argtypes in sig.items():
         fn = getattr(lib, name)
@@ -374,13 +385,19 @@ class Scene:
 class Renderer:
     """pt_renderer wrapper."""
 
-    def __init__(self, scene: Scene, width: int, height: int, d_accum: int = 0):
+    def __init__(self, scene: Scene, width: int, height: int, d_accum: int = 0, devices: Optional[Sequence[int]] = None):
+        """devices: None = the scene's device (pt_renderer_create); a list = one renderer per device behind this
+        handle, frames split, buffers merged by one ncclReduce on read (pt_renderer_create_multi)."""
         self.scene = scene
         self.lib = scene.lib
         self.W, self.H = width, height
         self.h = C.c_void_p()
-        _check(self.lib, self.lib.pt_renderer_create(scene.h, width, height, C.c_void_p(d_accum or None),
-                                                     C.byref(self.h)))
+        if devices is None:
+            _check(self.lib, self.lib.pt_renderer_create(scene.h, width, height, C.c_void_p(d_accum or None),
+                                                         C.byref(self.h)))
+        else:
+            ids = (C.c_int32 * len(devices))(*devices)
+            _check(self.lib, self.lib.pt_renderer_create_multi(scene.h, width, height, ids, len(devices), C.byref(self.h)))
 
     def close(self):
         if self.h:
@@ -433,6 +450,45 @@ class Renderer:
         s = Stats()
         _check(self.lib, self.lib.pt_get_stats(self.h, C.byref(s)))
         return s
+
+
+def split_frames(total_frames: int, rank: int, world: int, first_frame: int = 0, lib=None):
+    """pt_split_frames: (first_frame, nframes) of participant `rank` of `world`."""
+    lib = lib or load()
+    a, b = C.c_int32(), C.c_int32()
+    _check(lib, lib.pt_split_frames(total_frames, rank, world, first_frame, C.byref(a), C.byref(b)))
+    return a.value, b.value
+
+
+class Comm:
+    """pt_comm wrapper (one process per device): NCCL communicator inside the library."""
+
+    def __init__(self, comm_id: bytes, rank: int, world: int, lib=None):
+        self.lib = lib or load()
+        self.h = C.c_void_p()
+        buf = (C.c_uint8 * COMM_ID_BYTES).from_buffer_copy(comm_id)
+        _check(self.lib, self.lib.pt_comm_create(C.cast(buf, C.c_void_p), rank, world, C.byref(self.h)))
+
+    @staticmethod
+    def unique_id(lib=None) -> bytes:
+        lib = lib or load()
+        buf = (C.c_uint8 * COMM_ID_BYTES)()
+        _check(lib, lib.pt_comm_unique_id(C.cast(buf, C.c_void_p)))
+        return bytes(buf)
+
+    def reduce(self, renderer: "Renderer", root: int = 0):
+        _check(self.lib, self.lib.pt_comm_reduce(self.h, renderer.h, root))
+
+    def close(self):
+        if self.h:
+            self.lib.pt_comm_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def tonemap_png8(accum: np.ndarray, samples: int) -> np.ndarray:

@@ -9,7 +9,14 @@
 
 #include "../host_includes/image_save.hpp"
 
+static int g_gpus = 1;  // --gpus N: frames split over devices 0..N-1, one NCCL reduce at read-back
+
 static int Scene_Config(App_State& app) {
+  if (g_gpus > 1) {
+    std::vector<int> devs;
+    for (int i = 0; i < g_gpus; i++) devs.push_back(i);
+    app.context->setDevices(devs.begin(), devs.end());
+  }
   app.context->setRayTypeCount(2);
   app.context->setMaxTraceDepth(5);
   app.context["samples"]->setInt(app.samples);
@@ -56,12 +63,13 @@ int main(int ac, char** av) {
     else if (arg("--file")) app.fileName = av[++i];
     else if (arg("--type")) app.fileType = atoi(av[++i]);
     else if (arg("--batch")) batch = atoi(av[++i]);
+    else if (arg("--gpus")) g_gpus = atoi(av[++i]);
     else if (arg("--checkpoint")) checkpoint = av[++i];
     else if (arg("--resume")) resume = av[++i];
     else if (arg("--preview")) preview = av[++i];
     else {
       printf("usage: %s [--width W] [--height H] [--samples N] [--scene 0..10] [--model M] [--depth D]\n"
-             "          [--russian 0|1] [--file name] [--type 0(PNG)|1(HDR)] [--batch frames-per-launch]\n"
+             "          [--russian 0|1] [--file name] [--type 0(PNG)|1(HDR)] [--batch frames-per-launch] [--gpus N]\n"
              "          [--checkpoint file: save the accumulation buffer after every batch]\n"
              "          [--resume file: continue a checkpointed render] [--preview file.png: display buffer after every batch]\n",
              av[0]);

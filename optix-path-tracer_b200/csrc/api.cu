@@ -90,76 +90,6 @@ int add_analytic(pt_scene* s, std::vector<T>& store, int kind, const T* prims, c
   return PT_OK;
 }
 
-// Alias table (Vose) over the texels of the environment image, weight = luminance of the
-// radiance the miss program returns (2 x texel, programs/miss.cu:93) x sin(theta) of the row,
-// plus 1 % of the mean so no direction has zero probability.  Built on the host at commit:
-// it is scene set-up, not part of the per-sample path.
-void build_env_tables(pt_scene* s) {
-  s->env_alias_prob.clear();
-  s->env_alias_idx.clear();
-  s->env_texel_pdf.clear();
-  s->env_tables_valid = true;
-  const pt_miss& m = s->miss;
-  if (!m.env_nee || m.type != PT_MISS_HDR || !m.spherical || m.image < 0 || m.image >= (int)s->images.size()) return;
-  const HostImage& im = s->images[m.image];
-  const size_t n = (size_t)im.width * im.height;
-  std::vector<double> w(n);
-  double sum = 0.0;
-  for (int y = 0; y < im.height; y++) {
-    const double st = sin(3.14159265358979323846 * (y + 0.5) / im.height);
-    for (int x = 0; x < im.width; x++) {
-      const float* t = &im.rgba[4 * ((size_t)y * im.width + x)];
-      double lum = 2.0 * (0.2126 * t[0] + 0.7152 * t[1] + 0.0722 * t[2]);
-      if (!(lum > 0.0) || !std::isfinite(lum)) lum = 0.0;
-      w[(size_t)y * im.width + x] = lum * st;
-      sum += lum * st;
-    }
-  }
-  const double floor_w = sum > 0.0 ? 0.01 * sum / (double)n : 1.0;
-  sum = 0.0;
-  for (int y = 0; y < im.height; y++) {
-    const double st = sin(3.14159265358979323846 * (y + 0.5) / im.height);
-    for (int x = 0; x < im.width; x++) {
-      double& v = w[(size_t)y * im.width + x];
-      v += floor_w * st;
-      sum += v;
-    }
-  }
-  s->env_texel_pdf.resize(n);
-  s->env_alias_prob.resize(n);
-  s->env_alias_idx.resize(n);
-  std::vector<double> q(n);
-  std::vector<int32_t> small, large;
-  small.reserve(n);
-  large.reserve(n);
-  for (size_t i = 0; i < n; i++) {
-    const double p = w[i] / sum;
-    s->env_texel_pdf[i] = (float)p;
-    q[i] = p * (double)n;
-    (q[i] < 1.0 ? small : large).push_back((int32_t)i);
-  }
-  while (!small.empty() && !large.empty()) {
-    const int32_t a = small.back();
-    small.pop_back();
-    const int32_t b = large.back();
-    s->env_alias_prob[a] = (float)q[a];
-    s->env_alias_idx[a] = b;
-    q[b] = (q[b] + q[a]) - 1.0;
-    if (q[b] < 1.0) {
-      large.pop_back();
-      small.push_back(b);
-    }
-  }
-  for (int32_t i : large) {
-    s->env_alias_prob[i] = 1.f;
-    s->env_alias_idx[i] = i;
-  }
-  for (int32_t i : small) {
-    s->env_alias_prob[i] = 1.f;
-    s->env_alias_idx[i] = i;
-  }
-}
-
 template <typename T>
 int upload_vec(DevBuf& b, const std::vector<T>& v) {
   PT_CUDA(b.alloc(v.size() * sizeof(T)));
@@ -385,7 +315,13 @@ int pt_scene_set_lights(pt_scene* s, const pt_light* l, int32_t n) {
 int pt_scene_set_camera(pt_scene* s, const pt_camera* cam) {
   if (!s || !cam) return PT_ERR_INVALID;
   s->camera = *cam;
-  if (s->committed) s->dev.camera = *cam;  // cheap to change after commit
+  if (s->committed) {
+    // Cheap to change after commit - unless the bounds of moving spheres depend on it: their boxes cover the
+    // shutter interval of the camera the BVH was built for (bvh_core.h prim_bounds), and a ray whose time lies
+    // outside it would silently miss them.  A changed interval therefore needs a new commit.
+    if (!s->moving_spheres.empty() && (cam->time0 != s->built_time0 || cam->time1 != s->built_time1)) s->committed = false;
+    else s->dev.camera = *cam;
+  }
   return PT_OK;
 }
 int pt_scene_set_miss(pt_scene* s, const pt_miss* miss) {
@@ -396,10 +332,13 @@ int pt_scene_set_miss(pt_scene* s, const pt_miss* miss) {
   }
   const bool tables_change = miss->env_nee != s->miss.env_nee || miss->image != s->miss.image ||
                              miss->type != s->miss.type || miss->spherical != s->miss.spherical;
+  const bool had_tables = s->dev.env_n > 0;
   s->miss = *miss;
   if (tables_change) {
     s->env_tables_valid = false;
-    if (miss->env_nee) s->committed = false;  // tables are uploaded by commit
+    // the alias tables are built by commit; a committed scene that has them (or now needs them) must not keep
+    // rendering with stale ones (env_nee_active() keys on dev.env_n)
+    if (miss->env_nee || had_tables) s->committed = false;
   }
   if (s->committed) s->dev.miss = *miss;
   return PT_OK;
@@ -413,6 +352,8 @@ int pt_scene_commit(pt_scene* s) {
     cudaGetLastError();
     return PT_ERR_CUDA;
   }
+  s->committed = false;  // a commit that fails midway leaves device buffers half replaced: renderers must refuse the scene
+  PT_CUDA(cudaGetDevice(&s->device));
   const int nm = (int)s->materials.size();
   if (s->prims.empty()) {
     pt_set_error("scene has no primitives");
@@ -478,12 +419,11 @@ int pt_scene_commit(pt_scene* s) {
     imgs.push_back(d);
   }
   if ((rc = upload_vec(s->d_images, imgs))) return rc;
-  if (!s->env_tables_valid) build_env_tables(s);
-  if ((rc = upload_vec(s->d_env_prob, s->env_alias_prob))) return rc;
-  if ((rc = upload_vec(s->d_env_idx, s->env_alias_idx))) return rc;
-  if ((rc = upload_vec(s->d_env_pdf, s->env_texel_pdf))) return rc;
+  if ((rc = pt_env_tables_build(s))) return rc;  // GPU construction (env_alias.cu); sets dev.env_n / env_w / env_h
 
   if ((rc = pt_bvh_build(s))) return rc;
+  s->built_time0 = s->camera.time0;
+  s->built_time1 = s->camera.time1;
 
   SceneDev& d = s->dev;
   d.nodes8 = s->d_nodes8.as<uint4>();
@@ -503,9 +443,6 @@ int pt_scene_commit(pt_scene* s) {
   d.env_alias_prob = s->d_env_prob.as<float>();
   d.env_alias_idx = s->d_env_idx.as<int>();
   d.env_texel_pdf = s->d_env_pdf.as<float>();
-  d.env_n = (int)s->env_alias_prob.size();
-  d.env_w = d.env_n ? s->images[s->miss.image].width : 0;
-  d.env_h = d.env_n ? s->images[s->miss.image].height : 0;
   d.tex_need_uv = 0;
   for (const pt_texture& t : s->textures) d.tex_need_uv |= t.type == PT_TEX_IMAGE;
   d.qbias = 0x47000000u;
@@ -559,7 +496,7 @@ int pt_scene_get_desc(const pt_scene* cs, pt_scene_desc* o) {
   o->lights = s->lights.data();
   o->camera = s->camera;
   o->miss = s->miss;
-  if (!s->env_tables_valid) build_env_tables(s);
+  if (!s->env_tables_valid && pt_env_tables_fetch(s)) return PT_ERR_CUDA;
   o->env_n = (int)s->env_alias_prob.size();
   o->env_alias_prob = s->env_alias_prob.data();
   o->env_alias_idx = s->env_alias_idx.data();

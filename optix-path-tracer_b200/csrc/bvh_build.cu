@@ -6,9 +6,11 @@
 // (host_includes/scenes.hpp:205 etc., "OptiX Building Time" main.cpp:99).
 #include <cub/cub.cuh>
 
+#include <algorithm>
 #include <cfloat>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 
 #include "scene_host.h"
 
@@ -126,9 +128,10 @@ __global__ void k_treelet_mark(Bvh2 t, int lo, long long hi, int* roots, int* n_
   if (i >= t.n - 1) return;
   if (treelet_is_root(t, i, lo, hi)) roots[atomicAdd(n_roots, 1)] = i;
 }
-__global__ void k_treelet_sah(Bvh2 t, int lo, const int* roots, int n_roots) {
+// the number of roots stays on the device: the grid covers the upper bound, surplus threads leave
+__global__ void k_treelet_sah(Bvh2 t, int lo, const int* roots, const int* n_roots) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n_roots) treelet_sah(t, roots[i], lo);
+  if (i < *n_roots) treelet_sah(t, roots[i], lo);
 }
 
 // SAH cost: sum of inner-node areas (C_trav = 1) + leaf areas (C_isect = 1), over root area
@@ -143,19 +146,29 @@ __global__ void k_sah_cost(Bvh2 t, double* out) {
   if ((threadIdx.x & 31) == 0 && a != 0.0) atomicAdd(out, a);
 }
 
-__global__ void k_collapse(Collapse c, const uint2* work, int n_work, uint2* out_work, int* out_count) {
+// one level of the collapse; level counts live on the device (level_count[l] = work items of level l)
+__global__ void k_collapse(Collapse c, const uint2* work, const int* n_work, uint2* out_work, int* out_count) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_work) return;
+  if (i >= *n_work) return;
   uint2 w = work[i];
   collapse_node(c, (int)w.x, (int)w.y, out_work, out_count);
 }
 
-template <typename T>
-int upload(DevBuf& b, const std::vector<T>& v) {
-  PT_CUDA(b.alloc(v.size() * sizeof(T)));
-  if (!v.empty()) PT_CUDA(cudaMemcpy(b.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
-  return PT_OK;
-}
+// Grow-only scratch arena of the build, one per device, kept for the life of the process: a 10 M-triangle build
+// takes ~1.3 GB of scratch in ~20 pieces, and allocating them afresh per commit made build time depend on what the
+// allocator had to map (collapse 7 ms or 74 ms between two runs of the same scene, round-1 finding).
+// pt_release_caches() returns it.
+struct Arena {
+  DevBuf buf;
+  size_t off = 0;
+  void* take(size_t bytes) {
+    off = (off + 255) & ~(size_t)255;
+    void* p = (char*)buf.p + off;
+    off += bytes;
+    return p;
+  }
+};
+Arena g_arena[PT_MAX_DEVICES];
 
 }  // namespace
 
@@ -184,11 +197,21 @@ struct StageTimer {  // PTB200_BUILD_TIMING=1 prints per-stage GPU time of the b
 };
 }  // namespace
 
+void pt_bvh_release_arenas() {
+  for (auto& a : g_arena) a.buf.release();
+}
+
 int pt_bvh_build(pt_scene* s) {
   const int n = (int)s->prims.size();
   StageTimer tm;
   if (n <= 0) {
     pt_set_error("scene has no primitives");
+    return PT_ERR_INVALID;
+  }
+  int dev = 0;
+  PT_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= PT_MAX_DEVICES) {
+    pt_set_error("device ordinal %d outside the supported range", dev);
     return PT_ERR_INVALID;
   }
   cudaEvent_t ev0, ev1;
@@ -211,64 +234,80 @@ int pt_bvh_build(pt_scene* s) {
   in.materials = s->d_materials.as<pt_material>();
   in.n = n;
 
-  DevBuf plo, phi, sbounds, keys, keys2, vals, vals2, cubtmp;
-  DevBuf nodes2, parent, leaf_parent, count, flag, roots, counters, cost;
-  PT_CUDA(plo.alloc((size_t)n * 16));
-  PT_CUDA(phi.alloc((size_t)n * 16));
-  PT_CUDA(sbounds.alloc(8 * 4));
-  {
-    float init[8] = {FLT_MAX, FLT_MAX, FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX, 0.f, 0.f};
-    PT_CUDA(cudaMemcpy(sbounds.p, init, sizeof(init), cudaMemcpyHostToDevice));
-  }
-  k_prim_bounds<<<nblk(n), TB>>>(in, plo.as<float4>(), phi.as<float4>(), sbounds.as<float>());
-  PT_CUDA(cudaGetLastError());
-  k_pad_bounds<<<nblk(n), TB>>>(n, plo.as<float4>(), phi.as<float4>(), sbounds.as<float>());
-  PT_CUDA(cudaGetLastError());
-
-  tm.mark("bounds");
-  PT_CUDA(keys.alloc((size_t)n * 8));
-  PT_CUDA(keys2.alloc((size_t)n * 8));
-  PT_CUDA(vals.alloc((size_t)n * 4));
-  PT_CUDA(vals2.alloc((size_t)n * 4));
-  k_morton<<<nblk(n), TB>>>(n, plo.as<float4>(), phi.as<float4>(), sbounds.as<float>(), keys.as<uint64_t>(),
-                            vals.as<uint32_t>());
-  PT_CUDA(cudaGetLastError());
-  {
-    size_t tmp = 0;
-    PT_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp, keys.as<uint64_t>(), keys2.as<uint64_t>(),
-                                            vals.as<uint32_t>(), vals2.as<uint32_t>(), n, 0, 63));
-    PT_CUDA(cubtmp.alloc(tmp));
-    PT_CUDA(cub::DeviceRadixSort::SortPairs(cubtmp.p, tmp, keys.as<uint64_t>(), keys2.as<uint64_t>(),
-                                            vals.as<uint32_t>(), vals2.as<uint32_t>(), n, 0, 63));
-  }
-
-  tm.mark("morton+sort");
+  // ---- scratch: one arena, carved once; nothing below allocates or talks to the host until the end ----
   const int ni = n > 1 ? n - 1 : 1;
-  PT_CUDA(nodes2.alloc((size_t)ni * sizeof(Bvh2Node)));
-  PT_CUDA(parent.alloc((size_t)ni * 4));
-  PT_CUDA(leaf_parent.alloc((size_t)n * 4));
-  PT_CUDA(count.alloc((size_t)ni * 4));
-  PT_CUDA(flag.alloc((size_t)ni * 4));
-  PT_CUDA(cudaMemset(flag.p, 0, (size_t)ni * 4));
-  PT_CUDA(cudaMemset(leaf_parent.p, 0xff, (size_t)n * 4));
-  PT_CUDA(cudaMemset(parent.p, 0xff, (size_t)ni * 4));
-  PT_CUDA(cudaMemset(count.p, 0, (size_t)ni * 4));
+  size_t cub_bytes = 0;
+  PT_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const uint64_t*)nullptr, (uint64_t*)nullptr,
+                                          (const uint32_t*)nullptr, (uint32_t*)nullptr, n, 0, 63));
+  const size_t n8 = (size_t)(n > 1 ? n : 2);
+  const size_t need = (size_t)n * (16 + 16 + 8 + 8 + 4 + 4 + 4 + 8 + 8) + (size_t)ni * (sizeof(Bvh2Node) + 4 + 4 + 4 + 4) +
+                      n8 * 80 + cub_bytes + 64 * 256 + 4096;
+  Arena& ar = g_arena[dev];
+  if (ar.buf.bytes < need) PT_CUDA(ar.buf.alloc(need + need / 8));
+  ar.off = 0;
+  float4* plo = (float4*)ar.take((size_t)n * 16);
+  float4* phi = (float4*)ar.take((size_t)n * 16);
+  uint64_t* keys = (uint64_t*)ar.take((size_t)n * 8);
+  uint64_t* keys2 = (uint64_t*)ar.take((size_t)n * 8);
+  uint32_t* vals = (uint32_t*)ar.take((size_t)n * 4);
+  uint32_t* vals2 = (uint32_t*)ar.take((size_t)n * 4);
+  void* cubtmp = ar.take(cub_bytes);
+  Bvh2Node* nodes2 = (Bvh2Node*)ar.take((size_t)ni * sizeof(Bvh2Node));
+  int* parent = (int*)ar.take((size_t)ni * 4);
+  int* leaf_parent = (int*)ar.take((size_t)n * 4);
+  int* count = (int*)ar.take((size_t)ni * 4);
+  int* flag = (int*)ar.take((size_t)ni * 4);
+  int* roots = (int*)ar.take((size_t)ni * 4);
+  uint2* wa = (uint2*)ar.take((size_t)n * 8 + 64);
+  uint2* wb = (uint2*)ar.take((size_t)n * 8 + 64);
+  uint4* nodes8_tmp = (uint4*)ar.take(n8 * 80);
+  // small device-resident state, zeroed once:
+  //   [0..7] scene bounds (floats)   [8..15] treelet root counts per pass   [16] BVH8 node counter
+  //   [17] leaf counter   [32..32+MAXLEV] collapse work count per level   doubles at byte 1024: SAH sums
+  constexpr int MAXLEV = 160;
+  int* st = (int*)ar.take(2048);
+  float* sbounds = (float*)st;
+  int* pass_roots = st + 8;
+  int* d_cnt = st + 16;
+  int* level_count = st + 32;
+  double* cost = (double*)((char*)st + 1024);
+  {
+    int init[512];
+    memset(init, 0, sizeof(init));
+    const float fb[8] = {FLT_MAX, FLT_MAX, FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX, 0.f, 0.f};
+    memcpy(init, fb, sizeof(fb));
+    init[16] = 1;        // node 0 is the root
+    init[32] = 1;        // level 0 holds one work item
+    PT_CUDA(cudaMemcpyAsync(st, init, sizeof(init), cudaMemcpyHostToDevice, 0));
+  }
+
+  k_prim_bounds<<<nblk(n), TB>>>(in, plo, phi, sbounds);
+  PT_CUDA(cudaGetLastError());
+  k_pad_bounds<<<nblk(n), TB>>>(n, plo, phi, sbounds);
+  PT_CUDA(cudaGetLastError());
+  tm.mark("bounds");
+  k_morton<<<nblk(n), TB>>>(n, plo, phi, sbounds, keys, vals);
+  PT_CUDA(cudaGetLastError());
+  PT_CUDA(cub::DeviceRadixSort::SortPairs(cubtmp, cub_bytes, keys, keys2, vals, vals2, n, 0, 63));
+  tm.mark("morton+sort");
+
+  PT_CUDA(cudaMemsetAsync(flag, 0, (size_t)ni * 4, 0));
+  PT_CUDA(cudaMemsetAsync(leaf_parent, 0xff, (size_t)n * 4, 0));
+  PT_CUDA(cudaMemsetAsync(parent, 0xff, (size_t)ni * 4, 0));
+  PT_CUDA(cudaMemsetAsync(count, 0, (size_t)ni * 4, 0));
 
   Bvh2 t;
-  t.nodes = nodes2.as<Bvh2Node>();
-  t.parent = parent.as<int>();
-  t.leaf_parent = leaf_parent.as<int>();
-  t.count = count.as<int>();
-  t.flag = flag.as<int>();
-  t.keys = keys2.as<uint64_t>();
-  t.sorted = vals2.as<uint32_t>();
-  t.plo = plo.as<float4>();
-  t.phi = phi.as<float4>();
+  t.nodes = nodes2;
+  t.parent = parent;
+  t.leaf_parent = leaf_parent;
+  t.count = count;
+  t.flag = flag;
+  t.keys = keys2;
+  t.sorted = vals2;
+  t.plo = plo;
+  t.phi = phi;
   t.n = n;
 
-  double cost_lbvh = 0.0, cost_ref = 0.0;
-  PT_CUDA(counters.alloc(64));
-  PT_CUDA(cost.alloc(16));
   if (n > 1) {
     k_karras<<<nblk(n - 1), TB>>>(t);
     PT_CUDA(cudaGetLastError());
@@ -276,97 +315,83 @@ int pt_bvh_build(pt_scene* s) {
     k_refit<<<nblk(n), TB>>>(t);
     PT_CUDA(cudaGetLastError());
     tm.mark("refit");
-
-    PT_CUDA(cudaMemset(cost.p, 0, 16));
-    k_sah_cost<<<nblk(n - 1), TB>>>(t, cost.as<double>());
-    // treelet refinement
-    PT_CUDA(roots.alloc((size_t)ni * 4));
+    k_sah_cost<<<nblk(n - 1), TB>>>(t, cost);
     // hierarchical passes: leaves -> treelets of <= 64 leaves -> treelets of <= 64 treelets -> ...
+    // A pass-k root has more than lo_k leaves and disjoint subtrees, so there are at most n / lo_k of them:
+    // the grid is sized for that bound and the actual count never leaves the device.
     long long lo = 1, hi = PT_TREELET;
     for (int pass = 0; pass < 8 && lo < (long long)n; pass++) {
-      PT_CUDA(cudaMemset(counters.p, 0, 64));
-      k_treelet_mark<<<nblk(n - 1), TB>>>(t, (int)lo, hi, roots.as<int>(), counters.as<int>());
+      k_treelet_mark<<<nblk(n - 1), TB>>>(t, (int)lo, hi, roots, pass_roots + pass);
       PT_CUDA(cudaGetLastError());
-      int n_roots = 0;
-      PT_CUDA(cudaMemcpy(&n_roots, counters.p, 4, cudaMemcpyDeviceToHost));
-      if (n_roots > 0) {
-        k_treelet_sah<<<nblk(n_roots, 64), 64>>>(t, (int)lo, roots.as<int>(), n_roots);
-        PT_CUDA(cudaGetLastError());
-      }
+      const long long bound = std::min<long long>(n - 1, (long long)n / lo + 1);
+      k_treelet_sah<<<nblk(bound, 64), 64>>>(t, (int)lo, roots, pass_roots + pass);
+      PT_CUDA(cudaGetLastError());
       lo = hi;
       hi *= PT_TREELET;
     }
     tm.mark("treelet sah");
-    k_sah_cost<<<nblk(n - 1), TB>>>(t, cost.as<double>() + 1);
+    k_sah_cost<<<nblk(n - 1), TB>>>(t, cost + 1);
+  }
+
+  // collapse: level-synchronous work lists; the per-level counts stay on the device.  An inner BVH8 child holds
+  // more than 3 primitives, so a level has at most min(8^l, n / 4 + 1) items: launch for that bound.  Levels are
+  // launched in batches of 16 and the host looks at the counters once per batch (usually once in total).
+  PT_CUDA(s->d_leaves.alloc((size_t)n * sizeof(LeafRec)));
+  PT_CUDA(s->d_prim_leaf.alloc((size_t)n * 4));
+  Collapse c;
+  c.t = t;
+  c.in = in;
+  c.nodes8 = nodes8_tmp;
+  c.leaves = s->d_leaves.as<LeafRec>();
+  c.prim_leaf = s->d_prim_leaf.as<int>();
+  c.node_counter = d_cnt;
+  c.leaf_counter = d_cnt + 1;
+  const uint2 first = make_uint2(n > 1 ? 0u : (uint32_t)~0, 0u);  // n == 1: leaf ref ~0
+  PT_CUDA(cudaMemcpyAsync(wa, &first, sizeof(first), cudaMemcpyHostToDevice, 0));
+  int level = 0;
+  int h_state[2 + MAXLEV + 32];
+  for (;;) {
+    for (int k = 0; k < 16 && level < MAXLEV; k++, level++) {
+      long long bound = (long long)n / 4 + 1;
+      if (level < 10) bound = std::min<long long>(bound, 1ll << (3 * level));
+      k_collapse<<<nblk(bound, 128), 128>>>(c, wa, level_count + level, wb, level_count + level + 1);
+      PT_CUDA(cudaGetLastError());
+      std::swap(wa, wb);
+    }
+    PT_CUDA(cudaMemcpy(h_state, d_cnt, sizeof(int) * (16 + level + 2), cudaMemcpyDeviceToHost));
+    if (h_state[16 + level] == 0) break;  // the last level launched produced no work
+    if (level >= MAXLEV) {
+      pt_set_error("BVH collapse did not terminate");
+      return PT_ERR_INVALID;
+    }
+  }
+  tm.mark("collapse");
+  const int hcnt[2] = {h_state[0], h_state[1]};
+  if (hcnt[1] != n) {
+    pt_set_error("BVH collapse wrote %d leaf records for %d primitives", hcnt[1], n);
+    return PT_ERR_INVALID;
+  }
+  // the node array at its final size
+  PT_CUDA(s->d_nodes8.alloc((size_t)hcnt[0] * 80));
+  PT_CUDA(cudaMemcpyAsync(s->d_nodes8.p, nodes8_tmp, (size_t)hcnt[0] * 80, cudaMemcpyDeviceToDevice, 0));
+  double cost_lbvh = 0.0, cost_ref = 0.0;
+  if (n > 1) {
     double hc[2];
-    PT_CUDA(cudaMemcpy(hc, cost.p, 16, cudaMemcpyDeviceToHost));
     Bvh2Node root;
-    PT_CUDA(cudaMemcpy(&root, nodes2.p, sizeof(root), cudaMemcpyDeviceToHost));
+    PT_CUDA(cudaMemcpy(hc, cost, 16, cudaMemcpyDeviceToHost));
+    PT_CUDA(cudaMemcpy(&root, nodes2, sizeof(root), cudaMemcpyDeviceToHost));
     double ra = (double)box_half_area(f3(root.lo[0], root.lo[1], root.lo[2]), f3(root.hi[0], root.hi[1], root.hi[2]));
     if (ra > 0.0) {
       cost_lbvh = hc[0] / ra;
       cost_ref = hc[1] / ra;
     }
   }
-
-  // collapse: level-synchronous work lists
-  PT_CUDA(s->d_nodes8.alloc((size_t)(n > 1 ? n : 2) * 80));
-  PT_CUDA(s->d_leaves.alloc((size_t)n * sizeof(LeafRec)));
-  PT_CUDA(s->d_prim_leaf.alloc((size_t)n * 4));
-  DevBuf workA, workB;
-  PT_CUDA(workA.alloc((size_t)n * 8 + 64));
-  PT_CUDA(workB.alloc((size_t)n * 8 + 64));
-  Collapse c;
-  c.t = t;
-  c.in = in;
-  c.nodes8 = s->d_nodes8.as<uint4>();
-  c.leaves = s->d_leaves.as<LeafRec>();
-  c.prim_leaf = s->d_prim_leaf.as<int>();
-  int* d_cnt = counters.as<int>();  // [0]=node counter [1]=leaf counter [2]=work count
-  {
-    int init[3] = {1, 0, 0};
-    PT_CUDA(cudaMemcpy(d_cnt, init, sizeof(init), cudaMemcpyHostToDevice));
-  }
-  c.node_counter = d_cnt;
-  c.leaf_counter = d_cnt + 1;
-  uint2 first = make_uint2(n > 1 ? 0u : (uint32_t)~0, 0u);  // n==1: leaf ref ~0
-  PT_CUDA(cudaMemcpy(workA.p, &first, sizeof(first), cudaMemcpyHostToDevice));
-  int n_work = 1;
-  uint2* wa = workA.as<uint2>();
-  uint2* wb = workB.as<uint2>();
-  int levels = 0;
-  while (n_work > 0) {
-    PT_CUDA(cudaMemset(d_cnt + 2, 0, 4));
-    k_collapse<<<nblk(n_work, 128), 128>>>(c, wa, n_work, wb, d_cnt + 2);
-    PT_CUDA(cudaGetLastError());
-    PT_CUDA(cudaMemcpy(&n_work, d_cnt + 2, 4, cudaMemcpyDeviceToHost));
-    std::swap(wa, wb);
-    if (++levels > 128) {
-      pt_set_error("BVH collapse did not terminate");
-      return PT_ERR_INVALID;
-    }
-  }
-  tm.mark("collapse");
-  int hcnt[2];
-  PT_CUDA(cudaMemcpy(hcnt, d_cnt, 8, cudaMemcpyDeviceToHost));
   PT_CUDA(cudaEventRecord(ev1));
   PT_CUDA(cudaEventSynchronize(ev1));
   float ms = 0.f;
   PT_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
   cudaEventDestroy(ev0);
   cudaEventDestroy(ev1);
-  if (hcnt[1] != n) {
-    pt_set_error("BVH collapse wrote %d leaf records for %d primitives", hcnt[1], n);
-    return PT_ERR_INVALID;
-  }
-  // shrink the node array to its final size
-  {
-    DevBuf tight;
-    PT_CUDA(tight.alloc((size_t)hcnt[0] * 80));
-    PT_CUDA(cudaMemcpy(tight.p, s->d_nodes8.p, (size_t)hcnt[0] * 80, cudaMemcpyDeviceToDevice));
-    std::swap(tight.p, s->d_nodes8.p);
-    std::swap(tight.bytes, s->d_nodes8.bytes);
-  }
   s->info.n_prims = n;
   s->info.n_bvh2_nodes = n > 1 ? n - 1 : 0;
   s->info.n_bvh8_nodes = hcnt[0];

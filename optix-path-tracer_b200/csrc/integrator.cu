@@ -14,16 +14,22 @@
 //   k_shadow       shadow traversal + resolve + Russian roulette
 // Path state moves with the queue (double-buffered pool of 64-byte records, 4
 // float4 per path; shadow requests one array per float4), so appends are
-// coalesced 128-bit stores; only the material-sorted shade kernels gather.  No host synchronisation inside an iteration; the host polls the
-// control block every few iterations to detect completion.
+// coalesced 128-bit stores; only the material-sorted shade kernels gather.
+// Completion: k_iter_begin publishes its loop state in the first line of the control block and the host reads
+// it with asynchronous copies that trail the launches by one batch, so the GPU never waits for the host.  Once
+// every sample has been generated and at most PT_DRAIN_MAX paths are alive, one k_drain launch runs each of them
+// to its end in a single thread (trace + shade + shadow in one loop) instead of ~45 nearly empty wavefront
+// iterations of six or more kernels each.
 #include <cooperative_groups.h>
 
 #include <algorithm>
+#include <mutex>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
 
+#include "renderer_internal.h"
 #include "scene_host.h"
 #include "shading.h"
 #include "trace_sched.cuh"
@@ -93,7 +99,7 @@ struct alignas(PT_CTR_STRIDE) PaddedInt {
   int pad[PT_CTR_STRIDE / 4 - 1];
 };
 struct alignas(PT_CTR_STRIDE) Ctrl {
-  // written by k_iter_begin only, read as loop bounds
+  // written by k_iter_begin only, read as loop bounds; the first 64 bytes are what the host polls
   int n_cur, gen_base, gen_n;
   int first_frame;
   unsigned long long sample_base, next_sample, total_samples;
@@ -104,6 +110,11 @@ struct alignas(PT_CTR_STRIDE) Ctrl {
   alignas(PT_CTR_STRIDE) unsigned long long stat_nodes;
   alignas(PT_CTR_STRIDE) unsigned long long stat_leaves;
   alignas(PT_CTR_STRIDE) int error;  // 1 = traversal stack overflow
+};
+// what the host polls: the leading bytes of Ctrl, written by k_iter_begin
+struct CtrlPoll {
+  int n_cur, gen_base, gen_n, first_frame;
+  unsigned long long sample_base, next_sample, total_samples;
 };
 #define n_next n_next_.v
 #define n_shadow n_shadow_.v
@@ -153,17 +164,16 @@ __device__ __forceinline__ int push_slot(int* counter) {
   return base + (int)g.thread_rank();
 }
 
-// raygen.cu:97-118 tail of one loop iteration: Russian roulette, depth cut-off,
-// then either accumulate or append the path to the next wavefront
-__device__ __forceinline__ void finish_bounce(const Params& p, Ctrl* c, const PathBuf& next, uint32_t pix,
-                                              int depth, float3 o, float3 d, float3 thr, float3 rad,
-                                              uint32_t seed, bool specular, float pdf, float time) {
+// raygen.cu:97-118 tail of one loop iteration: Russian roulette and the depth cut-off.  Returns true when
+// the path continues (thr, depth, seed updated); otherwise the sample has been accumulated.
+__device__ __forceinline__ bool bounce_survives(const Params& p, uint32_t pix, int& depth, float3& thr, float3 rad,
+                                                uint32_t& seed) {
   if (p.russian) {
     float prob = pt_ffmax(pt_ffmax(thr.x, thr.y), thr.z);
     if (depth > 10) {
       if (pt_rnd(seed) >= prob) {
         accumulate(p, pix, rad + thr);
-        return;
+        return false;
       }
       thr *= 1.f / prob;
     }
@@ -171,8 +181,15 @@ __device__ __forceinline__ void finish_bounce(const Params& p, Ctrl* c, const Pa
   depth++;
   if (depth >= p.max_depth) {  // raygen.cu:122: recursion did not terminate -> black
     accumulate(p, pix, f3(0.f));
-    return;
+    return false;
   }
+  return true;
+}
+// ... then the path is appended to the next wavefront
+__device__ __forceinline__ void finish_bounce(const Params& p, Ctrl* c, const PathBuf& next, uint32_t pix,
+                                              int depth, float3 o, float3 d, float3 thr, float3 rad,
+                                              uint32_t seed, bool specular, float pdf, float time) {
+  if (!bounce_survives(p, pix, depth, thr, rad, seed)) return;
   int slot = push_slot(&c->n_next);
   next.f(P_OSEED, slot) = make_float4(o.x, o.y, o.z, __uint_as_float(seed));
   next.f(P_DPACK, slot) = make_float4(d.x, d.y, d.z, __uint_as_float(pack_state(pix, depth, specular)));
@@ -513,6 +530,122 @@ __global__ void __launch_bounds__(PT_TRACE_THREADS, PT_TRACE_MINBLOCKS) k_trace_
   }
 }
 
+
+// ---- drain: the last few thousand paths, one thread each, run to their end -------------------------------
+// After the last sample has been generated a render used to finish in ~45 nearly empty wavefront iterations (a few
+// paths survive Russian roulette up to depth 50): each costs the dependent latency of one traversal plus six or
+// more kernel boundaries, ~2 % of a C2 step and far more of a short per-rank step under a sample split.  Here each
+// surviving path is walked by one thread through the same functions the wavefront kernels call (bvh8_closest is
+// the single-ray loop over the same node / leaf steps; shade_hit / shade_miss / bounce_survives are shared), so
+// the RNG stream and every arithmetic operation of a path are unchanged.
+#ifndef PT_DRAIN_MAX
+#define PT_DRAIN_MAX 16384
+#endif
+template <int LK>
+__device__ __noinline__ void drain_shade(const SceneDev& sc, int mat, const PathIn& in, const TraceHit& h, ShadeOut& out) {
+  switch (mat) {
+    case PT_MAT_LAMBERTIAN: shade_hit<PT_MAT_LAMBERTIAN, LK>(sc, in, h.t, h.leaf, h.u, h.v, out); break;
+    case PT_MAT_METAL: shade_hit<PT_MAT_METAL, 0>(sc, in, h.t, h.leaf, h.u, h.v, out); break;
+    case PT_MAT_DIELECTRIC: shade_hit<PT_MAT_DIELECTRIC, 0>(sc, in, h.t, h.leaf, h.u, h.v, out); break;
+    case PT_MAT_DIFFUSE_LIGHT: shade_hit<PT_MAT_DIFFUSE_LIGHT, LK>(sc, in, h.t, h.leaf, h.u, h.v, out); break;
+    case PT_MAT_OREN_NAYAR: shade_hit<PT_MAT_OREN_NAYAR, LK>(sc, in, h.t, h.leaf, h.u, h.v, out); break;
+    case PT_MAT_TORRANCE_SPARROW: shade_hit<PT_MAT_TORRANCE_SPARROW, 0>(sc, in, h.t, h.leaf, h.u, h.v, out); break;
+    case PT_MAT_ASHIKHMIN_SHIRLEY: shade_hit<PT_MAT_ASHIKHMIN_SHIRLEY, 0>(sc, in, h.t, h.leaf, h.u, h.v, out); break;
+    case PT_MAT_NORMAL: shade_hit<PT_MAT_NORMAL, 0>(sc, in, h.t, h.leaf, h.u, h.v, out); break;
+    default: shade_hit<PT_MAT_ISOTROPIC, LK>(sc, in, h.t, h.leaf, h.u, h.v, out); break;
+  }
+}
+
+template <int LK>
+__global__ void __launch_bounds__(64) k_drain(SceneDev sc, Params p, Ctrl* c, PathBuf cur, int count_fetches) {
+  const int n = c->n_next;  // survivors of the last wavefront iteration, appended to `cur`
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 o4 = cur.f(P_OSEED, i), d4 = cur.f(P_DPACK, i), t4 = cur.f(P_THR, i), r4 = cur.f(P_RAD, i);
+  const uint32_t pk = __float_as_uint(d4.w);
+  const uint32_t pix = pk & 0x7fffffu;
+  PathIn in;
+  in.o = f3(o4.x, o4.y, o4.z);
+  in.d = f3(d4.x, d4.y, d4.z);
+  in.thr = f3(t4.x, t4.y, t4.z);
+  in.rad = f3(r4.x, r4.y, r4.z);
+  in.seed = __float_as_uint(o4.w);
+  in.depth = (pk >> 23) & 0xff;
+  in.prev_specular = (pk >> 31) != 0;
+  in.last_pdf = t4.w;
+  in.time = r4.w;
+  uint32_t q_closest = 0, q_shadow = 0, cn = 0, cl = 0;
+  int overflow = 0;
+  for (;;) {
+    TraceHit h;
+    q_closest++;
+    bvh8_closest<true>(sc, in.o, in.d, in.depth == 0 ? 1e-6f : 1e-3f, PT_RAY_MAX, h, cn, cl, RayAux{in.time, in.seed}, &overflow);
+    if (h.leaf < 0) {
+      accumulate(p, pix, shade_miss(sc, in));
+      break;
+    }
+    const int mat = (int)(__float_as_uint(__ldg(&sc.leaves[h.leaf].c.w)) >> 24);
+    ShadeOut out;
+    drain_shade<LK>(sc, mat, in, h, out);
+    if (out.kind == SH_TERMINATE) {
+      accumulate(p, pix, out.col);
+      break;
+    }
+    float3 dir = out.dir, thr = out.thr, rad = out.rad;
+    uint32_t seed = out.seed;
+    bool specular = out.specular;
+    float pdf = out.pdf;
+    if (out.kind == SH_SHADOW) {  // ShadowPolicy::emit, inline
+      q_shadow++;
+      TraceHit sh;
+      bvh8_closest<true>(sc, out.P, out.WiL, 1e-3f, PT_RAY_MAX, sh, cn, cl, RayAux{in.time, out.seedShadow}, &overflow);
+      const bool env = out.env_shadow && out.pdf >= 0.f;  // the request's tag (k_shade: s6.w = env ? pdf : -1)
+      bool visible = env ? sh.leaf < 0 : false;
+      if (!env && sh.leaf >= 0)
+        visible = (__float_as_uint(__ldg(&sc.leaves[sh.leaf].c.w)) >> 24) == PT_MAT_DIFFUSE_LIGHT;
+      if (!visible) {
+        dir = out.dirS;
+        thr = out.thrS;
+        rad = out.radS;
+        seed = out.seedS;
+      }
+      if (out.terminal) {
+        accumulate(p, pix, rad);
+        break;
+      }
+      specular = false;
+      pdf = env ? out.pdf : 0.f;
+    }
+    int depth = in.depth;
+    if (!bounce_survives(p, pix, depth, thr, rad, seed)) break;
+    in.o = out.P;
+    in.d = dir;
+    in.thr = thr;
+    in.rad = rad;
+    in.seed = seed;
+    in.depth = depth;
+    in.prev_specular = specular;
+    in.last_pdf = pdf;
+  }
+  atomicAdd(&c->stat_closest, (unsigned long long)q_closest);
+  if (q_shadow) atomicAdd(&c->stat_shadow, (unsigned long long)q_shadow);
+  if (count_fetches) {
+    atomicAdd(&c->stat_nodes, (unsigned long long)cn);
+    atomicAdd(&c->stat_leaves, (unsigned long long)cl);
+  }
+  if (overflow) atomicExch(&c->error, 1);
+}
+// after the drain nothing is alive
+__global__ void k_drain_end(Ctrl* c) {
+  c->n_next = 0;
+  c->n_cur = 0;
+}
+
+// raygen.cu:76,122 with maxDepth == 0: the loop body never runs, every sample is black but still counted
+__global__ void k_count_samples(float4* accum, int n, float nframes) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) accum[i].w += nframes;
+}
+
 // make_Color (raygen.cu:136-146): the preview pixel of the display buffer
 __global__ void k_display(const float4* __restrict__ accum, uchar4* __restrict__ out, int n) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -526,15 +659,21 @@ __global__ void k_display(const float4* __restrict__ accum, uchar4* __restrict__
   }
 }
 
-int g_sm_count = 0;
+// per-device caches, indexed by device ordinal (a multi-GPU renderer drives several devices from one process)
+int g_sm_count[PT_MAX_DEVICES] = {};
+int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return dev >= 0 && dev < PT_MAX_DEVICES ? dev : 0;
+}
 int sm_count() {
-  if (!g_sm_count) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
-    if (g_sm_count <= 0) g_sm_count = 148;
+  int dev = current_device();
+  if (!g_sm_count[dev]) {
+    int n = 0;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    g_sm_count[dev] = n > 0 ? n : 148;
   }
-  return g_sm_count;
+  return g_sm_count[dev];
 }
 
 // scheduler knobs; PTB200_REFILL_MIN / PTB200_LEAF_THRESH override the tuned defaults (dev only)
@@ -572,9 +711,9 @@ SchedParams sched_params_rays(const SceneDev& sc) {
 }
 
 // resident CTAs per SM of the persistent traversal kernels (they must all be co-resident)
-int g_trace_bpm[2] = {0, 0};
+int g_trace_bpm[PT_MAX_DEVICES][2] = {};
 int trace_blocks_per_sm(bool special) {
-  int& bpm = g_trace_bpm[special ? 1 : 0];
+  int& bpm = g_trace_bpm[current_device()][special ? 1 : 0];
   if (!bpm) {
     int a = 0, b = 0, c = 0, d = 0;
     if (special) {
@@ -613,6 +752,7 @@ int trace_blocks_per_sm(bool special) {
 // ---------------------------------------------------------------------------------------------
 struct pt_renderer {
   pt_scene* scene = nullptr;
+  int device = 0;  // the device everything below lives on (= the scene's)
   int W = 0, H = 0;
   int flags = 0;
   long long pool_req = 0;
@@ -626,7 +766,7 @@ struct pt_renderer {
   float4 *pathA[4] = {}, *pathB[4] = {}, *shadow[NSHADOW] = {}, *hits = nullptr;  // AoS: element [0] is the base
   uint32_t* bin_q = nullptr;
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_poll[2] = {nullptr, nullptr};
   bool started = false;
   // the wavefront iteration captured as two CUDA graphs (pools A->B and B->A), reused across
   // pt_render calls while the launch parameters stay the same
@@ -635,16 +775,21 @@ struct pt_renderer {
   unsigned long long g_commit_gen = 0;
   SceneDev g_scene{};  // kernel arguments are baked into the graphs: re-capture when they change
   pt_stats stats{};
-  Ctrl* h_ctrl = nullptr;  // pinned
+  // pinned host memory of this renderer: the full control block (final statistics), two poll records that
+  // trail the launches, and the staging buffer of pt_read_accum for pageable destinations (grow-only)
+  Ctrl* h_ctrl = nullptr;
+  CtrlPoll* h_poll = nullptr;
+  float* stage = nullptr;
+  size_t stage_bytes = 0;
+  pt_multi* multi = nullptr;  // != null: this handle fans out to one renderer per device (multi.cu)
 };
 
-// Process-level caches (the library is driven by one host thread, like the reference).
-//  * the path-pool slab of a destroyed renderer is parked here and handed to the next one: creating a
-//    renderer per job otherwise frees and re-allocates 2-3 GB each time, and the stream-ordered allocator
-//    answered that churn with re-mapping stalls of 100-700 ms (seen as e2e C4 1346 -> 1053 Msamples/s);
-//  * one pinned control-block mirror for all renderers (pinning / unpinning synchronises the device).
-static DevBuf g_slab_cache;
-static Ctrl* g_hctrl = nullptr;
+// Process-level cache (guarded by a mutex; one slot per device): the path-pool slab of a destroyed renderer is
+// parked and handed to the next renderer on the same device.  Creating a renderer per job otherwise frees and
+// re-allocates 2-3 GB each time, and the stream-ordered allocator answered that churn with re-mapping stalls of
+// 100-700 ms (seen as e2e C4 1346 -> 1053 Msamples/s).  pt_release_caches() empties it.
+static DevBuf g_slab_cache[PT_MAX_DEVICES];
+static std::mutex g_cache_mu;
 
 static int ensure_pool(pt_renderer* r, long long want) {
   long long npix = (long long)r->W * r->H;
@@ -659,12 +804,16 @@ static int ensure_pool(pt_renderer* r, long long want) {
   const size_t gap = 64 * 1024;
   const int n_arr = 4 + 4 + NSHADOW + NBINS;
   const size_t total = (arr + gap + 7 * skew + 256) * n_arr + (size_t)pool * 4 * NBINS + 64 * 1024;
-  if (g_slab_cache.p && g_slab_cache.bytes >= total && !r->slab.p) {
-    std::swap(r->slab.p, g_slab_cache.p);
-    std::swap(r->slab.bytes, g_slab_cache.bytes);
-  } else {
-    PT_CUDA(r->slab.alloc(total));
+  {
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    DevBuf& parked = g_slab_cache[r->device];
+    if (parked.p && parked.bytes >= total && !r->slab.p) {
+      std::swap(r->slab.p, parked.p);
+      std::swap(r->slab.bytes, parked.bytes);
+      std::swap(r->slab.dev, parked.dev);
+    }
   }
+  if (!r->slab.p || r->slab.bytes < total) PT_CUDA(r->slab.alloc(total));
   char* base = r->slab.as<char>();
   size_t off = 0;
   int k = 0;
@@ -696,6 +845,58 @@ static int ensure_pool(pt_renderer* r, long long want) {
   return PT_OK;
 }
 
+// ---- internal accessors for multi.cu ------------------------------------------------------------------
+float4* pt_r_accum(pt_renderer* r) { return r->accum; }
+cudaStream_t pt_r_stream(pt_renderer* r) { return r->stream; }
+int pt_r_device(pt_renderer* r) { return r->device; }
+int pt_r_width(pt_renderer* r) { return r->W; }
+int pt_r_height(pt_renderer* r) { return r->H; }
+void pt_r_mark_started(pt_renderer* r) { r->started = true; }
+void pt_r_set_ms_reduce(pt_renderer* r, float ms) { r->stats.ms_reduce = ms; }
+pt_multi* pt_r_multi(pt_renderer* r) { return r->multi; }
+pt_renderer* pt_r_new_multi_handle(pt_scene* scene, int w, int h, pt_multi* m) {
+  pt_renderer* r = new pt_renderer();
+  r->scene = scene;
+  r->W = w;
+  r->H = h;
+  r->multi = m;
+  return r;
+}
+void pt_r_delete_handle(pt_renderer* r) { delete r; }
+void pt_release_slab_cache() {
+  std::lock_guard<std::mutex> lk(g_cache_mu);
+  for (auto& b : g_slab_cache) b.release();
+}
+
+namespace {
+// ends a stream capture that an error interrupted, so the stream is usable again
+struct CaptureGuard {
+  cudaStream_t st;
+  bool active = false;
+  ~CaptureGuard() {
+    if (!active) return;
+    cudaGraph_t g = nullptr;
+    cudaStreamEndCapture(st, &g);
+    if (g) cudaGraphDestroy(g);
+    cudaGetLastError();
+  }
+};
+struct EventSet {  // per-kernel-class timing events of one pt_render call
+  cudaEvent_t e[6] = {};
+  ~EventSet() {
+    for (auto& ev : e)
+      if (ev) cudaEventDestroy(ev);
+  }
+};
+void drop_graphs(pt_renderer* r) {
+  for (auto& g : r->gexec) {
+    if (g) cudaGraphExecDestroy(g);
+    g = nullptr;
+  }
+  r->g_max_depth = -1;
+}
+}  // namespace
+
 extern "C" {
 
 int pt_renderer_create(pt_scene* scene, int32_t width, int32_t height, void* d_accum, pt_renderer** out) {
@@ -707,12 +908,14 @@ int pt_renderer_create(pt_scene* scene, int32_t width, int32_t height, void* d_a
     pt_set_error("pt_renderer_create: scene not committed");
     return PT_ERR_STATE;
   }
-  if ((long long)width * height > (1ll << 23)) {
-    pt_set_error("pt_renderer_create: more than 2^23 pixels");
+  if ((long long)width * height > PT_MAX_PIXELS) {
+    pt_set_error("pt_renderer_create: more than 2^23 pixels (the path state packs the pixel index into 23 bits)");
     return PT_ERR_INVALID;
   }
+  DeviceGuard dg(scene->device);
   pt_renderer* r = new pt_renderer();
   r->scene = scene;
+  r->device = scene->device >= 0 && scene->device < PT_MAX_DEVICES ? scene->device : 0;
   r->W = width;
   r->H = height;
   if (d_accum) {
@@ -728,27 +931,44 @@ int pt_renderer_create(pt_scene* scene, int32_t width, int32_t height, void* d_a
   if (cudaMemset(r->accum, 0, (size_t)width * height * 16) != cudaSuccess ||
       r->ctrl.alloc(sizeof(Ctrl)) != cudaSuccess || cudaStreamCreate(&r->stream) != cudaSuccess ||
       cudaEventCreate(&r->ev0) != cudaSuccess || cudaEventCreate(&r->ev1) != cudaSuccess ||
-      (!g_hctrl && cudaMallocHost((void**)&g_hctrl, sizeof(Ctrl)) != cudaSuccess)) {
+      cudaEventCreateWithFlags(&r->ev_poll[0], cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&r->ev_poll[1], cudaEventDisableTiming) != cudaSuccess ||
+      cudaMallocHost((void**)&r->h_ctrl, sizeof(Ctrl) + 2 * sizeof(CtrlPoll)) != cudaSuccess) {
     pt_set_error("renderer setup failed: %s", cudaGetErrorString(cudaGetLastError()));
-    delete r;
+    pt_renderer_destroy(r);
     return PT_ERR_CUDA;
   }
-  r->h_ctrl = g_hctrl;  // only read inside pt_render, which is synchronous
+  r->h_poll = (CtrlPoll*)(r->h_ctrl + 1);
   *out = r;
   return PT_OK;
 }
 
 int pt_renderer_destroy(pt_renderer* r) {
   if (!r) return PT_OK;
+  if (r->multi) {
+    int rc = pt_multi_destroy(r->multi);
+    delete r;
+    return rc;
+  }
+  DeviceGuard dg(r->device);
   if (r->stream) {
     cudaStreamSynchronize(r->stream);
     cudaStreamDestroy(r->stream);
   }
   if (r->ev0) cudaEventDestroy(r->ev0);
   if (r->ev1) cudaEventDestroy(r->ev1);
-  if (r->slab.p && r->slab.bytes > g_slab_cache.bytes) {  // park the larger slab, free the smaller
-    std::swap(r->slab.p, g_slab_cache.p);
-    std::swap(r->slab.bytes, g_slab_cache.bytes);
+  for (auto& e : r->ev_poll)
+    if (e) cudaEventDestroy(e);
+  if (r->h_ctrl) cudaFreeHost(r->h_ctrl);
+  if (r->stage) cudaFreeHost(r->stage);
+  if (r->slab.p) {  // park the larger slab, free the smaller
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    DevBuf& parked = g_slab_cache[r->device];
+    if (r->slab.bytes > parked.bytes) {
+      std::swap(r->slab.p, parked.p);
+      std::swap(r->slab.bytes, parked.bytes);
+      std::swap(r->slab.dev, parked.dev);
+    }
   }
   for (auto& g : r->gexec)
     if (g) cudaGraphExecDestroy(g);
@@ -758,22 +978,31 @@ int pt_renderer_destroy(pt_renderer* r) {
 
 int pt_renderer_set_flags(pt_renderer* r, int32_t flags) {
   if (!r) return PT_ERR_INVALID;
+  if (r->multi) return pt_multi_set_flags(r->multi, flags);
   r->flags = flags;
   return PT_OK;
 }
 int pt_renderer_set_pool(pt_renderer* r, int64_t paths) {
   if (!r || paths < 0) return PT_ERR_INVALID;
+  if (r->multi) return pt_multi_set_pool(r->multi, paths);
   r->pool_req = paths;
   return PT_OK;
 }
 
 int pt_render(pt_renderer* r, int32_t first_frame, int32_t nframes, int32_t max_depth, int32_t russian,
               int32_t clear_accum) {
-  if (!r || nframes < 0 || max_depth < 0 || max_depth > 255) {
-    pt_set_error("pt_render: bad arguments (max_depth must be 0..255)");
+  if (!r || nframes < 0 || max_depth < 0 || max_depth > PT_MAX_DEPTH) {
+    pt_set_error("pt_render: bad arguments (max_depth must be 0..255: the path state packs the depth into 8 bits)");
     return PT_ERR_INVALID;
   }
+  if (r->multi) return pt_multi_render(r->multi, first_frame, nframes, max_depth, russian, clear_accum);
   pt_scene* s = r->scene;
+  if (!s->committed) {
+    // add_* / set_* calls and a failed commit release or replace device buffers the kernels would read
+    pt_set_error("pt_render: the scene was modified after the last successful pt_scene_commit");
+    return PT_ERR_STATE;
+  }
+  DeviceGuard dg(r->device);
   const long long total = (long long)r->W * r->H * nframes;
   int rc = ensure_pool(r, total);
   if (rc) return rc;
@@ -782,15 +1011,14 @@ int pt_render(pt_renderer* r, int32_t first_frame, int32_t nframes, int32_t max_
     PT_CUDA(cudaMemsetAsync(r->accum, 0, (size_t)r->W * r->H * 16, st));
   r->started = true;
   if (total == 0 || max_depth == 0) {
-    // raygen.cu:76,122: the loop body never runs, every sample is black
+    // raygen.cu:76,122: the loop body never runs, every sample is black (but counted)
     if (total) {
-      std::vector<float> tmp((size_t)r->W * r->H * 4);
-      PT_CUDA(cudaMemcpyAsync(tmp.data(), r->accum, tmp.size() * 4, cudaMemcpyDeviceToHost, st));
-      PT_CUDA(cudaStreamSynchronize(st));
-      for (size_t i = 0; i < (size_t)r->W * r->H; i++) tmp[4 * i + 3] += (float)nframes;
-      PT_CUDA(cudaMemcpyAsync(r->accum, tmp.data(), tmp.size() * 4, cudaMemcpyHostToDevice, st));
+      k_count_samples<<<sm_count() * 4, 256, 0, st>>>(r->accum, r->W * r->H, (float)nframes);
+      PT_CUDA(cudaGetLastError());
       PT_CUDA(cudaStreamSynchronize(st));
     }
+    r->stats = pt_stats{};
+    r->stats.samples = (uint64_t)total;
     return PT_OK;
   }
 
@@ -859,10 +1087,11 @@ int pt_render(pt_renderer* r, int32_t first_frame, int32_t nframes, int32_t max_
   bool sphere_lights = false;
   for (const pt_light& l : s->lights) sphere_lights |= l.type == PT_LIGHT_SPHERE;
 
-  cudaEvent_t e[6] = {};
+  EventSet evs;
+  cudaEvent_t* e = evs.e;
   float ms_gen = 0, ms_trace = 0, ms_shade = 0, ms_shadow = 0;
   if (timing)
-    for (auto& ev : e) PT_CUDA(cudaEventCreate(&ev));
+    for (int k = 0; k < 6; k++) PT_CUDA(cudaEventCreate(&e[k]));
 
   // one wavefront iteration reading pool `cur`, appending survivors to pool `nxt`; returns #launches
   auto iteration = [&](const PathBuf& cur, const PathBuf& nxt, bool timed) {
@@ -921,20 +1150,26 @@ int pt_render(pt_renderer* r, int32_t first_frame, int32_t nframes, int32_t max_
   // removes the per-kernel launch gaps, which are ~10 % of an iteration on small scenes.  The
   // per-kernel timing mode launches directly instead.
   const bool use_graph = !timing && getenv("PTB200_NO_GRAPH") == nullptr;
-  if (use_graph && (r->gexec[0] == nullptr || r->g_max_depth != max_depth || r->g_russian != russian ||
-                    r->g_pool != r->pool || r->g_flags != r->flags || r->g_commit_gen != s->commit_gen ||
-                    memcmp(&r->g_scene, &sc, sizeof(SceneDev)) != 0)) {
-    for (auto& g : r->gexec) {
-      if (g) cudaGraphExecDestroy(g);
-      g = nullptr;
-    }
+  if (use_graph && (r->gexec[0] == nullptr || r->gexec[1] == nullptr || r->g_max_depth != max_depth ||
+                    r->g_russian != russian || r->g_pool != r->pool || r->g_flags != r->flags ||
+                    r->g_commit_gen != s->commit_gen || memcmp(&r->g_scene, &sc, sizeof(SceneDev)) != 0)) {
+    drop_graphs(r);
     for (int parity = 0; parity < 2; parity++) {
       cudaGraph_t graph = nullptr;
+      CaptureGuard cap{st};
       PT_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+      cap.active = true;
       r->g_launches = parity == 0 ? iteration(A, B, false) : iteration(B, A, false);
-      PT_CUDA(cudaStreamEndCapture(st, &graph));
-      PT_CUDA(cudaGraphInstantiate(&r->gexec[parity], graph, 0));
-      cudaGraphDestroy(graph);
+      cap.active = false;
+      cudaError_t ce = cudaStreamEndCapture(st, &graph);
+      if (ce == cudaSuccess) ce = cudaGraphInstantiate(&r->gexec[parity], graph, 0);
+      if (graph) cudaGraphDestroy(graph);
+      if (ce != cudaSuccess) {
+        drop_graphs(r);
+        pt_set_error("pt_render: capturing the wavefront iteration failed: %s", cudaGetErrorString(ce));
+        cudaGetLastError();
+        return PT_ERR_CUDA;
+      }
     }
     r->g_max_depth = max_depth;
     r->g_russian = russian;
@@ -946,14 +1181,21 @@ int pt_render(pt_renderer* r, int32_t first_frame, int32_t nframes, int32_t max_
 
   PT_CUDA(cudaEventRecord(r->ev0, st));
   unsigned long long launches = 0;
-  bool done = false;
   long long iter = 0;
-  // Completion is detected by polling the device control block.  While more than a pool-full of
-  // samples is still ungenerated, at least remaining/pool further iterations are certain, so the
-  // host keeps launching without synchronising; near the end it polls every 4 iterations.
-  long long poll_every = std::max<long long>(4, total / std::max(1, r->pool));
-  while (!done) {
-    for (long long k = 0; k < poll_every; k++, iter++) {
+  // Completion detection without stalling the device.  k_iter_begin leaves its loop state in the first bytes of
+  // the control block; after every batch of iterations the host enqueues an asynchronous copy of those bytes and
+  // only then waits for the copy of the PREVIOUS batch, so one batch is always queued behind the one being looked
+  // at.  While more than a pool-full of samples is ungenerated at least remaining / pool further iterations are
+  // certain and the batch is that long; near the end it is 4.  Batches are even so that the pool parity of
+  // iteration k is k & 1 and the survivors of a finished batch are in pool A.
+  const int drain_max = getenv("PTB200_DRAIN_MAX") ? std::min(atoi(getenv("PTB200_DRAIN_MAX")), 1 << 20) : PT_DRAIN_MAX;  // 0 = off (dev)
+  const bool use_drain = drain_max > 0 && !timing;
+  auto even = [](long long v) { return v + (v & 1); };
+  long long batch = even(std::max<long long>(4, total / std::max(1, r->pool)));
+  int slot = 0;
+  bool outstanding = false, finished = false, drained = false;
+  while (!finished) {
+    for (long long k = 0; k < batch; k++, iter++) {
       if (use_graph) {
         PT_CUDA(cudaGraphLaunch(r->gexec[iter & 1], st));
         launches += (unsigned long long)r->g_launches;
@@ -962,30 +1204,56 @@ int pt_render(pt_renderer* r, int32_t first_frame, int32_t nframes, int32_t max_
       }
     }
     PT_CUDA(cudaGetLastError());
-    PT_CUDA(cudaMemcpyAsync(r->h_ctrl, c, sizeof(Ctrl), cudaMemcpyDeviceToHost, st));
-    PT_CUDA(cudaStreamSynchronize(st));
-    done = r->h_ctrl->next_sample >= r->h_ctrl->total_samples && r->h_ctrl->n_next == 0;
-    poll_every = std::max<long long>(4, (long long)((r->h_ctrl->total_samples - r->h_ctrl->next_sample) / (unsigned)std::max(1, r->pool)));
-    if (poll_every & 1) poll_every++;  // keep the pool parity aligned with `iter`
+    PT_CUDA(cudaMemcpyAsync(&r->h_poll[slot], c, sizeof(CtrlPoll), cudaMemcpyDeviceToHost, st));
+    PT_CUDA(cudaEventRecord(r->ev_poll[slot], st));
+    if (outstanding) {
+      PT_CUDA(cudaEventSynchronize(r->ev_poll[slot ^ 1]));
+      // state at the BEGIN of the last iteration of the previous batch: n_cur paths were in flight then, so at
+      // most that many are alive now if nothing is left to generate
+      const CtrlPoll& q = r->h_poll[slot ^ 1];
+      const unsigned long long remaining = q.total_samples - q.next_sample;
+      if (remaining == 0 && q.n_cur <= (use_drain ? drain_max : 0)) {
+        finished = true;
+        drained = use_drain && q.n_cur > 0;
+      }
+      batch = even(std::max<long long>(4, (long long)(remaining / (unsigned)std::max(1, r->pool))));
+    } else {
+      batch = 4;
+    }
+    outstanding = true;
+    slot ^= 1;
     if (iter > 100000000ll) {
       pt_set_error("pt_render: did not converge");
+      cudaStreamSynchronize(st);
       return PT_ERR_INVALID;
     }
   }
+  if (drained) {
+    const int g_drain = (drain_max + 63) / 64;
+    if (sphere_lights) k_drain<1><<<g_drain, 64, 0, st>>>(sc, p, c, A, count ? 1 : 0);
+    else k_drain<0><<<g_drain, 64, 0, st>>>(sc, p, c, A, count ? 1 : 0);
+    k_drain_end<<<1, 1, 0, st>>>(c);
+    PT_CUDA(cudaGetLastError());
+    launches += 2;
+  }
+  PT_CUDA(cudaMemcpyAsync(r->h_ctrl, c, sizeof(Ctrl), cudaMemcpyDeviceToHost, st));
   PT_CUDA(cudaEventRecord(r->ev1, st));
   PT_CUDA(cudaEventSynchronize(r->ev1));
   float ms = 0.f;
   PT_CUDA(cudaEventElapsedTime(&ms, r->ev0, r->ev1));
-  if (timing)
-    for (auto& ev : e) cudaEventDestroy(ev);
   const Ctrl& hc = *r->h_ctrl;
   if (hc.error) {
     pt_set_error("pt_render: BVH traversal stack overflow (tree deeper than %d node groups)", PT_STACK);
     return PT_ERR_INVALID;
   }
+  if (hc.next_sample < hc.total_samples || hc.n_next != 0) {
+    pt_set_error("pt_render: internal error, %llu samples ungenerated and %d paths alive at the end",
+                 hc.total_samples - hc.next_sample, hc.n_next);
+    return PT_ERR_INVALID;
+  }
   r->stats.samples = (uint64_t)total;
   r->stats.closest_rays = hc.stat_closest;
-  r->stats.shadow_rays = hc.stat_shadow + (uint64_t)hc.n_shadow;
+  r->stats.shadow_rays = hc.stat_shadow + (uint64_t)hc.n_shadow;  // the last iteration's count was never folded in
   r->stats.nodes_fetched = hc.stat_nodes;
   r->stats.leaves_fetched = hc.stat_leaves;
   r->stats.iterations = hc.stat_iters;
@@ -995,17 +1263,26 @@ int pt_render(pt_renderer* r, int32_t first_frame, int32_t nframes, int32_t max_
   r->stats.ms_trace_closest = ms_trace;
   r->stats.ms_shade = ms_shade;
   r->stats.ms_trace_shadow = ms_shadow;
+  r->stats.ms_reduce = 0.f;
+  r->stats.drained_paths = drained ? 1u : 0u;
   return PT_OK;
 }
 
 int pt_renderer_sync(pt_renderer* r) {
   if (!r) return PT_ERR_INVALID;
+  if (r->multi) return pt_multi_sync(r->multi);
+  DeviceGuard dg(r->device);
   PT_CUDA(cudaStreamSynchronize(r->stream));
   return PT_OK;
 }
 
 int pt_read_accum(pt_renderer* r, float* host_rgba) {
   if (!r || !host_rgba) return PT_ERR_INVALID;
+  if (r->multi) {  // the per-device buffers are merged (NCCL sum-reduce) into the root's first
+    int rc = pt_multi_merge(r->multi);
+    return rc ? rc : pt_read_accum(pt_multi_root(r->multi), host_rgba);
+  }
+  DeviceGuard dg(r->device);
   const size_t bytes = (size_t)r->W * r->H * 16;
   // The caller's buffer is usually pageable, and a pageable device-to-host copy is staged by the driver at
   // ~2 GB/s (7.4 ms for the 15 MB of a 1200x800 image).  Copy into a pinned buffer of the renderer's own at
@@ -1018,25 +1295,26 @@ int pt_read_accum(pt_renderer* r, float* host_rgba) {
     PT_CUDA(cudaStreamSynchronize(r->stream));
     return PT_OK;
   }
-  // one grow-only staging buffer per process (pinning 15 MB costs ~7 ms: not something to pay per renderer);
-  // the library is driven by one host thread, like the reference
-  static float* g_stage = nullptr;
-  static size_t g_stage_bytes = 0;
-  if (g_stage_bytes < bytes) {
-    if (g_stage) cudaFreeHost(g_stage);
-    g_stage = nullptr;
-    g_stage_bytes = 0;
-    PT_CUDA(cudaMallocHost((void**)&g_stage, bytes));
-    g_stage_bytes = bytes;
+  if (r->stage_bytes < bytes) {  // grow-only, owned by the renderer
+    if (r->stage) cudaFreeHost(r->stage);
+    r->stage = nullptr;
+    r->stage_bytes = 0;
+    PT_CUDA(cudaMallocHost((void**)&r->stage, bytes));
+    r->stage_bytes = bytes;
   }
-  PT_CUDA(cudaMemcpyAsync(g_stage, r->accum, bytes, cudaMemcpyDeviceToHost, r->stream));
+  PT_CUDA(cudaMemcpyAsync(r->stage, r->accum, bytes, cudaMemcpyDeviceToHost, r->stream));
   PT_CUDA(cudaStreamSynchronize(r->stream));
-  memcpy(host_rgba, g_stage, bytes);
+  memcpy(host_rgba, r->stage, bytes);
   return PT_OK;
 }
 
 int pt_read_display(pt_renderer* r, uint8_t* host_rgba8) {
   if (!r || !host_rgba8) return PT_ERR_INVALID;
+  if (r->multi) {
+    int rc = pt_multi_merge(r->multi);
+    return rc ? rc : pt_read_display(pt_multi_root(r->multi), host_rgba8);
+  }
+  DeviceGuard dg(r->device);
   const int n = r->W * r->H;
   if (!r->display.p) PT_CUDA(r->display.alloc((size_t)n * 4));
   k_display<<<sm_count() * 4, 256, 0, r->stream>>>(r->accum, r->display.as<uchar4>(), n);
@@ -1048,6 +1326,8 @@ int pt_read_display(pt_renderer* r, uint8_t* host_rgba8) {
 
 int pt_write_accum(pt_renderer* r, const float* host_rgba) {
   if (!r || !host_rgba) return PT_ERR_INVALID;
+  if (r->multi) return pt_multi_write_accum(r->multi, host_rgba);
+  DeviceGuard dg(r->device);
   PT_CUDA(cudaMemcpyAsync(r->accum, host_rgba, (size_t)r->W * r->H * 16, cudaMemcpyHostToDevice, r->stream));
   PT_CUDA(cudaStreamSynchronize(r->stream));
   r->started = true;  // a restored buffer must not be cleared by the next pt_render(first_frame = 0)
@@ -1056,13 +1336,26 @@ int pt_write_accum(pt_renderer* r, const float* host_rgba) {
 
 int pt_accum_device_ptr(pt_renderer* r, void** d_ptr) {
   if (!r || !d_ptr) return PT_ERR_INVALID;
+  if (r->multi) {  // the merged buffer on the root device
+    int rc = pt_multi_merge(r->multi);
+    if (rc) return rc;
+    *d_ptr = pt_multi_root(r->multi)->accum;
+    return PT_OK;
+  }
   *d_ptr = r->accum;
   return PT_OK;
 }
 
 int pt_get_stats(pt_renderer* r, pt_stats* out) {
   if (!r || !out) return PT_ERR_INVALID;
+  if (r->multi) return pt_multi_get_stats(r->multi, out);
   *out = r->stats;
+  return PT_OK;
+}
+
+int pt_release_caches(void) {
+  pt_release_slab_cache();
+  pt_bvh_release_arenas();
   return PT_OK;
 }
 
@@ -1072,10 +1365,15 @@ int pt_trace_rays_device(pt_scene* scene, const void* d_rays, int64_t n, void* d
     return PT_ERR_STATE;
   }
   if (n <= 0) return PT_OK;
+  if (!d_rays || !d_hits) {
+    pt_set_error("pt_trace_rays_device: null ray or hit buffer");
+    return PT_ERR_INVALID;
+  }
   if (n > 0x7fffffff) {
     pt_set_error("pt_trace_rays: at most 2^31-1 rays per call");
     return PT_ERR_INVALID;
   }
+  DeviceGuard dg(scene->device);
   cudaStream_t st = (cudaStream_t)cuda_stream;
   unsigned long long* dc = nullptr;
   PT_CUDA(cudaMallocAsync((void**)&dc, 32, st));
@@ -1099,6 +1397,7 @@ int pt_trace_rays(pt_scene* scene, const pt_ray* rays, int64_t n, pt_hit* hits, 
     pt_set_error("pt_trace_rays: at most 2^31-1 rays per call");
     return PT_ERR_INVALID;
   }
+  DeviceGuard dg(scene->device);
   DevBuf dr, dh, dc;
   PT_CUDA(dr.alloc((size_t)n * sizeof(pt_ray)));
   PT_CUDA(dh.alloc((size_t)n * sizeof(pt_hit)));

@@ -438,7 +438,8 @@ struct FixedAux {
 };
 template <bool COUNT>
 PT_HD void bvh8_closest(const SceneDev& sc, float3 o, float3 d, float tmin, float tmax,
-                        TraceHit& hit, uint32_t& n_nodes, uint32_t& n_leaves, RayAux ra = RayAux{0.f, 0u}) {
+                        TraceHit& hit, uint32_t& n_nodes, uint32_t& n_leaves, RayAux ra = RayAux{0.f, 0u},
+                        int* overflow = nullptr) {
   const FixedAux aux{ra};
   RayCtx r;
   ray_setup(r, o, d, tmin, tmax);
@@ -452,7 +453,10 @@ PT_HD void bvh8_closest(const SceneDev& sc, float3 o, float3 d, float tmin, floa
       uint2 rest;
       bvh8_node_step(sc, r, hit.t, ng, lg, rest);
       if (COUNT) n_nodes++;
-      if ((rest.y & 0xff000000u) && sp < PT_STACK) stack[sp++] = rest;
+      if (rest.y & 0xff000000u) {
+        if (sp < PT_STACK) stack[sp++] = rest;
+        else if (overflow) *overflow = 1;  // never silently wrong: the caller turns this into an error
+      }
     }
     while (lg.y) {
       bvh8_leaf_step(sc, r, lg, hit, aux);

@@ -282,12 +282,22 @@ class ContextObj {
     check(pt_scene_set_miss(s, &miss));
     return s;
   }
+  // optixpp's Context::setDevices(begin, end) (OptiX 6 spreads a launch over the listed devices by itself);
+  // here the frames of a launch are split over them and the accumulation buffers merged by one NCCL reduce
+  // (pt_renderer_create_multi).  An empty list or one entry = the current device.
+  std::vector<int> devices;
+  template <class It>
+  void setDevices(It begin, It end) {
+    devices.assign(begin, end);
+    if (renderer) { pt_renderer_destroy(renderer); renderer = nullptr; }
+  }
   void ensureRenderer(int W, int H) {
     if (dirty || !scene) commit();
     if (!renderer || rW != W || rH != H) {
       if (renderer) pt_renderer_destroy(renderer);
       renderer = nullptr;
-      check(pt_renderer_create(scene, W, H, nullptr, &renderer));
+      if (devices.size() > 1) check(pt_renderer_create_multi(scene, W, H, devices.data(), (int)devices.size(), &renderer));
+      else check(pt_renderer_create(scene, W, H, nullptr, &renderer));
       rW = W;
       rH = H;
     }

@@ -8,6 +8,7 @@
 // loads it, and the shipped library has no CPU execution mode.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <vector>
@@ -37,6 +38,81 @@ static double sah_sum(const Bvh2& t) {
   const Bvh2Node& r = t.nodes[0];
   double ra = box_half_area(f3(r.lo[0], r.lo[1], r.lo[2]), f3(r.hi[0], r.hi[1], r.hi[2]));
   return ra > 0 ? a / ra : 0;
+}
+
+
+// ---- EXPERIMENT (dev): full top-down binned-SAH build into the same Bvh2 arrays, as the quality yardstick for the
+// GPU builder's LBVH + treelet refinement (scripts/bvh_quality_probe.py, PTSIM_BUILDER=sah) -----------------
+static void full_sah_build(Bvh2& t, int nbins) {
+  const int n = t.n;
+  std::vector<int> idx(n);
+  std::iota(idx.begin(), idx.end(), 0);  // sorted positions
+  struct Job { int node, lo, hi; };
+  std::vector<Job> stack;
+  int next_node = 1;
+  stack.push_back({0, 0, n});
+  t.parent[0] = -1;
+  while (!stack.empty()) {
+    Job j = stack.back();
+    stack.pop_back();
+    float3 blo = f3(INFINITY), bhi = f3(-INFINITY), clo = blo, chi = bhi;
+    for (int i = j.lo; i < j.hi; i++) {
+      uint32_t id = t.sorted[idx[i]];
+      float3 a = xyz(t.plo[id]), b = xyz(t.phi[id]);
+      blo = fmin3(blo, a); bhi = fmax3(bhi, b);
+      float3 c = (a + b) * 0.5f;
+      clo = fmin3(clo, c); chi = fmax3(chi, c);
+    }
+    bvh2_set_box(t.nodes[j.node], blo, bhi);
+    t.count[j.node] = j.hi - j.lo;
+    int mid = -1;
+    if (j.hi - j.lo > 2) {
+      float best = INFINITY; int bax = -1, bbin = -1;
+      for (int ax = 0; ax < 3; ax++) {
+        float cmin = comp(clo, ax), cmax = comp(chi, ax);
+        if (!(cmax > cmin)) continue;
+        float scale = nbins / (cmax - cmin);
+        std::vector<float3> binlo(nbins, f3(INFINITY)), binhi(nbins, f3(-INFINITY));
+        std::vector<int> cnt(nbins, 0);
+        for (int i = j.lo; i < j.hi; i++) {
+          uint32_t id = t.sorted[idx[i]];
+          float3 a = xyz(t.plo[id]), b = xyz(t.phi[id]);
+          int bi = std::min(nbins - 1, std::max(0, (int)(((comp(a, ax) + comp(b, ax)) * 0.5f - cmin) * scale)));
+          binlo[bi] = fmin3(binlo[bi], a); binhi[bi] = fmax3(binhi[bi], b); cnt[bi]++;
+        }
+        std::vector<float> rarea(nbins); std::vector<int> rcnt(nbins);
+        float3 alo = f3(INFINITY), ahi = f3(-INFINITY); int c = 0;
+        for (int b = nbins - 1; b > 0; b--) { alo = fmin3(alo, binlo[b]); ahi = fmax3(ahi, binhi[b]); c += cnt[b]; rarea[b] = c ? box_half_area(alo, ahi) : 0.f; rcnt[b] = c; }
+        alo = f3(INFINITY); ahi = f3(-INFINITY); c = 0;
+        for (int b = 0; b < nbins - 1; b++) {
+          alo = fmin3(alo, binlo[b]); ahi = fmax3(ahi, binhi[b]); c += cnt[b];
+          if (!c || !rcnt[b + 1]) continue;
+          float cost = box_half_area(alo, ahi) * c + rarea[b + 1] * rcnt[b + 1];
+          if (cost < best) { best = cost; bax = ax; bbin = b; }
+        }
+      }
+      if (bax >= 0) {
+        float cmin = comp(clo, bax), cmax = comp(chi, bax);
+        float scale = nbins / (cmax - cmin);
+        auto it = std::partition(idx.begin() + j.lo, idx.begin() + j.hi, [&](int k) {
+          uint32_t id = t.sorted[k];
+          float3 a = xyz(t.plo[id]), b = xyz(t.phi[id]);
+          int bi = std::min(nbins - 1, std::max(0, (int)(((comp(a, bax) + comp(b, bax)) * 0.5f - cmin) * scale)));
+          return bi <= bbin;
+        });
+        mid = (int)(it - idx.begin());
+      }
+    }
+    if (mid <= j.lo || mid >= j.hi) mid = (j.lo + j.hi) >> 1;
+    int refs[2];
+    for (int side = 0; side < 2; side++) {
+      int a = side ? mid : j.lo, b = side ? j.hi : mid;
+      if (b - a == 1) { refs[side] = ~idx[a]; t.leaf_parent[idx[a]] = j.node; }
+      else { int ch = next_node++; refs[side] = ch; t.parent[ch] = j.node; stack.push_back({ch, a, b}); }
+    }
+    t.nodes[j.node].left = refs[0];
+    t.nodes[j.node].right = refs[1];
+  }
 }
 
 extern "C" {
@@ -131,6 +207,9 @@ Sim* sim_create(const pt_scene_desc* desc, int refine) {
         lo = hi;
         hi *= PT_TREELET;
       }
+    }
+    if (const char* e = getenv("PTSIM_BUILDER")) {
+      if (!strcmp(e, "sah")) full_sah_build(t, getenv("PTSIM_BINS") ? atoi(getenv("PTSIM_BINS")) : 32);
     }
     s->sah_after = sah_sum(t);
   }

@@ -24,7 +24,7 @@ def test_header_symbols_exported(lib):
     assert set(syms) == set(pt.ABI_SYMBOLS), set(syms) ^ set(pt.ABI_SYMBOLS)
     for s in syms:
         assert hasattr(lib, s), s
-    assert lib.pt_abi_version() == 2
+    assert lib.pt_abi_version() == 3
 
 
 def test_struct_layout_matches_header():
