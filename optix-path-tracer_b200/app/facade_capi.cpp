@@ -60,6 +60,34 @@ int pth_decode_image(const char* path, int* w, int* h, int* n_channels, unsigned
   return PT_OK;
 }
 
+// loads an OBJ through Mesh(file, material) exactly as a scene function would (io_formats.hpp load_obj + mesh.hpp
+// flattening); reports the triangle count and whether per-corner normals / uvs were kept
+int pth_mesh_probe(const char* path, int* n_tris, int* has_normals, int* has_uvs) {
+  try {
+    App_State app;
+    Mesh mesh(path, new Lambertian(new Constant_Texture(0.5f)), false);
+    Group g = app.context->createGroup();
+    mesh.addTo(g, app.context);
+    long long tris = 0;
+    bool nn = false, uu = false;
+    for (auto& b : app.context->batches)
+      if (b.kind == PT_PRIM_TRIANGLE) {
+        tris += (long long)b.v.size() / 9;
+        nn = nn || !b.n.empty();
+        uu = uu || !b.uv.empty();
+      }
+    *n_tris = (int)tris;
+    *has_normals = nn;
+    *has_uvs = uu;
+    return PT_OK;
+  } catch (const char* e) {
+    fprintf(stderr, "pth_mesh_probe: %s\n", e);
+  } catch (const std::string& e) {
+    fprintf(stderr, "pth_mesh_probe: %s\n", e.c_str());
+  }
+  return PT_ERR_INVALID;
+}
+
 // Image_Texture's loader (host_includes/textures.hpp: float4 texels, optional vertical flip)
 int pth_load_ldr_image(const char* path, int flip_y, int* w, int* h, float* rgba, long long capacity_bytes) {
   std::vector<float> px;

@@ -35,6 +35,7 @@ struct BitReader {
   size_t n, pos = 0;
   uint64_t acc = 0;
   int cnt = 0;
+  bool eof = false;  // bits were consumed past the end of the input (they read as zero)
   void fill() {
     while (cnt <= 56 && pos < n) {
       acc |= (uint64_t)p[pos++] << cnt;
@@ -48,6 +49,10 @@ struct BitReader {
   void drop(int k) {
     acc >>= k;
     cnt -= k;
+    if (cnt < 0) {  // underflow: a truncated stream must not decode zeros for ever
+      cnt = 0;
+      eof = true;
+    }
   }
   uint32_t get(int k) {
     uint32_t v = peek(k);
@@ -107,6 +112,7 @@ inline bool inflate_zlib(const unsigned char* in, size_t n, std::vector<unsigned
   for (bool last = false; !last;) {
     last = br.get(1) != 0;
     int type = (int)br.get(2);
+    if (br.eof) { err = "truncated deflate stream"; return false; }
     if (type == 0) {
       br.align_byte();
       uint32_t len = br.get(16), nlen = br.get(16);
@@ -138,6 +144,7 @@ inline bool inflate_zlib(const unsigned char* in, size_t n, std::vector<unsigned
       while (i < nlit + ndist) {
         int s = clh.decode(br);
         if (s < 0) { err = "bad code-length symbol"; return false; }
+        if (br.eof) { err = "truncated deflate stream"; return false; }
         if (s < 16) { lens[i++] = (unsigned char)s; continue; }
         int rep, val = 0;
         if (s == 16) {
@@ -155,6 +162,7 @@ inline bool inflate_zlib(const unsigned char* in, size_t n, std::vector<unsigned
     for (;;) {
       int s = lit.decode(br);
       if (s < 0) { err = "bad literal/length code"; return false; }
+      if (br.eof) { err = "truncated deflate stream"; return false; }
       if (s < 256) { out.push_back((unsigned char)s); continue; }
       if (s == 256) break;
       s -= 257;
@@ -387,8 +395,8 @@ struct Bits {  // MSB-first entropy-coded segment reader with FF00 un-stuffing
     acc <<= k;
     cnt -= k;
   }
-  int receive_extend(int s) {  // T.81 F.2.2.1
-    if (!s) return 0;
+  int receive_extend(int s) {  // T.81 F.2.2.1; s <= 16 (callers check the category)
+    if (s <= 0 || s > 16) return 0;
     if (cnt < s) fill();
     int v = (int)(acc >> (32 - s));
     drop(s);
@@ -538,6 +546,8 @@ inline bool decode_jpeg(const unsigned char* data, size_t n, DecodedImage& im) {
           hmax = std::max(hmax, comp[c].h);
           vmax = std::max(vmax, comp[c].v);
         }
+        for (int c = 0; c < nc; c++)
+          if (hmax % comp[c].h != 0 || vmax % comp[c].v != 0) { im.error = "non-integer sampling ratio"; return false; }
         mcux = (W + 8 * hmax - 1) / (8 * hmax);
         mcuy = (H + 8 * vmax - 1) / (8 * vmax);
         for (auto& c : comp) {
@@ -558,6 +568,7 @@ inline bool decode_jpeg(const unsigned char* data, size_t n, DecodedImage& im) {
         break;
       case 0xda: {  // SOS + entropy-coded data
         if (!have_frame) { im.error = "SOS before SOF"; return false; }
+        if (sl < 1 || sl < 1 + 2 * (size_t)s[0] + 3) { im.error = "short SOS segment"; return false; }
         const int ns = s[0];
         if (ns != (int)comp.size() && !(ns == 1 && comp.size() == 1)) {
           im.error = "non-interleaved multi-scan JPEG is not supported";
@@ -590,6 +601,7 @@ inline bool decode_jpeg(const unsigned char* data, size_t n, DecodedImage& im) {
                   uint16_t e = hdc[c.td].tab[br.peek16()];
                   if (!e) { im.error = "bad DC Huffman code"; return false; }
                   br.drop(e >> 8);
+                  if ((e & 0xff) > 11) { im.error = "DC category above 11 (baseline JPEG)"; return false; }
                   c.pred += br.receive_extend(e & 0xff);
                   coef[0] = c.pred;
                   for (int k = 1; k < 64;) {

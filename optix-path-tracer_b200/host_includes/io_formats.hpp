@@ -255,7 +255,9 @@ inline bool load_obj(const std::string& path, const std::string& mtl_dir, ObjMes
         while (*p == ' ' || *p == '\t') p++;
         if (*p == '\n' || *p == '\r' || !*p) break;
         int v = 0, t = 0, n = 0;
+        char* tok = p;
         v = (int)strtol(p, &p, 10);
+        if (p == tok) break;  // not a number (e.g. a trailing "# comment"): the face ends here
         if (*p == '/') {
           p++;
           if (*p != '/') t = (int)strtol(p, &p, 10);

@@ -48,8 +48,9 @@ class Mesh {
     toRowMajor3x4(o2w, b.xf);
     const size_t nt = obj.vi.size() / 3;
     bool hasN = !obj.ni.empty(), hasT = !obj.ti.empty();
-    for (int i : obj.ni) hasN = hasN && i >= 0;
-    for (int i : obj.ti) hasT = hasT && i >= 0;
+    const int n_normals = (int)obj.normals.size() / 3, n_texcoords = (int)obj.texcoords.size() / 2;
+    for (int i : obj.ni) hasN = hasN && i >= 0 && i < n_normals;
+    for (int i : obj.ti) hasT = hasT && i >= 0 && i < n_texcoords;
     b.v.reserve(nt * 9);
     for (size_t t = 0; t < nt; t++) {
       for (int k = 0; k < 3; k++) {

@@ -66,6 +66,52 @@
   float b = rnd(seed)
 #endif
 
+// -DORC_ULP_NOISE builds liboracle_ulp.so: the same oracle with every libm call (sinf, cosf, tanf, atanf, atan2f,
+// asinf, acosf, logf, powf, expf - the functions whose CUDA implementations are allowed to differ from glibc's by
+// 1-2 ulp; sqrtf and the arithmetic are IEEE-exact on both sides) nudged by -1 / 0 / +1 ulp, chosen by a hash of
+// the result.  It answers ONE question (tests/test_gpu_parity.py::test_fixed_seed_radiance): how many pixels of a
+// fixed-seed image change when nothing but last-bit libm rounding changes?  That measured fraction is the bar the
+// GPU image is held to - the GPU's differing pixels are expected to be exactly this kind (a flipped branch after
+// a 1-ulp difference), so it must not show more of them than ulp noise alone produces.
+#ifdef ORC_ULP_NOISE
+namespace ulp_noise {
+inline float nudge(float v) {
+  if (!(v == v) || std::isinf(v) || v == 0.f) return v;
+  uint32_t b;
+  memcpy(&b, &v, 4);
+  uint32_t hsh = b * 2654435761u;
+  hsh ^= hsh >> 15;
+  hsh *= 2246822519u;
+  hsh ^= hsh >> 13;
+  const uint32_t k = hsh >> 30;  // 0,1: unchanged; 2: +1 ulp in magnitude; 3: -1 ulp
+  if (k == 2) b += 1;
+  else if (k == 3) b -= 1;
+  memcpy(&v, &b, 4);
+  return v;
+}
+inline float n_sinf(float x) { return nudge(::sinf(x)); }
+inline float n_cosf(float x) { return nudge(::cosf(x)); }
+inline float n_tanf(float x) { return nudge(::tanf(x)); }
+inline float n_atanf(float x) { return nudge(::atanf(x)); }
+inline float n_atan2f(float y, float x) { return nudge(::atan2f(y, x)); }
+inline float n_asinf(float x) { return nudge(::asinf(x)); }
+inline float n_acosf(float x) { return nudge(::acosf(x)); }
+inline float n_logf(float x) { return nudge(::logf(x)); }
+inline float n_powf(float x, float y) { return nudge(::powf(x, y)); }
+inline float n_expf(float x) { return nudge(::expf(x)); }
+}  // namespace ulp_noise
+#define sinf ulp_noise::n_sinf
+#define cosf ulp_noise::n_cosf
+#define tanf ulp_noise::n_tanf
+#define atanf ulp_noise::n_atanf
+#define atan2f ulp_noise::n_atan2f
+#define asinf ulp_noise::n_asinf
+#define acosf ulp_noise::n_acosf
+#define logf ulp_noise::n_logf
+#define powf ulp_noise::n_powf
+#define expf ulp_noise::n_expf
+#endif
+
 namespace {
 
 // ---------------------------------------------------------------------------

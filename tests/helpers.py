@@ -713,6 +713,19 @@ def build_mesh_scene(grid=32, W=64, H=64, lib=None, normals=False, mat_kind=None
     return s
 
 
+def build_backdrop(W, H, miss_type, spherical=1, lib=None):
+    """a mirror sphere and a diffuse one in front of an image background (miss.cu image_background /
+    environmental_mapping): the miss program's own (u, v) arithmetic decides every pixel"""
+    s = pt.Scene(lib)
+    s.set_textures([tex_const(0.8, 0.6, 0.2), tex_const(0.9)])
+    s.set_materials([material(pt.MAT_LAMBERTIAN, 0), material(pt.MAT_METAL, 1, p0=0.0)])
+    s.add_spheres([pt.Sphere(pt.F3(-1.1, 0, 0), 1.0), pt.Sphere(pt.F3(1.1, 0, 0), 1.0)], [0, 1])
+    s.set_camera(make_camera([0, 0.5, -6], [0, 0, 0], [0, 1, 0], 40.0, W / H, 0.0, 6.0))
+    img = s.add_image(synthetic_hdri(64, 32))
+    s.set_miss(pt.Miss(miss_type, pt.F3(0, 0, 0), pt.F3(0, 0, 0), img, spherical, 0))
+    return s
+
+
 def build_noise_scene(W=32, H=32):
     """Spheres with Perlin-noise, gradient and checker textures on Lambertian / metal."""
     rng = np.random.default_rng(7)

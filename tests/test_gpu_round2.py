@@ -1,0 +1,286 @@
+"""GPU parity tests added in round 2 (through the C ABI, against the CPU oracle):
+the remaining miss programs, the drain kernel, stale-scene refusal, the fixed limits, hit ids at the top of
+configuration 4's range (10 M triangles), full-size C1 / C3 per-pixel parity, and the MEASURED bar of the
+fixed-seed tests (how many pixels change under last-bit libm differences alone)."""
+import os
+
+import numpy as np
+import pytest
+
+import helpers as h
+
+pt = h.pt
+pytestmark = pytest.mark.gpu
+
+
+def same_hits(a, b):
+    return ((a["prim"] == b["prim"]) & (a["t"].view(np.uint32) == b["t"].view(np.uint32)) &
+            (a["u"].view(np.uint32) == b["u"].view(np.uint32)) & (a["v"].view(np.uint32) == b["v"].view(np.uint32)))
+
+
+def pixel_diff(g, a):
+    return np.abs(g[..., :3] - a[..., :3]).max(axis=-1)
+
+
+# ---- 8f-1: the two miss programs that had no GPU test ---------------------------------------------------------
+@pytest.mark.parametrize("what", ["image_background", "cylindrical_env"])
+def test_image_background_and_cylindrical_env(lib, what):
+    """programs/miss.cu:51-59 image_background (IMG: LDR image looked up by the ray direction's own (u, v)) and
+    :80-91 environmental_mapping with isSpherical == false (cylindrical lookup), on the device against the oracle.
+    The mirror sphere reflects the background, so the (u, v) arithmetic is exercised over the whole sphere of
+    directions, not only the camera's cone."""
+    W, H = 96, 64
+    miss, sph = (pt.MISS_IMG, 1) if what == "image_background" else (pt.MISS_HDR, 0)
+    sc = h.build_backdrop(W, H, miss, sph, lib)
+    sc.commit()
+    orc = h.OracleScene(sc)
+    # depth 1: camera ray -> miss program (or a black sphere pixel): no stochastic branch at all
+    r = pt.Renderer(sc, W, H)
+    r.render(0, 1, max_depth=1)
+    g = r.read_accum()
+    a, _ = orc.render(W, H, 0, 1, max_depth=1)
+    d = pixel_diff(g, a)
+    assert (g[..., 3] == 1).all()
+    assert a[..., :3].max() > 0.05
+    # atan2f / acosf differ by <= 2 ulp between glibc and CUDA; the bilinear lookup is continuous in (u, v)
+    assert d.max() <= 2e-4, d.max()
+    # full paths at fixed seed
+    r.render(0, 4, clear=True)
+    g = r.read_accum()
+    a, st = orc.render(W, H, 0, 4)
+    d = pixel_diff(g, a)
+    assert (d > 1e-3).mean() <= 0.01, (d > 1e-3).mean()
+    assert abs(g[..., :3].mean() - a[..., :3].mean()) <= 0.005 * a[..., :3].mean()
+    assert int(r.stats().closest_rays) == int(st.closest_rays) or \
+        abs(int(r.stats().closest_rays) - int(st.closest_rays)) <= 0.005 * st.closest_rays
+
+
+# ---- drain kernel ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("scene", ["spheres", "cornell", "smoke"])
+def test_drain_kernel_equals_wavefront_iterations(lib, scene):
+    """The last <= 16 Ki paths of a render are finished by k_drain (one thread per path, trace + shade + shadow
+    in one loop) instead of ~45 nearly empty wavefront iterations.  With one frame every pixel receives exactly
+    one sample, so the two ways must give the same image bit for bit and the same ray counts."""
+    W, H = 160, 96
+    sc = {"spheres": lambda: h.build_spheres(22, W=W, H=H, lib=lib),
+          "cornell": lambda: h.build_cornell(W, H, lib),
+          "smoke": lambda: h.build_smoke_scene(W, H, lib)}[scene]()
+    sc.commit()
+    r = pt.Renderer(sc, W, H)
+    old = os.environ.get("PTB200_DRAIN_MAX")
+    try:
+        os.environ["PTB200_DRAIN_MAX"] = "0"
+        r.render(5, 1, clear=True)
+        a, sa = r.read_accum(), r.stats()
+        os.environ.pop("PTB200_DRAIN_MAX")
+        r.render(5, 1, clear=True)
+        b, sb = r.read_accum(), r.stats()
+    finally:
+        if old is None:
+            os.environ.pop("PTB200_DRAIN_MAX", None)
+        else:
+            os.environ["PTB200_DRAIN_MAX"] = old
+    assert sa.drained_paths == 0 and sb.drained_paths == 1
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    assert sa.closest_rays == sb.closest_rays and sa.shadow_rays == sb.shadow_rays
+    assert sb.iterations < sa.iterations
+
+
+# ---- stale scenes ---------------------------------------------------------------------------------------------
+def test_modified_scene_is_refused_until_recommitted(lib):
+    """add_* / set_* after a commit release or replace device buffers: an existing renderer must refuse the scene
+    (PT_ERR_STATE) instead of launching kernels on them (advisor finding, round 1)."""
+    W, H = 48, 48
+    sc = h.build_cornell(W, H, lib)
+    sc.commit()
+    r = pt.Renderer(sc, W, H)
+    r.render(0, 1)
+    before = r.read_accum()
+    sc.add_spheres([pt.Sphere(pt.F3(278, 100, 278), 60.0)], [1])
+    with pytest.raises(pt.PtError):
+        r.render(0, 1, clear=True)
+    with pytest.raises(pt.PtError):
+        sc.trace(np.zeros(4, dtype=pt.RAY_DTYPE))
+    sc.commit()
+    r.render(0, 1, clear=True)
+    after = r.read_accum()
+    a, _ = h.OracleScene(sc).render(W, H, 0, 1)
+    assert (pixel_diff(after, a) > 1e-3).mean() <= 0.01
+    assert not np.array_equal(before, after)
+
+
+def test_camera_shutter_change_needs_a_new_commit(lib):
+    """The boxes of moving spheres cover the shutter interval of the camera the BVH was built for: a camera with
+    another interval un-commits the scene (silently missed hits otherwise; advisor finding, round 1).  A camera
+    change that keeps the interval stays a cheap update."""
+    W, H = 72, 48
+    sc = h.build_motion_scene(W, H, lib)
+    sc.commit()
+    r = pt.Renderer(sc, W, H)
+    r.render(0, 1)
+    cam = sc.desc().camera
+    cam2 = pt.Camera.from_buffer_copy(bytes(cam))
+    cam2.origin[0] += 0.25                       # same shutter: no rebuild needed
+    sc.set_camera(cam2)
+    r.render(0, 1, clear=True)
+    cam3 = pt.Camera.from_buffer_copy(bytes(cam))
+    cam3.time0, cam3.time1 = 2.0, 3.0            # extrapolated motion: outside every box of the old build
+    sc.set_camera(cam3)
+    with pytest.raises(pt.PtError):
+        r.render(0, 1, clear=True)
+    sc.commit()
+    r.render(0, 2, clear=True)
+    g = r.read_accum()
+    a, st = h.OracleScene(sc).render(W, H, 0, 2)
+    assert (pixel_diff(g, a) > 1e-3).mean() <= 0.015
+    assert abs(int(r.stats().closest_rays) - int(st.closest_rays)) <= 0.01 * st.closest_rays
+
+
+def test_switching_env_sampling_off_needs_a_new_commit(lib):
+    W = H = 48
+    sc = h.build_mesh_scene(24, W, H, lib, env_nee=True)
+    sc.commit()
+    r = pt.Renderer(sc, W, H)
+    r.render(0, 1)
+    m = sc.desc().miss
+    m.env_nee = 0
+    sc.set_miss(m)
+    with pytest.raises(pt.PtError):
+        r.render(0, 1, clear=True)
+    sc.commit()
+    r.render(0, 1, clear=True)
+    g = r.read_accum()
+    ref = h.build_mesh_scene(24, W, H, lib, env_nee=False)
+    ref.commit()
+    r2 = pt.Renderer(ref, W, H)
+    r2.render(0, 1)
+    assert np.array_equal(g.view(np.uint32), r2.read_accum().view(np.uint32))
+
+
+# ---- fixed limits ---------------------------------------------------------------------------------------------
+def test_fixed_limits_are_enforced_and_usable(lib):
+    """PT_MAX_PIXELS = 2^23 and PT_MAX_DEPTH = 255 (the 64-byte path record packs pixel | depth | specular flag into
+    32 bits): the limits themselves work, one more is refused."""
+    sc = h.build_cornell(64, 64, lib)
+    sc.commit()
+    with pytest.raises(pt.PtError):
+        pt.Renderer(sc, 4096, 2049)
+    r = pt.Renderer(sc, 4096, 2048)              # exactly 2^23 pixels
+    r.set_pool(1 << 20)
+    r.render(0, 1, max_depth=2)
+    acc = r.read_accum()
+    assert (acc[..., 3] == 1).all()
+    assert acc[0, 0, :3].sum() >= 0 and np.isfinite(acc).all()
+    # the last pixel index (2^23 - 1) lands in its own pixel: the image is not all black in its last row
+    small = pt.Renderer(sc, 64, 64)
+    with pytest.raises(pt.PtError):
+        small.render(0, 1, max_depth=256)
+    small.render(0, 2, max_depth=255, russian=False)
+    a, _ = h.OracleScene(sc).render(64, 64, 0, 2, max_depth=255, russian=False)
+    assert (pixel_diff(small.read_accum(), a) > 1e-3).mean() <= 0.015
+    # max_depth 0: the loop body never runs (raygen.cu:76,122): black, but counted
+    small.render(0, 3, max_depth=0, clear=True)
+    z = small.read_accum()
+    assert (z[..., 3] == 3).all() and (z[..., :3] == 0).all()
+
+
+# ---- hit ids at the top of configuration 4's range -------------------------------------------------------------
+def test_hit_ids_bit_exact_10m_triangles(lib):
+    """>= 1 M rays (camera + three generations of cosine-bounced rays) on the 10 M-triangle mesh of
+    configuration 4 (programs/hitables/triangle.cu:26-58 is the test every leaf runs)."""
+    sc = h.build_mesh_scene(2237, 512, 512, lib)
+    sc.commit()
+    info = sc.bvh_info()
+    assert info.n_prims == 2 * 2237 * 2237 and info.n_leaf_records == info.n_prims
+    orc = h.OracleScene(sc, mode=2)
+    cam = orc.camera_rays(512, 512, 0)
+    b1 = orc.bounce_rays(cam, 1)
+    b2 = orc.bounce_rays(b1, 2)
+    b3 = orc.bounce_rays(b2, 3)
+    rays = np.concatenate([cam, b1, b2, b3])
+    assert len(rays) >= 1_000_000
+    ho, _ = orc.trace(rays)
+    hg = sc.trace(rays)
+    ok = same_hits(ho, hg)
+    assert ok.all(), f"{(~ok).sum()} of {len(rays)} rays differ"
+    assert (ho["prim"] >= 0).mean() > 0.2
+
+
+# ---- full-size per-pixel parity ---------------------------------------------------------------------------------
+def test_full_size_c1_per_pixel(lib):
+    """C1 exactly as BASELINE.json states it: Cornell box 512x512 @ 64 spp, same frames on both sides.  A pixel is
+    the sum of 64 samples; a flipped path changes it by at most one sample's radiance (<= the light's emission)."""
+    W = H = 512
+    sc = h.build_cornell(W, H, lib)
+    sc.commit()
+    r = pt.Renderer(sc, W, H)
+    r.render(0, 64)
+    g = r.read_accum()
+    a, st = h.OracleScene(sc).render(W, H, 0, 64)
+    assert (g[..., 3] == 64).all()
+    d = pixel_diff(g, a) / 64.0
+    frac = float((d > 1e-3).mean())
+    print(f"C1 full size: {frac:.5f} of pixels differ by > 1e-3 in the mean, max {d.max():.4f}, "
+          f"rmse {h.rmse(g[..., :3] / 64, a[..., :3] / 64):.2e}")
+    assert frac <= 0.01
+    assert d.max() <= 2 * 7.0 / 64.0 + 1e-3          # at most a couple of flipped paths in any pixel (emission 7)
+    assert h.rmse(np.sqrt(np.clip(g[..., :3] / 64, 0, 1)), np.sqrt(np.clip(a[..., :3] / 64, 0, 1))) <= 2e-3
+    assert abs(int(r.stats().closest_rays) - int(st.closest_rays)) <= 1e-3 * st.closest_rays
+    assert abs(int(r.stats().shadow_rays) - int(st.shadow_rays)) <= 1e-3 * st.shadow_rays
+
+
+def test_full_resolution_c3_per_pixel(lib):
+    """C3's scene at its full 1024x1024 resolution, 8 of its 1024 spp (the oracle needs two minutes for all)."""
+    W = H = 1024
+    sc = h.build_material_zoo(W, H, lib)
+    sc.commit()
+    r = pt.Renderer(sc, W, H)
+    r.render(0, 8)
+    g = r.read_accum()
+    a, st = h.OracleScene(sc).render(W, H, 0, 8)
+    d = pixel_diff(g, a) / 8.0
+    frac = float((d > 1e-3).mean())
+    print(f"C3 full resolution: {frac:.5f} of pixels differ by > 1e-3 in the mean")
+    assert (g[..., 3] == 8).all() and frac <= 0.02
+    assert abs(g[..., :3].mean() - a[..., :3].mean()) <= 0.005 * a[..., :3].mean()
+    assert abs(int(r.stats().closest_rays) - int(st.closest_rays)) <= 2e-3 * st.closest_rays
+
+
+# ---- the measured bar of the fixed-seed tests --------------------------------------------------------------------
+FIXED_SEED_SCENES = {
+    "cornell": lambda lib: h.build_cornell(64, 64, lib),
+    "zoo": lambda lib: h.build_material_zoo(64, 64, lib),
+    "spheres488": lambda lib: h.build_spheres(22, W=64, H=64, lib=lib),
+    "mesh8k": lambda lib: h.build_mesh_scene(64, 64, 64, lib),
+    "motion": lambda lib: h.build_motion_scene(64, 64, lib),
+    "backdrop": lambda lib: h.build_backdrop(64, 64, pt.MISS_HDR, 1, lib),
+}
+
+
+@pytest.mark.parametrize("name", list(FIXED_SEED_SCENES))
+def test_fixed_seed_differences_are_libm_flips(lib, name):
+    """GPU and oracle draw the same random numbers and run the same arithmetic (kernel bodies == oracle bit for bit
+    on one libm: tests/test_hostsim.py), so a pixel can only differ where a libm function returned a neighbouring
+    float and a branch went the other way.  That is MEASURED here instead of assumed: liboracle_ulp.so is the oracle
+    with every libm result nudged by -1/0/+1 ulp, and the image it renders differs from the oracle's in the pixels
+    that are sensitive to last-bit libm rounding.  The GPU image must not differ in more pixels than a small multiple
+    of that, and - flips being whole-path changes - every difference is bounded by a few samples' radiance."""
+    W = H = 64
+    n = 16
+    sc = FIXED_SEED_SCENES[name](lib)
+    sc.commit()
+    r = pt.Renderer(sc, W, H)
+    r.render(0, n)
+    g = r.read_accum()
+    a, _ = h.OracleScene(sc).render(W, H, 0, n)
+    u, _ = h.OracleScene(sc, 0, "_ulp").render(W, H, 0, n)
+    d_gpu, d_ulp = pixel_diff(g, a), pixel_diff(u, a)
+    f_gpu, f_ulp = float((d_gpu > 1e-3).mean()), float((d_ulp > 1e-3).mean())
+    tiny_gpu = float(((d_gpu > 0) & (d_gpu <= 1e-3)).mean())
+    print(f"{name}: GPU differs in {f_gpu:.5f} of pixels (> 1e-3), ulp-noise oracle in {f_ulp:.5f}; "
+          f"GPU sub-threshold differences in {tiny_gpu:.5f}; max |d| GPU {d_gpu.max():.3f} ulp {d_ulp.max():.3f}")
+    assert (g[..., 3] == n).all()
+    assert f_gpu <= 3.0 * f_ulp + 0.004, (f_gpu, f_ulp)
+    # a flipped path changes the pixel by at most its own radiance; scenes here emit <= 7 per sample (Cornell light)
+    peak = max(float(a[..., :3].max()) / n, 1.0) * 4
+    assert d_gpu.max() <= peak * 3

@@ -269,3 +269,93 @@ def test_image_texture_loads_png_and_jpeg_like_the_reference(host, tmp_path):
     assert (w.value, hh.value) == (20, 10)
     assert np.array_equal(out[..., :3], rgb[::-1].astype(np.float32) / np.float32(255.0))
     assert np.all(out[..., 3] == np.float32(1.0) / np.float32(255.0))
+
+
+# ---- malformed inputs (advisor findings, round 1): every reader must fail or finish, never hang / overrun ----
+@pytest.mark.timeout(60)
+def test_truncated_png_is_rejected_not_inflated_for_ever(host, tmp_path):
+    """A deflate stream that ends inside a block used to decode zero bits for ever (an all-zero code that is a
+    literal grows the output until memory runs out); the bit reader now reports the underflow."""
+    img = make_image(64, 48)
+    good = tmp_path / "good.png"
+    PIL.fromarray(img).save(good)
+    data = good.read_bytes()
+    assert decode(host, good) is not None
+    # keep the header + IHDR and a shortened IDAT with a fixed-up chunk length / CRC
+    pos = 8
+    chunks = []
+    while pos < len(data):
+        ln, = struct.unpack(">I", data[pos:pos + 4])
+        chunks.append((data[pos + 4:pos + 8], data[pos + 8:pos + 8 + ln]))
+        pos += 12 + ln
+    out = data[:8]
+    for typ, body in chunks:
+        if typ == b"IDAT":
+            body = body[:len(body) // 3]
+        out += struct.pack(">I", len(body)) + typ + body + struct.pack(">I", zlib.crc32(typ + body) & 0xffffffff)
+    bad = tmp_path / "truncated.png"
+    bad.write_bytes(out)
+    assert decode(host, bad) is None
+
+
+def _jpeg_with_sampling(tmp_path, name, sampling_bytes):
+    """baseline JPEG from Pillow with the SOF0 sampling-factor bytes overwritten"""
+    img = make_image(48, 32)
+    p = tmp_path / name
+    PIL.fromarray(img).save(p, quality=90, subsampling=0)
+    b = bytearray(p.read_bytes())
+    i = b.find(b"\xff\xc0")
+    assert i > 0
+    nc = b[i + 9]
+    for c in range(nc):
+        b[i + 11 + 3 * c] = sampling_bytes[c]
+    p.write_bytes(bytes(b))
+    return p
+
+
+@pytest.mark.timeout(60)
+def test_jpeg_with_non_integer_sampling_ratio_is_rejected(host, tmp_path):
+    """h = 3 next to h = 2 (ratio 3/2) took the 1:1 copy path and read W bytes from a narrower plane"""
+    assert decode(host, _jpeg_with_sampling(tmp_path, "h32.jpg", [0x31, 0x21, 0x11])) is None
+
+
+@pytest.mark.timeout(60)
+def test_jpeg_with_short_sos_is_rejected(host, tmp_path):
+    img = make_image(32, 32)
+    p = tmp_path / "sos.jpg"
+    PIL.fromarray(img).save(p, quality=90)
+    b = bytearray(p.read_bytes())
+    i = b.find(b"\xff\xda")
+    b[i + 2:i + 4] = struct.pack(">H", 3)     # SOS length too short for its own component list
+    p.write_bytes(bytes(b[:i + 5]))
+    assert decode(host, p) is None
+
+
+def _mesh_probe(host, path):
+    host.pth_mesh_probe.argtypes = [C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    n, hn, hu = C.c_int(), C.c_int(), C.c_int()
+    rc = host.pth_mesh_probe(str(path).encode(), C.byref(n), C.byref(hn), C.byref(hu))
+    return rc, n.value, hn.value, hu.value
+
+
+@pytest.mark.timeout(60)
+def test_obj_face_with_trailing_comment_terminates(host, tmp_path):
+    """strtol does not advance on a non-numeric token: the face loop used to push corners for ever"""
+    p = tmp_path / "c.obj"
+    p.write_text("v 0 0 0\nv 1 0 0\nv 0 1 0\nv 1 1 0\nf 1 2 3 # first\nf 2 4 3 garbage\n")
+    rc, n, hn, hu = _mesh_probe(host, p)
+    assert rc == 0 and n == 2 and not hn and not hu
+
+
+@pytest.mark.timeout(60)
+def test_obj_with_out_of_range_normal_and_uv_indices_drops_them(host, tmp_path):
+    """vn / vt indices beyond the arrays were only checked for >= 0: an out-of-bounds read.  Like a mesh without
+    normals, such a mesh falls back to geometric normals and uv = 0."""
+    p = tmp_path / "n.obj"
+    p.write_text("v 0 0 0\nv 1 0 0\nv 0 1 0\nvn 0 0 1\nvt 0 0\nf 1/1/1 2/1/7 3/9/1\n")
+    rc, n, hn, hu = _mesh_probe(host, p)
+    assert rc == 0 and n == 1 and not hn and not hu
+    q = tmp_path / "ok.obj"
+    q.write_text("v 0 0 0\nv 1 0 0\nv 0 1 0\nvn 0 0 1\nvt 0 0\nf 1/1/1 2/1/1 3/1/1\n")
+    rc, n, hn, hu = _mesh_probe(host, q)
+    assert rc == 0 and n == 1 and hn and hu

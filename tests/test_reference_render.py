@@ -38,17 +38,7 @@ def build_empty(W, H, constant=False):
     return s
 
 
-def build_backdrop(W, H, miss_type, spherical=1):
-    """a mirror sphere and a diffuse one in front of an image background (miss.cu image_background /
-    environmental_mapping): the miss program's own (u, v) arithmetic decides every pixel"""
-    s = pt.Scene(None)
-    s.set_textures([h.tex_const(0.8, 0.6, 0.2), h.tex_const(0.9)])
-    s.set_materials([h.material(pt.MAT_LAMBERTIAN, 0), h.material(pt.MAT_METAL, 1, p0=0.0)])
-    s.add_spheres([pt.Sphere(pt.F3(-1.1, 0, 0), 1.0), pt.Sphere(pt.F3(1.1, 0, 0), 1.0)], [0, 1])
-    s.set_camera(h.make_camera([0, 0.5, -6], [0, 0, 0], [0, 1, 0], 40.0, W / H, 0.0, 6.0))
-    img = s.add_image(h.synthetic_hdri(64, 32))
-    s.set_miss(pt.Miss(miss_type, pt.F3(0, 0, 0), pt.F3(0, 0, 0), img, spherical, 0))
-    return s
+build_backdrop = h.build_backdrop
 
 
 def scene_table():
