@@ -262,12 +262,13 @@ int pt_bvh_build(pt_scene* s) {
   uint2* wb = (uint2*)ar.take((size_t)n * 8 + 64);
   uint4* nodes8_tmp = (uint4*)ar.take(n8 * 80);
   // small device-resident state, zeroed once:
-  //   [0..7] scene bounds (floats)   [8..15] treelet root counts per pass   [16] BVH8 node counter
-  //   [17] leaf counter   [32..32+MAXLEV] collapse work count per level   doubles at byte 1024: SAH sums
-  constexpr int MAXLEV = 160;
+  //   [0..7] scene bounds (floats)   [16] BVH8 node counter   [17] leaf counter
+  //   [32..32+MAXLEV] collapse work count per level   [200..200+MAXPASS) treelet root counts per (round, pass)
+  //   doubles at byte 1024: SAH sums
+  constexpr int MAXLEV = 160, MAXPASS = 48;
   int* st = (int*)ar.take(2048);
   float* sbounds = (float*)st;
-  int* pass_roots = st + 8;
+  int* pass_roots = st + 200;
   int* d_cnt = st + 16;
   int* level_count = st + 32;
   double* cost = (double*)((char*)st + 1024);
@@ -316,18 +317,23 @@ int pt_bvh_build(pt_scene* s) {
     PT_CUDA(cudaGetLastError());
     tm.mark("refit");
     k_sah_cost<<<nblk(n - 1), TB>>>(t, cost);
-    // hierarchical passes: leaves -> treelets of <= 64 leaves -> treelets of <= 64 treelets -> ...
-    // A pass-k root has more than lo_k leaves and disjoint subtrees, so there are at most n / lo_k of them:
-    // the grid is sized for that bound and the actual count never leaves the device.
-    long long lo = 1, hi = PT_TREELET;
-    for (int pass = 0; pass < 8 && lo < (long long)n; pass++) {
-      k_treelet_mark<<<nblk(n - 1), TB>>>(t, (int)lo, hi, roots, pass_roots + pass);
-      PT_CUDA(cudaGetLastError());
-      const long long bound = std::min<long long>(n - 1, (long long)n / lo + 1);
-      k_treelet_sah<<<nblk(bound, 64), 64>>>(t, (int)lo, roots, pass_roots + pass);
-      PT_CUDA(cudaGetLastError());
-      lo = hi;
-      hi *= PT_TREELET;
+    // hierarchical passes: leaves -> treelets of <= T leaves -> treelets of <= T treelets -> ..., one such
+    // sweep per entry of PT_TREELET_ROUNDS.  A pass-k root has more than lo_k leaves and roots are disjoint
+    // subtrees, so there are at most n / lo_k of them: the grid is sized for that bound and the actual count
+    // never leaves the device.
+    static const int rounds[] = PT_TREELET_ROUNDS;
+    int slot = 0;
+    for (int T : rounds) {
+      long long lo = 1, hi = T;
+      for (int pass = 0; pass < 12 && lo < (long long)n && slot < MAXPASS; pass++, slot++) {
+        k_treelet_mark<<<nblk(n - 1), TB>>>(t, (int)lo, hi, roots, pass_roots + slot);
+        PT_CUDA(cudaGetLastError());
+        const long long bound = std::min<long long>(n - 1, (long long)n / lo + 1);
+        k_treelet_sah<<<nblk(bound, 64), 64>>>(t, (int)lo, roots, pass_roots + slot);
+        PT_CUDA(cudaGetLastError());
+        lo = hi;
+        hi *= T;
+      }
     }
     tm.mark("treelet sah");
     k_sah_cost<<<nblk(n - 1), TB>>>(t, cost + 1);

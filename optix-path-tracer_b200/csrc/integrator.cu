@@ -531,6 +531,26 @@ __global__ void __launch_bounds__(PT_TRACE_THREADS, PT_TRACE_MINBLOCKS) k_trace_
 }
 
 
+// ray sets on deep trees: two node steps per vote round, like k_trace_deep (never flat)
+template <bool COUNT, bool SPECIAL>
+__global__ void __launch_bounds__(PT_TRACE_THREADS, PT_TRACE_MINBLOCKS) k_trace_rays_deep(SceneDev sc, const pt_ray* rays, int n, pt_hit* hits,
+                                                                      unsigned long long* counters, SchedParams sched) {
+  __shared__ uint2 s_stack[PT_SMEM_STACK * PT_TRACE_THREADS];
+  RaySetPolicy pol{rays, hits, sc.camera.time0};
+  uint32_t cn = 0, cl = 0;
+  trace_persistent<COUNT, SPECIAL, PT_DEEP_BURST>(sc, n, (int*)(counters + 2), pol, s_stack, sched, (int*)(counters + 3), cn, cl);
+  if (COUNT) {
+    for (int o = 16; o > 0; o >>= 1) {
+      cn += __shfl_xor_sync(0xffffffffu, cn, o);
+      cl += __shfl_xor_sync(0xffffffffu, cl, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+      atomicAdd(counters, (unsigned long long)cn);
+      atomicAdd(counters + 1, (unsigned long long)cl);
+    }
+  }
+}
+
 // ---- drain: the last few thousand paths, one thread each, run to their end -------------------------------
 // After the last sample has been generated a render used to finish in ~45 nearly empty wavefront iterations (a few
 // paths survive Russian roulette up to depth 50): each costs the dependent latency of one traversal plus six or
@@ -710,6 +730,16 @@ SchedParams sched_params_rays(const SceneDev& sc) {
   return p;
 }
 
+// deep trees (>= PTB200_DEEP_MIN primitives, default 64 Ki) take two node steps per vote round
+long long deep_min_prims() {
+  static const long long v = getenv("PTB200_DEEP_MIN") ? atoll(getenv("PTB200_DEEP_MIN")) : 65536;
+  return v;
+}
+bool rays_deep(const SceneDev& sc, const SchedParams& sched) {
+  static const int on = getenv("PTB200_DEEP_RAYS") ? atoi(getenv("PTB200_DEEP_RAYS")) : 1;
+  return on && deep_min_prims() > 0 && sc.n_prims >= deep_min_prims() && !sched.flat;
+}
+
 // resident CTAs per SM of the persistent traversal kernels (they must all be co-resident)
 int g_trace_bpm[PT_MAX_DEVICES][2] = {};
 int trace_blocks_per_sm(bool special) {
@@ -721,11 +751,17 @@ int trace_blocks_per_sm(bool special) {
       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d, k_trace_deep<false, true>, PT_TRACE_THREADS, 0);
       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_shadow<false, true>, PT_TRACE_THREADS, 0);
       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c, k_trace_rays<false, true>, PT_TRACE_THREADS, 0);
+      int c2 = 0;
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c2, k_trace_rays_deep<false, true>, PT_TRACE_THREADS, 0);
+      c = std::min(c, c2);
     } else {
       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_trace<false, false>, PT_TRACE_THREADS, 0);
       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d, k_trace_deep<false, false>, PT_TRACE_THREADS, 0);
       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_shadow<false, false>, PT_TRACE_THREADS, 0);
       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c, k_trace_rays<false, false>, PT_TRACE_THREADS, 0);
+      int c2 = 0;
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c2, k_trace_rays_deep<false, false>, PT_TRACE_THREADS, 0);
+      c = std::min(c, c2);
     }
     bpm = std::max(1, std::min(std::min(a, d), std::min(b, c)));
 #ifdef PT_TRACE_BPM
@@ -1069,8 +1105,7 @@ int pt_render(pt_renderer* r, int32_t first_frame, int32_t nframes, int32_t max_
   const SchedParams sched = sched_params(sc);
   // deep trees (>= 64 Ki primitives: five or more BVH8 levels) take two node steps per vote round for closest-hit
   // rays; PTB200_DEEP_MIN overrides the size (dev), 0 switches it off
-  static const long long deep_min = getenv("PTB200_DEEP_MIN") ? atoll(getenv("PTB200_DEEP_MIN")) : 65536;
-  const bool deep = deep_min > 0 && sc.n_prims >= deep_min && !sched.flat;
+  const bool deep = deep_min_prims() > 0 && sc.n_prims >= deep_min_prims() && !sched.flat;
   // shadow rays keep the BVH walk even in tiny scenes: they start on a surface and aim at a light, the one
   // node test culls most primitives, and testing all of them flat was 7 % slower end to end (C1, C3);
   // closest-hit rays are 25-45 % faster flat.  PTB200_FLAT_SHADOW=1 overrides (dev)
@@ -1379,8 +1414,13 @@ int pt_trace_rays_device(pt_scene* scene, const void* d_rays, int64_t n, void* d
   PT_CUDA(cudaMallocAsync((void**)&dc, 32, st));
   PT_CUDA(cudaMemsetAsync(dc, 0, 32, st));
   const bool special = scene->dev.special_mask != 0;
-  PT_LAUNCH_TRACE(k_trace_rays, false, special, sm_count() * trace_blocks_per_sm(special), st, scene->dev,
-                  (const pt_ray*)d_rays, (int)n, (pt_hit*)d_hits, dc, sched_params_rays(scene->dev));
+  const SchedParams sched = sched_params_rays(scene->dev);
+  if (rays_deep(scene->dev, sched))
+    PT_LAUNCH_TRACE(k_trace_rays_deep, false, special, sm_count() * trace_blocks_per_sm(special), st, scene->dev,
+                    (const pt_ray*)d_rays, (int)n, (pt_hit*)d_hits, dc, sched);
+  else
+    PT_LAUNCH_TRACE(k_trace_rays, false, special, sm_count() * trace_blocks_per_sm(special), st, scene->dev,
+                    (const pt_ray*)d_rays, (int)n, (pt_hit*)d_hits, dc, sched);
   PT_CUDA(cudaGetLastError());
   PT_CUDA(cudaFreeAsync(dc, st));
   return PT_OK;
@@ -1406,8 +1446,13 @@ int pt_trace_rays(pt_scene* scene, const pt_ray* rays, int64_t n, pt_hit* hits, 
   PT_CUDA(cudaMemcpy(dr.p, rays, (size_t)n * sizeof(pt_ray), cudaMemcpyHostToDevice));
   const bool special = scene->dev.special_mask != 0;
   const int grid = sm_count() * trace_blocks_per_sm(special);
-  PT_LAUNCH_TRACE(k_trace_rays, counters != nullptr, special, grid, (cudaStream_t)0, scene->dev, dr.as<pt_ray>(), (int)n,
-                  dh.as<pt_hit>(), dc.as<unsigned long long>(), sched_params_rays(scene->dev));
+  const SchedParams sched = sched_params_rays(scene->dev);
+  if (rays_deep(scene->dev, sched))
+    PT_LAUNCH_TRACE(k_trace_rays_deep, counters != nullptr, special, grid, (cudaStream_t)0, scene->dev, dr.as<pt_ray>(), (int)n,
+                    dh.as<pt_hit>(), dc.as<unsigned long long>(), sched);
+  else
+    PT_LAUNCH_TRACE(k_trace_rays, counters != nullptr, special, grid, (cudaStream_t)0, scene->dev, dr.as<pt_ray>(), (int)n,
+                    dh.as<pt_hit>(), dc.as<unsigned long long>(), sched);
   PT_CUDA(cudaGetLastError());
   PT_CUDA(cudaMemcpy(hits, dh.p, (size_t)n * sizeof(pt_hit), cudaMemcpyDeviceToHost));
   unsigned long long hc[4];
