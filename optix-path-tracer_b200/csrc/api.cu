@@ -426,8 +426,8 @@ int pt_scene_commit(pt_scene* s) {
   s->built_time1 = s->camera.time1;
 
   SceneDev& d = s->dev;
-  d.nodes8 = s->d_nodes8.as<uint4>();
-  d.leaves = s->d_leaves.as<LeafRec>();
+  d.nodes8 = s->d_bvh.as<uint4>();
+  d.leaves = (const LeafRec*)((const char*)s->d_bvh.p + s->bvh_leaves_off);
   d.prim_ref = s->d_prim_ref.as<pt_prim_ref>();
   d.prim_leaf = s->d_prim_leaf.as<int>();
   d.xforms = s->d_xforms.as<pt_xform>();

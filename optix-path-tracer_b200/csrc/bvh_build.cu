@@ -241,7 +241,7 @@ int pt_bvh_build(pt_scene* s) {
                                           (const uint32_t*)nullptr, (uint32_t*)nullptr, n, 0, 63));
   const size_t n8 = (size_t)(n > 1 ? n : 2);
   const size_t need = (size_t)n * (16 + 16 + 8 + 8 + 4 + 4 + 4 + 8 + 8) + (size_t)ni * (sizeof(Bvh2Node) + 4 + 4 + 4 + 4) +
-                      n8 * 80 + cub_bytes + 64 * 256 + 4096;
+                      n8 * 80 + (size_t)n * sizeof(LeafRec) + cub_bytes + 64 * 256 + 4096;
   Arena& ar = g_arena[dev];
   if (ar.buf.bytes < need) PT_CUDA(ar.buf.alloc(need + need / 8));
   ar.off = 0;
@@ -261,6 +261,7 @@ int pt_bvh_build(pt_scene* s) {
   uint2* wa = (uint2*)ar.take((size_t)n * 8 + 64);
   uint2* wb = (uint2*)ar.take((size_t)n * 8 + 64);
   uint4* nodes8_tmp = (uint4*)ar.take(n8 * 80);
+  LeafRec* leaves_tmp = (LeafRec*)ar.take((size_t)n * sizeof(LeafRec));
   // small device-resident state, zeroed once:
   //   [0..7] scene bounds (floats)   [16] BVH8 node counter   [17] leaf counter
   //   [32..32+MAXLEV] collapse work count per level   [200..200+MAXPASS) treelet root counts per (round, pass)
@@ -342,13 +343,12 @@ int pt_bvh_build(pt_scene* s) {
   // collapse: level-synchronous work lists; the per-level counts stay on the device.  An inner BVH8 child holds
   // more than 3 primitives, so a level has at most min(8^l, n / 4 + 1) items: launch for that bound.  Levels are
   // launched in batches of 16 and the host looks at the counters once per batch (usually once in total).
-  PT_CUDA(s->d_leaves.alloc((size_t)n * sizeof(LeafRec)));
   PT_CUDA(s->d_prim_leaf.alloc((size_t)n * 4));
   Collapse c;
   c.t = t;
   c.in = in;
   c.nodes8 = nodes8_tmp;
-  c.leaves = s->d_leaves.as<LeafRec>();
+  c.leaves = leaves_tmp;
   c.prim_leaf = s->d_prim_leaf.as<int>();
   c.node_counter = d_cnt;
   c.leaf_counter = d_cnt + 1;
@@ -377,9 +377,13 @@ int pt_bvh_build(pt_scene* s) {
     pt_set_error("BVH collapse wrote %d leaf records for %d primitives", hcnt[1], n);
     return PT_ERR_INVALID;
   }
-  // the node array at its final size
-  PT_CUDA(s->d_nodes8.alloc((size_t)hcnt[0] * 80));
-  PT_CUDA(cudaMemcpyAsync(s->d_nodes8.p, nodes8_tmp, (size_t)hcnt[0] * 80, cudaMemcpyDeviceToDevice, 0));
+  // nodes (at their final size) and leaf records into one block, nodes first
+  s->bvh_nodes_bytes = (size_t)hcnt[0] * 80;
+  s->bvh_leaves_off = (s->bvh_nodes_bytes + 255) & ~(size_t)255;
+  PT_CUDA(s->d_bvh.alloc(s->bvh_leaves_off + (size_t)n * sizeof(LeafRec)));
+  PT_CUDA(cudaMemcpyAsync(s->d_bvh.p, nodes8_tmp, s->bvh_nodes_bytes, cudaMemcpyDeviceToDevice, 0));
+  PT_CUDA(cudaMemcpyAsync((char*)s->d_bvh.p + s->bvh_leaves_off, leaves_tmp, (size_t)n * sizeof(LeafRec),
+                          cudaMemcpyDeviceToDevice, 0));
   double cost_lbvh = 0.0, cost_ref = 0.0;
   if (n > 1) {
     double hc[2];

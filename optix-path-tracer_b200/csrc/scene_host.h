@@ -130,7 +130,11 @@ struct pt_scene : SceneHostData {
   DevBuf d_prim_ref, d_spheres, d_rects, d_boxes, d_tri_v, d_tri_n, d_tri_uv, d_tri_tex, d_xforms;
   DevBuf d_materials, d_textures, d_texvec, d_texdata, d_images, d_lights;
   std::vector<DevBuf*> d_image_texels;
-  DevBuf d_nodes8, d_leaves, d_prim_leaf, d_env_prob, d_env_idx, d_env_pdf;
+  // BVH8 nodes and leaf records live in ONE block, nodes first (one allocation per commit; an L2 access-policy
+  // window over it was measured and not kept: profiles/r02_l2_persist_ab.md)
+  DevBuf d_bvh;
+  size_t bvh_nodes_bytes = 0, bvh_leaves_off = 0;
+  DevBuf d_prim_leaf, d_env_prob, d_env_idx, d_env_pdf;
   DevBuf build_arena;  // scratch of the BVH build, kept across commits (grow-only)
   SceneDev dev{};
   pt_bvh_info info{};
