@@ -123,6 +123,7 @@ struct CtrlPoll {
 
 struct Params {
   int W, H, max_depth, russian, pool;  // (the first frame index lives in Ctrl so captured graphs stay valid)
+  int tiled;                           // camera samples enumerated in 8x4 tiles (W % 8 == 0 && H % 4 == 0)
   float4* accum;
   uint32_t c16, c1;  // the constants 16 and 1 as run-time values, see pt_tea64_balanced
 };
@@ -230,7 +231,20 @@ __global__ void k_generate(SceneDev sc, Params p, const Ctrl* c, PathBuf cur) {
     const uint32_t fr = t / npix;
     int frame = frame0 + (int)fr;
     uint32_t pix = t - fr * npix;
-    int x = pix % p.W, y = pix / p.W;
+    int x, y;
+    if (p.tiled) {
+      // samples of a frame are enumerated in 8x4-pixel tiles: the 32 camera rays a warp fetches together cover a
+      // compact patch of the image instead of a 32-pixel strip of one scanline, so they walk the same BVH nodes for
+      // longer.  The seed depends on (pixel, frame) only (raygen.cu:150): the set of samples per pixel is unchanged.
+      const uint32_t tile = pix >> 5, in = pix & 31u, tiles_x = (uint32_t)p.W >> 3;
+      const uint32_t ty = tile / tiles_x, tx = tile - ty * tiles_x;
+      x = (int)(tx * 8u + (in & 7u));
+      y = (int)(ty * 4u + (in >> 3));
+      pix = (uint32_t)y * (uint32_t)p.W + (uint32_t)x;
+    } else {
+      x = pix % p.W;
+      y = pix / p.W;
+    }
     uint32_t seed;
     float3 o, d;
     seed = pt_tea64_balanced((uint32_t)p.W * (uint32_t)y + (uint32_t)x, (uint32_t)frame, p.c16, p.c1);
@@ -1069,6 +1083,7 @@ int pt_render(pt_renderer* r, int32_t first_frame, int32_t nframes, int32_t max_
   p.max_depth = max_depth;
   p.russian = russian;
   p.pool = r->pool;
+  p.tiled = (r->W % 8 == 0 && r->H % 4 == 0 && !getenv("PTB200_NO_TILES")) ? 1 : 0;
   p.accum = r->accum;
   p.c16 = 16u;
   p.c1 = 1u;

@@ -6,8 +6,9 @@ Bars (BASELINE.json north_star):
   2. per-pixel radiance at fixed seed for non-stochastic passes (Normal_Shader, depth-1):
      |diff| <= 2e-5 absolute (libm sinf/atan2f/... differ by <= 2 ulp between glibc and CUDA);
   3. stochastic passes at fixed seed: identical RNG streams, so images agree except where a
-     1-ulp libm difference flips a branch: <= 1.5 % of pixels may differ by > 1e-3, and the
-     image means agree to 1 %;
+     1-ulp libm difference flips a branch: <= 0.4 % of pixels may differ by > 1e-3 (1.2 % on the
+     material zoo), the image means agree to 1 %, and the GPU must not show more differing pixels than
+     the oracle with ulp-nudged libm does (tests/test_gpu_round2.py);
   4. converged images: RMSE on the gamma-encoded [0,1] image <= 0.02 against the oracle
      rendered with DIFFERENT frame indices (independent samples).
 """
@@ -120,7 +121,11 @@ def test_fixed_seed_radiance(lib, name):
     assert (g[..., 3] == 4).all()
     d = np.abs(g[..., :3] - a[..., :3]).max(axis=-1)
     frac = float((d > 1e-3).mean())
-    assert frac <= 0.015, f"{frac:.4f} of pixels differ"
+    # bars from what was observed on the B200 (round 2: <= 0.12 % on every scene but the material zoo, whose GGX /
+    # Ashikhmin-Shirley lobes amplify last-bit differences: 0.8 % at 16 spp) with a factor of ~3 of headroom; that
+    # these differences ARE last-bit libm flips is measured in tests/test_gpu_round2.py against the ulp-noise oracle
+    bar = 0.012 if name == "zoo" else 0.004
+    assert frac <= bar, f"{frac:.4f} of pixels differ"
     assert abs(g[..., :3].mean() - a[..., :3].mean()) <= 0.01 * a[..., :3].mean()
     s = r.stats()
     assert abs(int(s.closest_rays) - int(st.closest_rays)) <= 0.01 * st.closest_rays

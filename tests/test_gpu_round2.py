@@ -280,7 +280,9 @@ def test_fixed_seed_differences_are_libm_flips(lib, name):
     print(f"{name}: GPU differs in {f_gpu:.5f} of pixels (> 1e-3), ulp-noise oracle in {f_ulp:.5f}; "
           f"GPU sub-threshold differences in {tiny_gpu:.5f}; max |d| GPU {d_gpu.max():.3f} ulp {d_ulp.max():.3f}")
     assert (g[..., 3] == n).all()
-    assert f_gpu <= 3.0 * f_ulp + 0.004, (f_gpu, f_ulp)
+    # observed on the B200: GPU <= ulp-noise oracle on all six scenes (0.05 / 0.8 / 0.12 / 0 / 0.10 / 0 % against
+    # 0.10 / 1.4 / 0.12 / 0 / 0.15 / 0 %)
+    assert f_gpu <= 1.5 * f_ulp + 0.002, (f_gpu, f_ulp)
     # a flipped path changes the pixel by at most its own radiance; scenes here emit <= 7 per sample (Cornell light)
     peak = max(float(a[..., :3].max()) / n, 1.0) * 4
     assert d_gpu.max() <= peak * 3
