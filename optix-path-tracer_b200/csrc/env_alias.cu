@@ -6,7 +6,8 @@
 // mirror that answers pt_scene_get_desc for scenes that were never committed.
 //
 // Pipeline (n = W * H texels):
-//   k_env_row_sum    one thread per image row, serial in x (summation order is part of the result)
+//   k_env_row_sum    one warp per image row: 32 strided partial sums added in lane order (the summation order is
+//                    part of the result and is the same in the host mirror)
 //   k_env_total      one thread: total of the row sums in row order, 1 % floor, grand total
 //   k_env_pdf        per texel: pdf (float), q = pdf * n in 32.32 fixed point, light flag, deficit / excess
 //   cub scans        rank of each item among lights / heavies, deficit and excess prefix sums (uint64: exact)
@@ -15,6 +16,8 @@
 #include <cub/cub.cuh>
 
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 
 #include "env_alias_core.h"
 #include "scene_host.h"
@@ -25,12 +28,16 @@ struct EnvTotals {
   double total0, floor_w, total;
 };
 
+// one warp per image row: lane l sums the texels l, l + 32, ... (coalesced), lane 0 adds the 32 partials in order
 __global__ void k_env_row_sum(const float4* __restrict__ texels, int w, int h, const double* __restrict__ row_sin,
                               const EnvTotals* tot, int with_floor, double* __restrict__ row_sums) {
-  const int y = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (y >= h) return;
   const double fl = with_floor ? tot->floor_w : 0.0;
-  row_sums[y] = env_row_sum((const float*)(texels + (size_t)y * w), w, row_sin[y], fl);
+  const double part = env_row_partial((const float*)(texels + (size_t)y * w), w, lane, row_sin[y], fl);
+  double s = 0.0;
+  for (int l = 0; l < PT_ENV_LANES; l++) s += __shfl_sync(0xffffffffu, part, l);
+  if (lane == 0) row_sums[y] = s;
 }
 
 __global__ void k_env_total(const double* __restrict__ row_sums, int h, int n, int second, EnvTotals* tot) {
@@ -197,16 +204,22 @@ int pt_env_tables_build(pt_scene* s) {
   PT_CUDA(d_ldf.alloc(((size_t)n + 1) * 8));
   PT_CUDA(d_hex.alloc((size_t)n * 8));
   PT_CUDA(d_na.alloc(16));
+  const bool timing = getenv("PTB200_BUILD_TIMING") != nullptr;
+  cudaEvent_t te[4] = {};
+  if (timing)
+    for (auto& e : te) cudaEventCreate(&e);
+  if (timing) cudaEventRecord(te[0]);
   const int TB = 256;
-  const int gb = (n + TB - 1) / TB, gr = (h + 63) / 64;
+  const int gb = (n + TB - 1) / TB, gr = (h * 32 + 127) / 128;  // row sums: one warp per row, 4 rows per block
   EnvTotals* tot = d_tot.as<EnvTotals>();
-  k_env_row_sum<<<gr, 64>>>(texels, w, h, d_rs.as<double>(), tot, 0, d_rows.as<double>());
+  k_env_row_sum<<<gr, 128>>>(texels, w, h, d_rs.as<double>(), tot, 0, d_rows.as<double>());
   k_env_total<<<1, 1>>>(d_rows.as<double>(), h, n, 0, tot);
-  k_env_row_sum<<<gr, 64>>>(texels, w, h, d_rs.as<double>(), tot, 1, d_rows.as<double>());
+  k_env_row_sum<<<gr, 128>>>(texels, w, h, d_rs.as<double>(), tot, 1, d_rows.as<double>());
   k_env_total<<<1, 1>>>(d_rows.as<double>(), h, n, 1, tot);
   k_env_pdf<<<gb, TB>>>(texels, w, n, d_rs.as<double>(), tot, s->d_env_pdf.as<float>(), d_q.as<unsigned long long>(),
                         d_flag.as<int>(), d_def.as<unsigned long long>(), d_exc.as<unsigned long long>());
   PT_CUDA(cudaGetLastError());
+  if (timing) cudaEventRecord(te[1]);
   size_t t1 = 0, t2 = 0, t3 = 0;
   PT_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, t1, d_flag.as<int>(), d_lrank.as<int>(), n));
   PT_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, t2, d_def.as<unsigned long long>(), d_dfx.as<unsigned long long>(), n));
@@ -216,6 +229,7 @@ int pt_env_tables_build(pt_scene* s) {
   PT_CUDA(cub::DeviceScan::ExclusiveSum(d_tmp.p, tmp, d_flag.as<int>(), d_lrank.as<int>(), n));
   PT_CUDA(cub::DeviceScan::ExclusiveSum(d_tmp.p, tmp, d_def.as<unsigned long long>(), d_dfx.as<unsigned long long>(), n));
   PT_CUDA(cub::DeviceScan::InclusiveSum(d_tmp.p, tmp, d_exc.as<unsigned long long>(), d_exi.as<unsigned long long>(), n));
+  if (timing) cudaEventRecord(te[2]);
   k_env_scatter<<<gb, TB>>>(n, d_q.as<unsigned long long>(), d_lrank.as<int>(), d_dfx.as<unsigned long long>(),
                             d_exi.as<unsigned long long>(), d_rank.as<int>(), d_lidx.as<int>(), d_hidx.as<int>(),
                             d_ldf.as<unsigned long long>(), d_hex.as<unsigned long long>(), d_na.as<int>());
@@ -223,6 +237,16 @@ int pt_env_tables_build(pt_scene* s) {
                 d_ldf.as<unsigned long long>(), d_hex.as<unsigned long long>(), n, 0, 0};
   k_env_alias<<<gb, TB>>>(in, d_na.as<int>(), s->d_env_prob.as<float>(), s->d_env_idx.as<int>());
   PT_CUDA(cudaGetLastError());
+  if (timing) {
+    cudaEventRecord(te[3]);
+    cudaEventSynchronize(te[3]);
+    float a = 0, b = 0, c = 0;
+    cudaEventElapsedTime(&a, te[0], te[1]);
+    cudaEventElapsedTime(&b, te[1], te[2]);
+    cudaEventElapsedTime(&c, te[2], te[3]);
+    fprintf(stderr, "[env tables] weights + pdf %.3f ms, scans %.3f ms, scatter + alias %.3f ms\n", a, b, c);
+    for (auto& e : te) cudaEventDestroy(e);
+  }
   PT_CUDA(cudaStreamSynchronize(0));  // the scratch buffers above are released when this function returns
   d.env_n = n;
   d.env_w = w;

@@ -30,10 +30,18 @@ PT_HD double env_texel_weight(const float* rgba, double row_sin) {
   return lum * row_sin;
 }
 
-// sum of one image row in index order (one thread per row; the order is part of the result)
-PT_HD double env_row_sum(const float* rgba_row, int w, double row_sin, double floor_w) {
+// Sum of one image row.  The order of the additions is part of the result (device and host mirror must agree bit
+// for bit), and it is chosen so that a warp can do it with coalesced loads: 32 partial sums, partial l over the
+// texels x = l, l + 32, l + 64, ... in increasing x, then the partials added in order 0..31.
+#define PT_ENV_LANES 32
+PT_HD double env_row_partial(const float* rgba_row, int w, int lane, double row_sin, double floor_w) {
   double s = 0.0;
-  for (int x = 0; x < w; x++) s += env_texel_weight(rgba_row + 4 * (size_t)x, row_sin) + floor_w * row_sin;
+  for (int x = lane; x < w; x += PT_ENV_LANES) s += env_texel_weight(rgba_row + 4 * (size_t)x, row_sin) + floor_w * row_sin;
+  return s;
+}
+PT_HD double env_row_sum(const float* rgba_row, int w, double row_sin, double floor_w) {  // serial form (host mirror)
+  double s = 0.0;
+  for (int l = 0; l < PT_ENV_LANES; l++) s += env_row_partial(rgba_row, w, l, row_sin, floor_w);
   return s;
 }
 
