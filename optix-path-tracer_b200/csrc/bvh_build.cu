@@ -71,15 +71,182 @@ __global__ void k_pad_bounds(int n, float4* plo, float4* phi, const float* scene
   phi[i] = make_float4(hi.x, hi.y, hi.z, 0.f);
 }
 
-__global__ void k_morton(int n, const float4* plo, const float4* phi, const float* sb, uint64_t* keys,
-                         uint32_t* vals) {
+// ---- top-down binned-SAH partition of the upper levels (bodies and rationale: bvh_core.h 2b) -------------
+__global__ void k_td_root(TdNode* nodes, const float* sb, int* node_id, uint32_t* code, int* clen, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) {
+    TdNode r;
+    for (int a = 0; a < 3; a++) {
+      r.cmin[a] = sb[a];
+      r.cmax[a] = sb[3 + a];
+    }
+    r.axis = -1;
+    r.bin = 0;
+    r.child = -1;
+    r.pad = 0;
+    nodes[0] = r;
+  }
+  if (i < n) {
+    node_id[i] = 0;
+    code[i] = 0u;
+    clen[i] = 0;
+  }
+}
+__global__ void k_td_clear(TdBin* bins, const int* n_nodes) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= *n_nodes * 3 * PT_TD_BINS) return;
+  TdBin b;
+  b.count = 0;
+  for (int a = 0; a < 3; a++) {
+    b.lo[a] = FLT_MAX;
+    b.hi[a] = -FLT_MAX;
+  }
+  bins[i] = b;
+}
+// order-preserving float <-> uint mapping (warp reductions work on integers)
+__device__ __forceinline__ uint32_t f2ord(float f) {
+  const uint32_t b = __float_as_uint(f);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(uint32_t u) { return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u); }
+__device__ __forceinline__ void td_bin_merge(TdBin* b, int count, float3 lo, float3 hi) {
+  atomicAdd(&b->count, count);
+  atomic_min_f(&b->lo[0], lo.x);
+  atomic_min_f(&b->lo[1], lo.y);
+  atomic_min_f(&b->lo[2], lo.z);
+  atomic_max_f(&b->hi[0], hi.x);
+  atomic_max_f(&b->hi[1], hi.y);
+  atomic_max_f(&b->hi[2], hi.z);
+}
+// Binning.  Every primitive adds its box to one bin per axis of its node: 21 atomics per primitive and level if done
+// naively, with a million primitives aiming at the 48 bins of the root.  Two remedies:
+//   SMEM   (level has <= PT_TD_SMEM_NODES nodes) bins are accumulated per block in shared memory and merged once;
+//   else   lanes of a warp that aim at the same bin (meshes arrive spatially ordered) are reduced with
+//          match.any + redux first, and one lane issues the atomics.
+#define PT_TD_SMEM_NODES 16
+template <bool SMEM>
+__global__ void __launch_bounds__(256) k_td_bin(int n, const float4* __restrict__ plo, const float4* __restrict__ phi,
+                                                const int* __restrict__ node_id, const TdNode* __restrict__ nodes,
+                                                const int* n_nodes, TdBin* bins) {
+  __shared__ TdBin sb[SMEM ? PT_TD_SMEM_NODES * 3 * PT_TD_BINS : 1];
+  const int nb = SMEM ? *n_nodes * 3 * PT_TD_BINS : 0;
+  if (SMEM) {
+    for (int k = threadIdx.x; k < nb; k += blockDim.x) {
+      sb[k].count = 0;
+      for (int a = 0; a < 3; a++) {
+        sb[k].lo[a] = FLT_MAX;
+        sb[k].hi[a] = -FLT_MAX;
+      }
+    }
+    __syncthreads();
+  }
+  const int lane = threadIdx.x & 31;
+  const int stride = gridDim.x * blockDim.x;
+  for (int base = blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < n; base += stride) {  // warp-uniform trip count
+    const int i = base + lane;
+    const int id = i < n ? node_id[i] : -1;
+    float3 lo = f3(0.f), hi = f3(0.f), c = f3(0.f);
+    TdNode nd;
+    if (id >= 0) {
+      nd = nodes[id];
+      lo = xyz(plo[i]);
+      hi = xyz(phi[i]);
+      c = (lo + hi) * 0.5f;
+    }
+    for (int a = 0; a < 3; a++) {
+      const int slot = id >= 0 ? (id * 3 + a) * PT_TD_BINS + td_bin_of(comp(c, a), nd.cmin[a], nd.cmax[a]) : -1;
+      if (SMEM) {
+        if (slot >= 0) td_bin_merge(sb + slot, 1, lo, hi);
+      } else {
+        const unsigned peers = __match_any_sync(0xffffffffu, slot);
+        if (slot >= 0) {
+          const int cnt = __popc(peers);
+          float3 l, h;
+          l.x = ord2f(__reduce_min_sync(peers, f2ord(lo.x)));
+          l.y = ord2f(__reduce_min_sync(peers, f2ord(lo.y)));
+          l.z = ord2f(__reduce_min_sync(peers, f2ord(lo.z)));
+          h.x = ord2f(__reduce_max_sync(peers, f2ord(hi.x)));
+          h.y = ord2f(__reduce_max_sync(peers, f2ord(hi.y)));
+          h.z = ord2f(__reduce_max_sync(peers, f2ord(hi.z)));
+          if (lane == __ffs(peers) - 1) td_bin_merge(bins + slot, cnt, l, h);
+        }
+      }
+    }
+  }
+  if (SMEM) {
+    __syncthreads();
+    for (int k = threadIdx.x; k < nb; k += blockDim.x)
+      if (sb[k].count) td_bin_merge(bins + k, sb[k].count, f3(sb[k].lo[0], sb[k].lo[1], sb[k].lo[2]), f3(sb[k].hi[0], sb[k].hi[1], sb[k].hi[2]));
+  }
+}
+__global__ void k_td_split(TdNode* nodes, const int* n_nodes, const TdBin* bins, int leaf_size, int depth, TdNode* next,
+                           int* n_next) {
+  const int id = blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= *n_nodes) return;
+  TdNode nd = nodes[id];
+  td_choose(bins + (size_t)id * 3 * PT_TD_BINS, nd, leaf_size, depth);
+  if (nd.axis >= 0) {
+    nd.child = atomicAdd(n_next, 2);
+    TdNode ch;
+    for (int a = 0; a < 3; a++) {
+      ch.cmin[a] = FLT_MAX;
+      ch.cmax[a] = -FLT_MAX;
+    }
+    ch.axis = -1;
+    ch.bin = 0;
+    ch.child = -1;
+    ch.pad = 0;
+    next[nd.child] = ch;
+    next[nd.child + 1] = ch;
+  }
+  nodes[id] = nd;
+}
+__global__ void __launch_bounds__(256) k_td_assign(int n, const float4* __restrict__ plo, const float4* __restrict__ phi, int* node_id,
+                                                   uint32_t* code, int* clen, const TdNode* __restrict__ nodes, TdNode* next) {
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // the grid covers n rounded up to whole warps
+  int ch = -1;
+  float3 c = f3(0.f);
+  const int id = i < n ? node_id[i] : -1;
+  if (id >= 0) {
+    const TdNode nd = nodes[id];
+    if (nd.axis < 0) {  // finished group: the path code stays as it is
+      node_id[i] = -1;
+    } else {
+      c = (xyz(plo[i]) + xyz(phi[i])) * 0.5f;
+      const int side = td_bin_of(comp(c, nd.axis), nd.cmin[nd.axis], nd.cmax[nd.axis]) <= nd.bin ? 0 : 1;
+      ch = nd.child + side;
+      node_id[i] = ch;
+      code[i] = (code[i] << 1) | (uint32_t)side;
+      clen[i] += 1;
+    }
+  }
+  // centroid bounds of the children: lanes with the same child reduce first, one lane issues the six atomics
+  const unsigned peers = __match_any_sync(0xffffffffu, ch);
+  if (ch >= 0) {
+    const float lx = ord2f(__reduce_min_sync(peers, f2ord(c.x))), ly = ord2f(__reduce_min_sync(peers, f2ord(c.y)));
+    const float lz = ord2f(__reduce_min_sync(peers, f2ord(c.z))), hx = ord2f(__reduce_max_sync(peers, f2ord(c.x)));
+    const float hy = ord2f(__reduce_max_sync(peers, f2ord(c.y))), hz = ord2f(__reduce_max_sync(peers, f2ord(c.z)));
+    if (lane == __ffs(peers) - 1) {
+      atomic_min_f(&next[ch].cmin[0], lx);
+      atomic_min_f(&next[ch].cmin[1], ly);
+      atomic_min_f(&next[ch].cmin[2], lz);
+      atomic_max_f(&next[ch].cmax[0], hx);
+      atomic_max_f(&next[ch].cmax[1], hy);
+      atomic_max_f(&next[ch].cmax[2], hz);
+    }
+  }
+}
+
+__global__ void k_morton(int n, const float4* plo, const float4* phi, const float* sb, const uint32_t* code, const int* clen,
+                         uint64_t* keys, uint32_t* vals) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float3 smin = f3(sb[0], sb[1], sb[2]);
   float3 ext = f3(sb[3], sb[4], sb[5]) - smin;
   float3 sinv = f3(ext.x > 0.f ? 1.f / ext.x : 0.f, ext.y > 0.f ? 1.f / ext.y : 0.f, ext.z > 0.f ? 1.f / ext.z : 0.f);
   float3 c = (xyz(plo[i]) + xyz(phi[i])) * 0.5f;
-  keys[i] = morton63(c, smin, sinv);
+  keys[i] = td_compose_key(morton63(c, smin, sinv), code ? code[i] : 0u, code ? clen[i] : 0);
   vals[i] = (uint32_t)i;
 }
 
@@ -240,7 +407,11 @@ int pt_bvh_build(pt_scene* s) {
   PT_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const uint64_t*)nullptr, (uint64_t*)nullptr,
                                           (const uint32_t*)nullptr, (uint32_t*)nullptr, n, 0, 63));
   const size_t n8 = (size_t)(n > 1 ? n : 2);
-  const size_t need = (size_t)n * (16 + 16 + 8 + 8 + 4 + 4 + 4 + 8 + 8) + (size_t)ni * (sizeof(Bvh2Node) + 4 + 4 + 4 + 4) +
+  // nodes alive on one level of the top-down partition: two children per node that still holds > leaf_size primitives
+  const int td_leaf = td_leaf_size(n);
+  const size_t td_cap = std::min<size_t>(PT_TD_MAXNODES, 2 * ((size_t)n / td_leaf) + 2) + 2;
+  const size_t td_bytes = (size_t)n * 12 + 2 * td_cap * sizeof(TdNode) + td_cap * 3 * PT_TD_BINS * sizeof(TdBin) + 4096;
+  const size_t need = td_bytes + (size_t)n * (16 + 16 + 8 + 8 + 4 + 4 + 4 + 8 + 8) + (size_t)ni * (sizeof(Bvh2Node) + 4 + 4 + 4 + 4) +
                       n8 * 80 + (size_t)n * sizeof(LeafRec) + cub_bytes + 64 * 256 + 4096;
   Arena& ar = g_arena[dev];
   if (ar.buf.bytes < need) PT_CUDA(ar.buf.alloc(need + need / 8));
@@ -261,15 +432,22 @@ int pt_bvh_build(pt_scene* s) {
   uint2* wa = (uint2*)ar.take((size_t)n * 8 + 64);
   uint2* wb = (uint2*)ar.take((size_t)n * 8 + 64);
   uint4* nodes8_tmp = (uint4*)ar.take(n8 * 80);
+  int* td_node_id = (int*)ar.take((size_t)n * 4);
+  uint32_t* td_code = (uint32_t*)ar.take((size_t)n * 4);
+  int* td_clen = (int*)ar.take((size_t)n * 4);
+  TdNode* td_nodes[2] = {(TdNode*)ar.take(td_cap * sizeof(TdNode)), (TdNode*)ar.take(td_cap * sizeof(TdNode))};
+  TdBin* td_bins = (TdBin*)ar.take(td_cap * 3 * PT_TD_BINS * sizeof(TdBin));
   LeafRec* leaves_tmp = (LeafRec*)ar.take((size_t)n * sizeof(LeafRec));
   // small device-resident state, zeroed once:
   //   [0..7] scene bounds (floats)   [16] BVH8 node counter   [17] leaf counter
   //   [32..32+MAXLEV] collapse work count per level   [200..200+MAXPASS) treelet root counts per (round, pass)
+  //   [300..300+PT_TD_MAXDEPTH] active nodes per level of the top-down partition
   //   doubles at byte 1024: SAH sums
   constexpr int MAXLEV = 160, MAXPASS = 48;
   int* st = (int*)ar.take(2048);
   float* sbounds = (float*)st;
   int* pass_roots = st + 200;
+  int* td_count = st + 300;
   int* d_cnt = st + 16;
   int* level_count = st + 32;
   double* cost = (double*)((char*)st + 1024);
@@ -280,6 +458,7 @@ int pt_bvh_build(pt_scene* s) {
     memcpy(init, fb, sizeof(fb));
     init[16] = 1;        // node 0 is the root
     init[32] = 1;        // level 0 holds one work item
+    init[300] = 1;       // the top-down partition starts with the root
     PT_CUDA(cudaMemcpyAsync(st, init, sizeof(init), cudaMemcpyHostToDevice, 0));
   }
 
@@ -288,7 +467,33 @@ int pt_bvh_build(pt_scene* s) {
   k_pad_bounds<<<nblk(n), TB>>>(n, plo, phi, sbounds);
   PT_CUDA(cudaGetLastError());
   tm.mark("bounds");
-  k_morton<<<nblk(n), TB>>>(n, plo, phi, sbounds, keys, vals);
+  // top-down binned-SAH partition of the upper levels: path bits per primitive (bvh_core.h 2b)
+  static const int td_on = getenv("PTB200_NO_TOPDOWN") ? 0 : 1;
+  static const int td_leaf_env = getenv("PTB200_TD_LEAF") ? atoi(getenv("PTB200_TD_LEAF")) : 0;  // dev
+  const int leaf_size = std::max(td_leaf, td_leaf_env);
+  const bool topdown = td_on && n > leaf_size;
+  if (topdown) {
+    k_td_root<<<nblk(n), TB>>>(td_nodes[0], sbounds, td_node_id, td_code, td_clen, n);
+    PT_CUDA(cudaGetLastError());
+    for (int level = 0; level < PT_TD_MAXDEPTH; level++) {
+      TdNode* cur = td_nodes[level & 1];
+      TdNode* nxt = td_nodes[(level + 1) & 1];
+      const long long bound = std::min<long long>((long long)td_cap - 2, level < 30 ? (1ll << level) : (long long)td_cap);
+      k_td_clear<<<nblk(bound * 3 * PT_TD_BINS), TB>>>(td_bins, td_count + level);
+      if (bound <= PT_TD_SMEM_NODES) k_td_bin<true><<<std::min(nblk(n), 148 * 4), TB>>>(n, plo, phi, td_node_id, cur, td_count + level, td_bins);
+      else k_td_bin<false><<<std::min(nblk(n), 148 * 16), TB>>>(n, plo, phi, td_node_id, cur, td_count + level, td_bins);
+      k_td_split<<<nblk(bound, 64), 64>>>(cur, td_count + level, td_bins, leaf_size, level, nxt, td_count + level + 1);
+      k_td_assign<<<nblk(n), TB>>>(n, plo, phi, td_node_id, td_code, td_clen, cur, nxt);
+      PT_CUDA(cudaGetLastError());
+      if ((level & 3) == 3) {  // a look at the counters every four levels: stop when no node is left to split
+        int alive = 0;
+        PT_CUDA(cudaMemcpy(&alive, td_count + level + 1, 4, cudaMemcpyDeviceToHost));
+        if (alive == 0) break;
+      }
+    }
+    tm.mark("top-down sah");
+  }
+  k_morton<<<nblk(n), TB>>>(n, plo, phi, sbounds, topdown ? td_code : nullptr, td_clen, keys, vals);
   PT_CUDA(cudaGetLastError());
   PT_CUDA(cub::DeviceRadixSort::SortPairs(cubtmp, cub_bytes, keys, keys2, vals, vals2, n, 0, 63));
   tm.mark("morton+sort");

@@ -24,11 +24,12 @@
 #endif
 // Rounds of the hierarchical treelet refinement, each with its own treelet size (<= PT_TREELET).  One round fixes
 // the grouping of leaves into treelets by the tree it starts from; a further round with another size regroups
-// across the previous round's treelet boundaries.  1 M-triangle mesh, SAH cost: LBVH 54.5 -> {64} 45.8 ->
-// {64, 32, 48} 40.2 (a full top-down binned-SAH build reaches 35.3); BVH8 nodes per camera ray 10.9 -> 10.4
-// (full SAH 9.5).  Each extra round costs ~2 ms of build per million triangles.
+// across the previous round's treelet boundaries.  On a plain LBVH that pays (1 M-triangle mesh, SAH cost: LBVH
+// 54.5 -> {64} 45.8 -> {64, 32, 48} 40.2); on top of the top-down partition of the upper levels (2b), which fixes
+// the grouping itself, further rounds change nothing (SAH 35.6 with {64}, 35.7 with {64, 32, 48}; nodes per ray
+// equal) and cost ~5 ms of build per million triangles each: one round.
 #ifndef PT_TREELET_ROUNDS
-#define PT_TREELET_ROUNDS {64, 32, 48}
+#define PT_TREELET_ROUNDS {64}
 #endif
 
 struct BuildIn {  // device copies of the flat scene arrays
@@ -162,6 +163,100 @@ PT_HD uint64_t morton63(float3 c, float3 smin, float3 sinv) {
   return (expand_bits21((uint64_t)x) << 2) | (expand_bits21((uint64_t)y) << 1) | expand_bits21((uint64_t)z);
 }
 
+PT_HD float box_half_area(float3 lo, float3 hi) {
+  float3 e = hi - lo;
+  return e.x * e.y + e.y * e.z + e.z * e.x;
+}
+
+// ---- 2b: top-down binned-SAH partition of the upper levels -----------------------------------------
+// LBVH groups primitives by Morton cells, and the treelet refinement (5) can only re-arrange what those groups
+// contain: on the 1 M-triangle mesh it stops at a SAH cost of 40.2 where a full top-down binned-SAH build reaches
+// 35.3 (9 % fewer node visits per ray).  This pass decides the UPPER levels top-down instead: level by level every
+// active node bins its primitives (16 bins per axis, counts and boxes by atomics), takes the cheapest split and
+// hands each primitive one more PATH BIT (0 = left, 1 = right), until a node holds <= leaf_size primitives.  The
+// path bits are then put IN FRONT of the Morton bits of the sort key, so the radix tree the Karras step builds over
+// the sorted keys reproduces the top-down tree above the groups and is plain LBVH inside them - where the first
+// treelet pass (<= 64 leaves) rebuilds everything anyway.  Nothing downstream changes.
+// Measured in the host simulation (1 M triangles): SAH 40.2 -> 35.6 (a full top-down binned-SAH build: 35.3), BVH8
+// nodes per camera / bounce ray 10.38 / 9.34 -> 9.67 / 8.66 (full build: 9.46 / 8.61).  On the B200: C4 +5.7 %,
+// incoherent rays +6.1 %, C2 +3.5 %; the pass itself takes 2.3 ms per million triangles.
+#ifndef PT_TD_BINS
+#define PT_TD_BINS 16
+#endif
+#define PT_TD_MAXDEPTH 20
+#ifndef PT_TD_LEAF
+#define PT_TD_LEAF 64
+#endif
+#ifndef PT_TD_MAXNODES
+#define PT_TD_MAXNODES 65536  // active nodes per level (leaf_size grows with the scene so that this holds)
+#endif
+
+struct TdBin {
+  int count;
+  float lo[3], hi[3];
+};
+struct TdNode {
+  float cmin[3], cmax[3];  // centroid bounds of the node's primitives
+  int axis, bin;           // chosen split: centroid bin <= bin goes left; axis < 0: the node is a finished group
+  int child;               // index of the left child among the next level's nodes (right = child + 1)
+  int pad;
+};
+PT_HD int td_leaf_size(int n) { return n / (PT_TD_MAXNODES / 2) > PT_TD_LEAF ? n / (PT_TD_MAXNODES / 2) : PT_TD_LEAF; }
+PT_HD int td_bin_of(float c, float cmin, float cmax) {
+  if (!(cmax > cmin)) return 0;
+  const float scale = (float)PT_TD_BINS / (cmax - cmin);
+  const int b = (int)((c - cmin) * scale);
+  return b < 0 ? 0 : (b > PT_TD_BINS - 1 ? PT_TD_BINS - 1 : b);
+}
+// bins: [3][PT_TD_BINS] of one node, complete.  Chooses the split (or declares the node a finished group).
+PT_HD void td_choose(const TdBin* bins, TdNode& nd, int leaf_size, int depth) {
+  nd.axis = -1;
+  nd.bin = 0;
+  nd.child = -1;
+  int total = 0;
+  for (int b = 0; b < PT_TD_BINS; b++) total += bins[b].count;
+  if (total <= leaf_size || depth >= PT_TD_MAXDEPTH) return;
+  float best = INFINITY;
+  for (int ax = 0; ax < 3; ax++) {
+    if (!(nd.cmax[ax] > nd.cmin[ax])) continue;
+    const TdBin* B = bins + ax * PT_TD_BINS;
+    float rarea[PT_TD_BINS];
+    int rcnt[PT_TD_BINS];
+    float3 alo = f3(INFINITY), ahi = f3(-INFINITY);
+    int c = 0;
+    for (int b = PT_TD_BINS - 1; b > 0; b--) {
+      if (B[b].count) {
+        alo = fmin3(alo, f3(B[b].lo[0], B[b].lo[1], B[b].lo[2]));
+        ahi = fmax3(ahi, f3(B[b].hi[0], B[b].hi[1], B[b].hi[2]));
+      }
+      c += B[b].count;
+      rarea[b] = c ? box_half_area(alo, ahi) : 0.f;
+      rcnt[b] = c;
+    }
+    alo = f3(INFINITY);
+    ahi = f3(-INFINITY);
+    c = 0;
+    for (int b = 0; b < PT_TD_BINS - 1; b++) {
+      if (B[b].count) {
+        alo = fmin3(alo, f3(B[b].lo[0], B[b].lo[1], B[b].lo[2]));
+        ahi = fmax3(ahi, f3(B[b].hi[0], B[b].hi[1], B[b].hi[2]));
+      }
+      c += B[b].count;
+      if (!c || !rcnt[b + 1]) continue;
+      const float cost = box_half_area(alo, ahi) * (float)c + rarea[b + 1] * (float)rcnt[b + 1];
+      if (cost < best) {
+        best = cost;
+        nd.axis = ax;
+        nd.bin = b;
+      }
+    }
+  }
+}
+// sort key: `len` path bits in front of the Morton bits
+PT_HD uint64_t td_compose_key(uint64_t morton, uint32_t code, int len) {
+  return len ? (((uint64_t)code << (63 - len)) | (morton >> len)) : morton;
+}
+
 // ---- 3: Karras LBVH hierarchy --------------------------------------------------------
 PT_HD int lbvh_delta(const uint64_t* keys, int n, int i, int j) {
   if (j < 0 || j >= n) return -1;
@@ -215,10 +310,6 @@ PT_HD void bvh2_child_box(const Bvh2& t, int ref, float3& lo, float3& hi, int& c
 PT_HD void bvh2_set_box(Bvh2Node& nd, float3 lo, float3 hi) {
   nd.lo[0] = lo.x; nd.lo[1] = lo.y; nd.lo[2] = lo.z;
   nd.hi[0] = hi.x; nd.hi[1] = hi.y; nd.hi[2] = hi.z;
-}
-PT_HD float box_half_area(float3 lo, float3 hi) {
-  float3 e = hi - lo;
-  return e.x * e.y + e.y * e.z + e.z * e.x;
 }
 
 // ---- 5: hierarchical binned-SAH treelet rebuild ------------------------------------------

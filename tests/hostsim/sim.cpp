@@ -7,6 +7,7 @@
 // a machine without a GPU.  This is not a product path: nothing in the package
 // loads it, and the shipped library has no CPU execution mode.
 #include <algorithm>
+#include <cfloat>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -159,6 +160,84 @@ Sim* sim_create(const pt_scene_desc* desc, int refine) {
   std::vector<uint64_t> keys(n);
   std::vector<uint32_t> order(n);
   for (int i = 0; i < n; i++) keys[i] = morton63((xyz(plo[i]) + xyz(phi[i])) * 0.5f, cmin, sinv);
+  // top-down binned-SAH partition of the upper levels (mirrors bvh_build.cu: same bodies, serial loops)
+  {
+    const int leaf_size = td_leaf_size(n);
+    std::vector<uint32_t> code(n, 0u);
+    std::vector<int> clen(n, 0), node_id(n, 0);
+    if (n > leaf_size && refine && !getenv("PTSIM_NO_TOPDOWN")) {
+      std::vector<TdNode> cur(1), nxt;
+      for (int a = 0; a < 3; a++) {
+        cur[0].cmin[a] = comp(cmin, a);
+        cur[0].cmax[a] = comp(cmax, a);
+      }
+      cur[0].axis = -1;
+      cur[0].bin = 0;
+      cur[0].child = -1;
+      for (int level = 0; level < PT_TD_MAXDEPTH && !cur.empty(); level++) {
+        std::vector<TdBin> bins(cur.size() * 3 * PT_TD_BINS);
+        for (auto& bq : bins) {
+          bq.count = 0;
+          for (int a = 0; a < 3; a++) {
+            bq.lo[a] = FLT_MAX;
+            bq.hi[a] = -FLT_MAX;
+          }
+        }
+        for (int i = 0; i < n; i++) {
+          const int id = node_id[i];
+          if (id < 0) continue;
+          const float3 lo = xyz(plo[i]), hi = xyz(phi[i]);
+          const float3 c = (lo + hi) * 0.5f;
+          for (int a = 0; a < 3; a++) {
+            TdBin& bq = bins[(size_t)(id * 3 + a) * PT_TD_BINS + td_bin_of(comp(c, a), cur[id].cmin[a], cur[id].cmax[a])];
+            bq.count++;
+            for (int k = 0; k < 3; k++) {
+              bq.lo[k] = fminf(bq.lo[k], comp(lo, k));
+              bq.hi[k] = fmaxf(bq.hi[k], comp(hi, k));
+            }
+          }
+        }
+        nxt.clear();
+        for (size_t id = 0; id < cur.size(); id++) {
+          td_choose(bins.data() + id * 3 * PT_TD_BINS, cur[id], leaf_size, level);
+          if (cur[id].axis >= 0) {
+            cur[id].child = (int)nxt.size();
+            TdNode ch;
+            for (int a = 0; a < 3; a++) {
+              ch.cmin[a] = FLT_MAX;
+              ch.cmax[a] = -FLT_MAX;
+            }
+            ch.axis = -1;
+            ch.bin = 0;
+            ch.child = -1;
+            nxt.push_back(ch);
+            nxt.push_back(ch);
+          }
+        }
+        for (int i = 0; i < n; i++) {
+          const int id = node_id[i];
+          if (id < 0) continue;
+          const TdNode& nd = cur[id];
+          if (nd.axis < 0) {
+            node_id[i] = -1;
+            continue;
+          }
+          const float3 c = (xyz(plo[i]) + xyz(phi[i])) * 0.5f;
+          const int side = td_bin_of(comp(c, nd.axis), nd.cmin[nd.axis], nd.cmax[nd.axis]) <= nd.bin ? 0 : 1;
+          const int ch = nd.child + side;
+          node_id[i] = ch;
+          code[i] = (code[i] << 1) | (uint32_t)side;
+          clen[i]++;
+          for (int a = 0; a < 3; a++) {
+            nxt[ch].cmin[a] = fminf(nxt[ch].cmin[a], comp(c, a));
+            nxt[ch].cmax[a] = fmaxf(nxt[ch].cmax[a], comp(c, a));
+          }
+        }
+        cur.swap(nxt);
+      }
+    }
+    for (int i = 0; i < n; i++) keys[i] = td_compose_key(keys[i], code[i], clen[i]);
+  }
   std::iota(order.begin(), order.end(), 0u);
   std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return keys[a] < keys[b]; });
   std::vector<uint64_t> skeys(n);
