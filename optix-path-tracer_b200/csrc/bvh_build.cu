@@ -313,6 +313,44 @@ __global__ void k_sah_cost(Bvh2 t, double* out) {
   if ((threadIdx.x & 31) == 0 && a != 0.0) atomicAdd(out, a);
 }
 
+// SAH-optimal collapse decisions (bvh_core.h 6a), bottom-up like the refit: the second thread to arrive at a node
+// finds both children's cost tables complete
+__global__ void k_collapse_dp(Bvh2 t, float* cost, unsigned char* dec) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= t.n) return;
+  int cur = t.leaf_parent[j];
+  while (cur >= 0) {
+    __threadfence();
+    int old = atomicAdd(t.flag + cur, 1);
+    if (old == 0) return;
+    const Bvh2Node nd = t.nodes[cur];
+    float cl[7], cr[7];
+    for (int side = 0; side < 2; side++) {
+      const int rf = side ? nd.right : nd.left;
+      float* dst = side ? cr : cl;
+      if (rf >= 0) {
+        const float4* p = (const float4*)(cost + (size_t)rf * 8);
+        const float4 a = __ldcg(p), b = __ldcg(p + 1);
+        dst[0] = a.x; dst[1] = a.y; dst[2] = a.z; dst[3] = a.w;
+        dst[4] = b.x; dst[5] = b.y; dst[6] = b.z;
+      } else {
+        const uint32_t id = t.sorted[~rf];
+        const float a = box_half_area(xyz(t.plo[id]), xyz(t.phi[id])) * PT_DP_CPRIM;
+        for (int i = 0; i < 7; i++) dst[i] = a;
+      }
+    }
+    float c8[8];
+    unsigned char d9[9];
+    collapse_dp_node(box_half_area(f3(nd.lo[0], nd.lo[1], nd.lo[2]), f3(nd.hi[0], nd.hi[1], nd.hi[2])), t.count[cur], cl, cr, c8, d9);
+    c8[7] = 0.f;
+    float4* q = (float4*)(cost + (size_t)cur * 8);
+    q[0] = make_float4(c8[0], c8[1], c8[2], c8[3]);
+    q[1] = make_float4(c8[4], c8[5], c8[6], c8[7]);
+    for (int i = 0; i < 9; i++) dec[(size_t)cur * 9 + i] = d9[i];
+    cur = t.parent[cur];
+  }
+}
+
 // one level of the collapse; level counts live on the device (level_count[l] = work items of level l)
 __global__ void k_collapse(Collapse c, const uint2* work, const int* n_work, uint2* out_work, int* out_count) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -411,7 +449,8 @@ int pt_bvh_build(pt_scene* s) {
   const int td_leaf = td_leaf_size(n);
   const size_t td_cap = std::min<size_t>(PT_TD_MAXNODES, 2 * ((size_t)n / td_leaf) + 2) + 2;
   const size_t td_bytes = (size_t)n * 12 + 2 * td_cap * sizeof(TdNode) + td_cap * 3 * PT_TD_BINS * sizeof(TdBin) + 4096;
-  const size_t need = td_bytes + (size_t)n * (16 + 16 + 8 + 8 + 4 + 4 + 4 + 8 + 8) + (size_t)ni * (sizeof(Bvh2Node) + 4 + 4 + 4 + 4) +
+  const size_t dp_bytes = (size_t)ni * (32 + 9) + 512;
+  const size_t need = td_bytes + dp_bytes + (size_t)n * (16 + 16 + 8 + 8 + 4 + 4 + 4 + 8 + 8) + (size_t)ni * (sizeof(Bvh2Node) + 4 + 4 + 4 + 4) +
                       n8 * 80 + (size_t)n * sizeof(LeafRec) + cub_bytes + 64 * 256 + 4096;
   Arena& ar = g_arena[dev];
   if (ar.buf.bytes < need) PT_CUDA(ar.buf.alloc(need + need / 8));
@@ -432,6 +471,8 @@ int pt_bvh_build(pt_scene* s) {
   uint2* wa = (uint2*)ar.take((size_t)n * 8 + 64);
   uint2* wb = (uint2*)ar.take((size_t)n * 8 + 64);
   uint4* nodes8_tmp = (uint4*)ar.take(n8 * 80);
+  float* dp_cost = (float*)ar.take((size_t)ni * 32);
+  unsigned char* dp_dec = (unsigned char*)ar.take((size_t)ni * 9);
   int* td_node_id = (int*)ar.take((size_t)n * 4);
   uint32_t* td_code = (uint32_t*)ar.take((size_t)n * 4);
   int* td_clen = (int*)ar.take((size_t)n * 4);
@@ -555,6 +596,16 @@ int pt_bvh_build(pt_scene* s) {
   c.nodes8 = nodes8_tmp;
   c.leaves = leaves_tmp;
   c.prim_leaf = s->d_prim_leaf.as<int>();
+  // SAH-optimal choice of every wide node's children instead of the greedy expansion (PTB200_NO_DP=1: greedy, dev)
+  static const int dp_on = getenv("PTB200_NO_DP") ? 0 : 1;
+  c.dp = nullptr;
+  if (dp_on && n > 1) {
+    PT_CUDA(cudaMemsetAsync(flag, 0, (size_t)ni * 4, 0));
+    k_collapse_dp<<<nblk(n), TB>>>(t, dp_cost, dp_dec);
+    PT_CUDA(cudaGetLastError());
+    c.dp = dp_dec;
+    tm.mark("collapse dp");
+  }
   c.node_counter = d_cnt;
   c.leaf_counter = d_cnt + 1;
   const uint2 first = make_uint2(n > 1 ? 0u : (uint32_t)~0, 0u);  // n == 1: leaf ref ~0

@@ -491,7 +491,55 @@ struct Collapse {
   int* prim_leaf;
   int* node_counter;   // next free BVH8 node
   int* leaf_counter;   // next free leaf record
+  const unsigned char* dp;  // optional: per BVH2 inner node 9 decision bytes of the SAH-optimal collapse (collapse_dp)
 };
+
+// ---- 6a: SAH-optimal choice of the BVH8 children (dynamic programme of Ylitie, Karras, Laine 2017, section 3) ----
+// C(n, i) = cheapest way to represent the subtree of BVH2 node n with at most i child slots of a wide node:
+//   C(n, 1) = min( leaf: A(n) * P(n) * c_prim  if P(n) <= 3,   own wide node: D(n, 8) + A(n) * c_node )
+//   C(n, i) = min( D(n, i), C(n, i - 1) ),   D(n, j) = min over 0 < k < j of C(left, k) + C(right, j - k)
+// dec[1] = 1 when n becomes a wide node of its own (0: leaf child); dec[j], j = 2..8: the k of D(n, j), or 0 when
+// fewer slots are as good (C(n, j) = C(n, j - 1)).  cost[0..7] = C(n, 1..7) + D(n, 8) in cost[7].
+#ifndef PT_DP_CNODE
+#define PT_DP_CNODE 1.0f
+#endif
+#ifndef PT_DP_CPRIM
+#define PT_DP_CPRIM 0.6f
+#endif
+PT_HD void collapse_dp_node(float area, int count, const float* cl, const float* cr, float* cost, unsigned char* dec) {
+  // cl / cr: C(child, 1..7) of the two children (a primitive: its area * c_prim for every i)
+  float dist[9];
+  unsigned char dk[9];
+  for (int j = 2; j <= 8; j++) {
+    float best = INFINITY;
+    int bk = 1;
+    for (int k = 1; k < j; k++) {
+      if (k > 7 || j - k > 7) continue;
+      const float c = cl[k - 1] + cr[j - k - 1];
+      if (c < best) {
+        best = c;
+        bk = k;
+      }
+    }
+    dist[j] = best;
+    dk[j] = (unsigned char)bk;
+  }
+  const float c_leaf = count <= 3 ? area * (float)count * PT_DP_CPRIM : INFINITY;
+  const float c_int = dist[8] + area * PT_DP_CNODE;
+  cost[0] = c_leaf <= c_int ? c_leaf : c_int;
+  dec[0] = 0;
+  dec[1] = c_leaf <= c_int ? 0 : 1;
+  for (int i = 2; i <= 7; i++) {
+    if (dist[i] < cost[i - 2]) {
+      cost[i - 1] = dist[i];
+      dec[i] = dk[i];
+    } else {
+      cost[i - 1] = cost[i - 2];
+      dec[i] = 0;
+    }
+  }
+  dec[8] = dk[8];
+}
 
 PT_HD LeafRec make_leaf_rec(const BuildIn& in, int id) {
   const pt_prim_ref p = in.prim_ref[id];
@@ -592,6 +640,52 @@ PT_HD void collapse_node(const Collapse& c, int ref, int dst, uint2* out_work, i
     node_ext = fmaxf(fmaxf(uhi.x - ulo.x, uhi.y - ulo.y), uhi.z - ulo.z);
   }
   const float min_child_ext = node_ext * ((float)PT_QUANT_MIN_STEPS / 255.0f);
+  if (c.dp && ref >= 0) {
+    // children from the dynamic programme: distribute 8 slots over the subtree as recorded
+    int sref[16], sslots[16], sp2 = 0;
+    n = 0;
+    sref[0] = ref;
+    sslots[0] = 8;
+    sp2 = 1;
+    bool top = true;
+    while (sp2) {
+      --sp2;
+      const int rf = sref[sp2];
+      int sl = sslots[sp2];
+      bool open = false;
+      int k = 0;
+      if (rf >= 0) {
+        const unsigned char* d = c.dp + (size_t)rf * 9;
+        if (top) {
+          open = true;
+          k = d[8];
+        } else {
+          while (sl > 1 && d[sl] == 0) sl--;
+          if (sl > 1) {
+            open = true;
+            k = d[sl];
+            // quantisation guard (see above): a subtree spanning only a few steps of this node's grid stays one child
+            const Bvh2Node& sn = t.nodes[rf];
+            const float ext = fmaxf(fmaxf(sn.hi[0] - sn.lo[0], sn.hi[1] - sn.lo[1]), sn.hi[2] - sn.lo[2]);
+            if (ext < min_child_ext && t.count[rf] > 3) open = false;
+          }
+        }
+      }
+      top = false;
+      if (open) {
+        sref[sp2] = t.nodes[rf].right;
+        sslots[sp2] = sl - k;
+        sp2++;
+        sref[sp2] = t.nodes[rf].left;
+        sslots[sp2] = k;
+        sp2++;
+      } else {
+        cref[n] = rf;
+        bvh2_child_box(t, rf, clo[n], chi[n], ccnt[n]);
+        n++;
+      }
+    }
+  } else
   // greedy expansion by surface area: first only subtrees too big for a leaf
   // (> 3 primitives), then any inner node while slots remain
   for (int pass = 0; pass < 2; pass++) {

@@ -315,7 +315,42 @@ Sim* sim_create(const pt_scene_desc* desc, int refine) {
   s->leaves.resize(n);
   s->prim_leaf.assign(n, -1);
   int counters[2] = {1, 0};
+  // SAH-optimal collapse: decisions per BVH2 inner node, bottom-up
+  std::vector<unsigned char> dp;
+  if (n > 1 && refine && !getenv("PTSIM_NO_DP")) {  // mirrors k_collapse_dp
+    dp.assign((size_t)(n - 1) * 9, 0);
+    std::vector<float> cost((size_t)(n - 1) * 8, 0.f);
+    // post-order over inner nodes
+    std::vector<int> order2, stk = {0};
+    while (!stk.empty()) {
+      int v = stk.back();
+      stk.pop_back();
+      order2.push_back(v);
+      if (t.nodes[v].left >= 0) stk.push_back(t.nodes[v].left);
+      if (t.nodes[v].right >= 0) stk.push_back(t.nodes[v].right);
+    }
+    for (size_t q = order2.size(); q-- > 0;) {
+      const int v = order2[q];
+      float cl[7], cr[7];
+      for (int side = 0; side < 2; side++) {
+        const int rf = side ? t.nodes[v].right : t.nodes[v].left;
+        float* dst = side ? cr : cl;
+        if (rf >= 0) {
+          for (int i = 0; i < 7; i++) dst[i] = cost[(size_t)rf * 8 + i];
+        } else {
+          float3 a, b;
+          int cn;
+          bvh2_child_box(t, rf, a, b, cn);
+          for (int i = 0; i < 7; i++) dst[i] = box_half_area(a, b) * PT_DP_CPRIM;
+        }
+      }
+      const Bvh2Node& nd = t.nodes[v];
+      collapse_dp_node(box_half_area(f3(nd.lo[0], nd.lo[1], nd.lo[2]), f3(nd.hi[0], nd.hi[1], nd.hi[2])), t.count[v], cl, cr,
+                       &cost[(size_t)v * 8], &dp[(size_t)v * 9]);
+    }
+  }
   Collapse c;
+  c.dp = dp.empty() ? nullptr : dp.data();
   c.t = t;
   c.in = in;
   c.nodes8 = s->nodes8.data();
