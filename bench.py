@@ -12,7 +12,10 @@ programs/raygen.cu:150), scene + BVH replicated.  --workload c1|c2|c3|c4_10m|c5 
   value    whole-job Msamples/s, scene and BVH resident in HBM (device-timed)
   e2e      same metric through the C ABI from HOST buffers: scene upload (H2D), GPU BVH
            build, render, accumulation-buffer read-back (D2H) all inside the timed region
-  roofline k_trace (closest-hit traversal): algorithmic bytes / CUDA-event time vs measured HBM peak
+  roofline closest-hit traversal kernel on the TIMED configuration: algorithmic bytes / CUDA-event time vs measured
+           HBM peak, with what actually bounds the kernel (ncu counters of the current build, profiles/ncu_traffic.json)
+  incoherent_secondary  Mrays/s of closest-hit queries on uniform random secondary rays (triangle scenes)
+  other_configs  C1 / C2 / C3 device-timed at full size, C4 with HDRI importance sampling on (N = 1 only)
   cpu_baseline  the CPU oracle on the host cores, bounded sample of the same workload
 
 `--impl reference` times the reference's own programs on the host cores: compiled unmodified inside the
@@ -188,7 +191,7 @@ def run_reference(args, rank, world):
     sc = build_scene(h, args.workload, W, H)
     base = {
         "impl": "reference", "metric": "Msamples/s", "unit": "Msamples/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": desc, "width": W, "height": H, "spp": spp, "max_depth": 50, "russian": True},
     }
