@@ -842,10 +842,13 @@ static DevBuf g_slab_cache[PT_MAX_DEVICES];
 static std::mutex g_cache_mu;
 
 static int ensure_pool(pt_renderer* r, long long want) {
-  long long npix = (long long)r->W * r->H;
-  long long pool = r->pool_req > 0 ? r->pool_req : (1ll << 23);  // 8 Mi paths (3.5 GB of state): +5 % over 4 Mi on C1 / C3 / C4
+  // Paths in flight.  Longer launches amortise the tail of every persistent traversal launch (the last warps of a
+  // launch run alone) and the per-iteration kernel boundaries: 8 Mi -> 32 Mi paths is +5.3 % on C4, +5.2 % on C3,
+  // +7 % on 10 M triangles.  But once the samples run out the pool drains over some 15 ever emptier iterations, and
+  // that phase grows with the pool: C2 (245 M samples = 7.7 fills of 32 Mi) loses 3.7 % with it.  So: 1/32 of the
+  // job, between 8 Mi (3.5 GB of path state, shadow requests, hit records and bins) and 32 Mi (14 GB of the 180).
+  long long pool = r->pool_req > 0 ? r->pool_req : std::max<long long>(1ll << 23, std::min<long long>(1ll << 25, want / 32));
   pool = std::min<long long>(pool, std::max<long long>(want, 1024));
-  (void)npix;
   pool = std::min<long long>(pool, 1ll << 25);
   if (pool <= r->pool) return PT_OK;
   r->pool = (int)pool;
