@@ -11,8 +11,9 @@ python bench.py --workload c2 --no-other-configs > $O/${R}_bench_c2.json 2>/dev/
 for w in c1 c3; do python bench.py --workload $w --steps 3 --warmup 3 --no-other-configs > $O/${R}_bench_$w.json 2>/dev/null; done
 python bench.py --workload c4_10m --steps 2 --warmup 3 --no-cpu-baseline --no-other-configs > $O/${R}_bench_c4_10m.json 2>/dev/null
 python bench.py --env-nee --steps 3 --warmup 3 --no-cpu-baseline --no-other-configs > $O/${R}_bench_c4_env_nee.json 2>/dev/null
-# launch list of one timed step of the default command (C4 at 512 spp: ~1170 launches per step; three warm-up steps skipped)
-ncu --metrics gpu__time_duration.sum --clock-control none -s 3520 -c 1180 --csv --log-file $O/${R}_launches_c4.csv \
+# launch list of one timed step of the default command (C4 at 512 spp, 32 Mi-path pool: 58 iterations x 5 kernels + the
+# drain = ~295 launches per step; the scene commit and three warm-up steps are skipped)
+ncu --metrics gpu__time_duration.sum --clock-control none -s 940 -c 296 --csv --log-file $O/${R}_launches_c4.csv \
   python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-other-configs > /dev/null 2>&1
 python scripts/summarize_launches.py $O/${R}_launches_c4.csv > $O/${R}_launches_c4.md
 # full captures of the dominant kernel (pool-full launch) of the current build -> ncu_traffic.json
