@@ -290,22 +290,6 @@ Sim* sim_create(const pt_scene_desc* desc, int refine) {
         }
       }
     }
-    if (const char* e = getenv("PTSIM_ROUNDS")) {  // EXPERIMENT: further hierarchical rounds with other treelet sizes
-      std::vector<int> sizes;
-      for (const char* q = e; *q;) { sizes.push_back(atoi(q)); while (*q && *q != ',') q++; if (*q) q++; }
-      for (int T : sizes) {
-        long long lo = 1, hi = T;
-        for (int pass = 0; pass < 12 && lo < (long long)n; pass++) {
-          std::vector<int> roots;
-          for (int i = 0; i < n - 1; i++)
-            if (treelet_is_root(t, i, (int)lo, hi)) roots.push_back(i);
-          for (int r : roots) treelet_sah(t, r, (int)lo);
-          lo = hi;
-          hi *= T;
-        }
-        fprintf(stderr, "round T=%d: SAH %.2f\n", T, sah_sum(t));
-      }
-    }
     if (const char* e = getenv("PTSIM_BUILDER")) {
       if (!strcmp(e, "sah")) full_sah_build(t, getenv("PTSIM_BINS") ? atoi(getenv("PTSIM_BINS")) : 32);
     }
