@@ -843,11 +843,16 @@ static std::mutex g_cache_mu;
 
 static int ensure_pool(pt_renderer* r, long long want) {
   // Paths in flight.  Longer launches amortise the tail of every persistent traversal launch (the last warps of a
-  // launch run alone) and the per-iteration kernel boundaries: 8 Mi -> 32 Mi paths is +5.3 % on C4, +5.2 % on C3,
-  // +7 % on 10 M triangles.  But once the samples run out the pool drains over some 15 ever emptier iterations, and
-  // that phase grows with the pool: C2 (245 M samples = 7.7 fills of 32 Mi) loses 3.7 % with it.  So: 1/32 of the
-  // job, between 8 Mi (3.5 GB of path state, shadow requests, hit records and bins) and 32 Mi (14 GB of the 180).
-  long long pool = r->pool_req > 0 ? r->pool_req : std::max<long long>(1ll << 23, std::min<long long>(1ll << 25, want / 32));
+  // launch run alone) and the per-iteration kernel boundaries: 8 Mi -> 32 Mi paths is +5.3 % on C4 (+4.8 % even on a
+  // 64-spp share of it, i.e. four fills), +5.2 % on C3, +7 % on 10 M triangles.  The shading kernels pay for it: they
+  // gather path records by index over a buffer four times the size (C2, three material bins, shading 31 -> 34 % of the
+  // step while its traversal gets 2 % faster: -3 % in total).  So: traversal-dominated scenes (the deep ones, >= 64 Ki
+  // primitives) take 32 Mi paths (14 GB of path state, shadow requests, hit records and bins, of the 180), the others
+  // 1/32 of the job between 8 Mi (3.5 GB) and 32 Mi.
+  const bool deep_scene = deep_min_prims() > 0 && r->scene->dev.n_prims >= deep_min_prims();
+  long long pool = r->pool_req > 0 ? r->pool_req
+                   : deep_scene   ? (1ll << 25)
+                                  : std::max<long long>(1ll << 23, std::min<long long>(1ll << 25, want / 32));
   pool = std::min<long long>(pool, std::max<long long>(want, 1024));
   pool = std::min<long long>(pool, 1ll << 25);
   if (pool <= r->pool) return PT_OK;
