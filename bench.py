@@ -359,6 +359,8 @@ def main():
     ap.add_argument("--no-other-configs", action="store_true")
     ap.add_argument("--env-nee", action="store_true", help="C4/C5 with HDRI importance sampling switched on (not the reference estimator)")
     ap.add_argument("--pool", type=int, default=0, help="path-pool size (dev only; 0 = library default)")
+    ap.add_argument("--static-split", action="store_true",
+                    help="N > 1: keep the equal split of the frames (default: shares follow the ranks' warm-up rates)")
     args = ap.parse_args()
     # stdout carries exactly ONE line: the JSON.  Libraries write there on their own (NCCL prints its version
     # banner at communicator creation, the facade's scene functions printf progress like the reference), so
@@ -446,6 +448,22 @@ def main():
     for _ in range(warm):
         step()
         flush.zero_()
+    # GPUs of one box differ by 2-3 % in speed and a sample split ends when its slowest rank does: after the warm-up
+    # the shares follow the ranks' measured rates (pt_split_frames_weighted; same frames, same total, every frame
+    # rendered exactly once).  --static-split keeps the equal split.
+    shares = [spp] * world
+    if world > 1:
+        rate = torch.tensor([spp / max(r.stats().ms_total, 1e-6)], device="cuda", dtype=torch.float32)
+        rates = [torch.zeros_like(rate) for _ in range(world)]
+        dist.all_gather(rates, rate)
+        weights = [float(x) for x in rates]
+        if strong and not args.static_split:
+            first, spp = pt.split_frames_weighted(total_spp, rank, world, weights, lib=lib)
+            shares = [pt.split_frames_weighted(total_spp, k, world, weights, lib=lib)[1] for k in range(world)]
+            step()                      # one more warm-up step with the final shares
+            flush.zero_()
+        elif strong:
+            shares = [pt.split_frames(total_spp, k, world, lib=lib)[1] for k in range(world)]
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -613,7 +631,9 @@ def main():
             "warmup": warm, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
             "scaling": "strong" if strong else "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": desc, "width": W, "height": H, "spp": total_spp, "spp_per_rank": spp, "max_depth": 50,
+            "config": {"workload": desc, "width": W, "height": H, "spp": total_spp, "spp_per_rank": shares if world > 1 else spp,
+                       "split": ("rate-weighted after warm-up (pt_split_frames_weighted)" if world > 1 and strong and not args.static_split
+                                 else "equal (pt_split_frames)"), "max_depth": 50,
                        "russian": True, "env_nee": bool(args.env_nee),
                        "l2": "flushed between timed steps (256 MiB write); path pool >> L2",
                        "prims": info.n_prims, "bvh8_nodes": info.n_bvh8_nodes,

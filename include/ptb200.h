@@ -459,6 +459,12 @@ int pt_renderer_create_multi(pt_scene* scene, int32_t width, int32_t height, con
 int pt_split_frames(int32_t total_frames, int32_t rank, int32_t world, int32_t first_frame,
                     int32_t* out_first, int32_t* out_n);
 
+/* the same with shares proportional to `weights` (e.g. the ranks' measured rates: GPUs of one box differ by 2-3 %
+ * and a sample split ends when its slowest rank does); largest-remainder rounding, deterministic, every frame assigned
+ * exactly once; weights NULL or all equal = pt_split_frames */
+int pt_split_frames_weighted(int32_t total_frames, int32_t rank, int32_t world, const float* weights,
+                             int32_t first_frame, int32_t* out_first, int32_t* out_n);
+
 typedef struct pt_comm pt_comm;
 #define PT_COMM_ID_BYTES 128
 int pt_comm_unique_id(uint8_t id[PT_COMM_ID_BYTES]);

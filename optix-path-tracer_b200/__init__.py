@@ -166,7 +166,7 @@ ABI_SYMBOLS = [
     "pt_renderer_set_flags", "pt_renderer_set_pool", "pt_read_display", "pt_write_accum",
     # ABI 3
     "pt_release_caches", "pt_renderer_create_multi", "pt_split_frames", "pt_comm_unique_id", "pt_comm_create",
-    "pt_comm_destroy", "pt_comm_reduce",
+    "pt_comm_destroy", "pt_comm_reduce", "pt_split_frames_weighted",
 ]
 MAX_PIXELS, MAX_DEPTH, COMM_ID_BYTES = 1 << 23, 255, 128
 
@@ -228,6 +228,7 @@ def load(path: Optional[str] = None) -> C.CDLL:
         "pt_release_caches": [],
         "pt_renderer_create_multi": [vp, i32, i32, P(i32), i32, P(vp)],
         "pt_split_frames": [i32, i32, i32, i32, P(i32), P(i32)],
+        "pt_split_frames_weighted": [i32, i32, i32, vp, i32, P(i32), P(i32)],
         "pt_comm_unique_id": [vp],
         "pt_comm_create": [vp, i32, i32, P(vp)],
         "pt_comm_destroy": [vp],
@@ -457,6 +458,15 @@ def split_frames(total_frames: int, rank: int, world: int, first_frame: int = 0,
     lib = lib or load()
     a, b = C.c_int32(), C.c_int32()
     _check(lib, lib.pt_split_frames(total_frames, rank, world, first_frame, C.byref(a), C.byref(b)))
+    return a.value, b.value
+
+
+def split_frames_weighted(total_frames: int, rank: int, world: int, weights, first_frame: int = 0, lib=None):
+    """pt_split_frames_weighted: shares proportional to `weights` (measured rates of the ranks)."""
+    lib = lib or load()
+    w = np.ascontiguousarray(weights, dtype=np.float32)
+    a, b = C.c_int32(), C.c_int32()
+    _check(lib, lib.pt_split_frames_weighted(total_frames, rank, world, _ptr(w), first_frame, C.byref(a), C.byref(b)))
     return a.value, b.value
 
 

@@ -120,6 +120,7 @@ struct pt_multi {
   std::vector<ncclComm_t> comms;
   unsigned long long seen_commit_gen = 0;
   bool merged = true;  // the root buffer holds the sum, the others are zero
+  std::vector<float> rate;  // frames per ms of every device in the previous render (0 = unknown): the next split follows it
   float ms_reduce = 0.f;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;  // on the root device
 };
@@ -212,14 +213,24 @@ int pt_multi_render(pt_multi* m, int32_t first_frame, int32_t nframes, int32_t m
   int rc = refresh_replicas(m);
   if (rc) return rc;
   const int n = (int)m->devices.size();
+  // GPUs of one box differ by 2-3 % in speed and a split ends when its slowest device does: shares follow the rates
+  // measured in the previous render (equal shares the first time)
+  std::vector<int32_t> share_n((size_t)n, 0);
   rc = for_each_device(n, [&](int i) {
     int32_t f0 = 0, fn = 0;
-    pt_split_frames(nframes, i, n, first_frame, &f0, &fn);
+    pt_split_frames_weighted(nframes, i, n, m->rate.size() == (size_t)n ? m->rate.data() : nullptr, first_frame, &f0, &fn);
+    share_n[i] = fn;
     // every buffer starts from zero (creation, clear, or the zeroing that follows a merge); the reference's
     // "frame 0 clears" rule (raygen.cu:154) is applied by the renderer that owns frame 0
     return pt_render(m->subs[i], f0, fn, max_depth, russian, clear_accum);
   });
   if (rc) return rc;
+  m->rate.assign((size_t)n, 0.f);
+  for (int i = 0; i < n; i++) {
+    pt_stats st{};
+    pt_get_stats(m->subs[i], &st);
+    m->rate[i] = share_n[i] > 0 && st.ms_total > 0.f ? (float)share_n[i] / st.ms_total : 0.f;
+  }
   m->merged = false;
   return PT_OK;
 }
@@ -313,6 +324,44 @@ int pt_split_frames(int32_t total_frames, int32_t rank, int32_t world, int32_t f
   const int32_t base = total_frames / world, rem = total_frames % world;
   *out_n = base + (rank < rem ? 1 : 0);
   *out_first = first_frame + rank * base + (rank < rem ? rank : rem);
+  return PT_OK;
+}
+
+int pt_split_frames_weighted(int32_t total_frames, int32_t rank, int32_t world, const float* weights, int32_t first_frame,
+                             int32_t* out_first, int32_t* out_n) {
+  if (total_frames < 0 || world <= 0 || rank < 0 || rank >= world || !out_first || !out_n) {
+    pt_set_error("pt_split_frames_weighted: bad arguments");
+    return PT_ERR_INVALID;
+  }
+  double sum = 0.0;
+  bool usable = weights != nullptr;
+  for (int i = 0; usable && i < world; i++) {
+    if (!(weights[i] > 0.f) || !(weights[i] < 1e30f)) usable = false;
+    else sum += (double)weights[i];
+  }
+  if (!usable) return pt_split_frames(total_frames, rank, world, first_frame, out_first, out_n);
+  // largest-remainder apportionment: floor of the exact share, the leftover frames to the largest fractions
+  // (ties to the lower rank)
+  std::vector<int32_t> n((size_t)world);
+  std::vector<double> frac((size_t)world);
+  int32_t given = 0;
+  for (int i = 0; i < world; i++) {
+    const double share = (double)total_frames * (double)weights[i] / sum;
+    n[i] = (int32_t)share;
+    frac[i] = share - (double)n[i];
+    given += n[i];
+  }
+  for (int32_t left = total_frames - given; left > 0; left--) {
+    int best = 0;
+    for (int i = 1; i < world; i++)
+      if (frac[i] > frac[best]) best = i;
+    n[best]++;
+    frac[best] = -1.0;
+  }
+  int32_t start = first_frame;
+  for (int i = 0; i < rank; i++) start += n[i];
+  *out_first = start;
+  *out_n = n[rank];
   return PT_OK;
 }
 

@@ -98,3 +98,31 @@ def test_no_cpu_fallback(lib):
 def test_missing_library_is_loud(tmp_path):
     with pytest.raises(pt.PtError):
         pt.load(str(tmp_path / "nope.so"))
+
+
+def test_frame_splits(lib):
+    """pt_split_frames / pt_split_frames_weighted (host logic of the multi-GPU sample split): every frame is assigned
+    exactly once, shares are contiguous, equal shares differ by at most one, weighted shares follow the weights."""
+    for world in (1, 2, 3, 8):
+        for total in (0, 1, 7, 512, 4096 + 3):
+            got = [pt.split_frames(total, r, world, 10, lib) for r in range(world)]
+            frames = [f for a, n in got for f in range(a, a + n)]
+            assert frames == list(range(10, 10 + total))
+            ns = [n for _, n in got]
+            assert max(ns) - min(ns) <= 1
+    import importlib
+    mg = importlib.import_module("optix_path_tracer_b200.multigpu")
+    for world in (1, 2, 4, 8):
+        for r in range(world):
+            assert pt.split_frames(4099, r, world, 10, lib) == mg.split_frames(4099, r, world, 10)   # the Python twin
+    w = [1.0, 0.97, 1.02, 0.99, 1.0, 1.01, 0.98, 1.03]
+    got = [pt.split_frames_weighted(512, r, 8, w, 0, lib) for r in range(8)]
+    assert [f for a, n in got for f in range(a, a + n)] == list(range(512))
+    ns = [n for _, n in got]
+    assert ns[7] == max(ns) and ns[1] == min(ns)
+    assert all(abs(n - 512 * wi / sum(w)) < 1.0 for n, wi in zip(ns, w))
+    assert [pt.split_frames_weighted(512, r, 4, [1, 1, 1, 1], 0, lib) for r in range(4)] == \
+        [pt.split_frames(512, r, 4, 0, lib) for r in range(4)]
+    assert [pt.split_frames_weighted(5, r, 2, [0.0, 1.0], 0, lib) for r in range(2)] == [(0, 3), (3, 2)]   # unusable weights
+    with pytest.raises(pt.PtError):
+        pt.split_frames(8, 2, 2, 0, lib)
