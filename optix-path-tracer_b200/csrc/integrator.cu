@@ -1119,7 +1119,8 @@ int pt_render(pt_renderer* r, int32_t first_frame, int32_t nframes, int32_t max_
   const bool timing = (r->flags & 2) != 0;
   const int sms = sm_count();
   const bool special = sc.special_mask != 0;
-  const int g_trace = sms * trace_blocks_per_sm(special), g_shade = sms * PT_SHADE_MINBLOCKS, g_gen = sms * 4;
+  const int g_trace = sms * trace_blocks_per_sm(special), g_shade = sms * PT_SHADE_MINBLOCKS;
+  const int g_gen = sms * 8;  // 2048 threads per SM hide the 64-round dependency chain of tea<64> (4 -> 8 blocks: +0.3 %)
 #ifndef PT_MISS_BLOCKS
 #define PT_MISS_BLOCKS 8
 #endif
