@@ -237,6 +237,11 @@ int pt_multi_render(pt_multi* m, int32_t first_frame, int32_t nframes, int32_t m
 
 int pt_multi_merge(pt_multi* m) {
   if (m->merged) return PT_OK;
+  if (m->devices.size() == 1) {  // nothing to merge, and no NCCL needed
+    m->merged = true;
+    m->ms_reduce = 0.f;
+    return pt_multi_sync(m);
+  }
   const NcclApi* api = nccl();
   if (!api) return PT_ERR_STATE;
   const int n = (int)m->devices.size();

@@ -28,6 +28,27 @@ def n_devices():
 needs2 = pytest.mark.skipif(n_devices() < 2, reason="needs two CUDA devices")
 
 
+def test_multi_handle_over_one_device(lib):
+    """pt_renderer_create_multi with a single device: the same fan-out code path (handle -> sub-renderer, split, merge
+    state, statistics) without a second GPU and without NCCL; must equal the plain renderer bit for bit."""
+    W, H = 128, 96
+    sc = h.build_spheres(22, W=W, H=H, lib=lib)
+    sc.commit()
+    plain = pt.Renderer(sc, W, H)
+    multi = pt.Renderer(sc, W, H, devices=[0])
+    plain.render(2, 1)
+    multi.render(2, 1)
+    a, b = plain.read_accum(), multi.read_accum()
+    assert (b[..., 3] == 1).all() and np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    multi.render(3, 5)
+    plain.render(3, 5)
+    assert (multi.read_accum()[..., 3] == 6).all()
+    assert np.allclose(plain.read_accum(), multi.read_accum(), rtol=1e-5, atol=1e-5)
+    st = multi.stats()
+    assert st.samples == W * H * 5 and st.ms_reduce == 0 and st.closest_rays == plain.stats().closest_rays
+    assert np.array_equal(plain.read_display(), multi.read_display())
+
+
 @needs2
 def test_one_handle_two_devices_equals_one_device(lib):
     W, H = 160, 96
