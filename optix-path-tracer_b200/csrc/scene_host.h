@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <string>
 #include <vector>
 
@@ -45,9 +46,8 @@ struct DevBuf {  // owning device allocation; remembers the device it lives on
   // stream-ordered allocations from the device's default pool (kept warm: repeated scene
   // commits reuse memory instead of paying cudaMalloc/cudaFree every time)
   static void warm_pool(int dev) {
-    static unsigned long long done_mask = 0;  // bit per device ordinal (< 64)
-    if (dev < 0 || dev >= 64 || (done_mask >> dev) & 1ull) return;
-    done_mask |= 1ull << dev;
+    static std::atomic<unsigned long long> done_mask{0};  // bit per device ordinal (< 64); commits may run on several threads
+    if (dev < 0 || dev >= 64 || (done_mask.fetch_or(1ull << dev) >> dev) & 1ull) return;
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
       unsigned long long keep = ~0ull;
