@@ -100,7 +100,7 @@ class ClockSampler(threading.Thread):
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.stop_flag, self.sm, self.reasons, self.max_mhz = index, False, [], set(), None
+        self.index, self.stop_flag, self.sm, self.reasons, self.max_mhz, self.power = index, False, [], set(), None, []
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -120,6 +120,10 @@ class ClockSampler(threading.Thread):
             try:
                 self.sm.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
                 try:
+                    self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+                except Exception:
+                    pass
+                try:
                     r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
                 except Exception:
                     r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
@@ -128,11 +132,14 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(nm)
             except Exception:
                 pass
-            time.sleep(0.1)
+            time.sleep(float(os.environ.get("PTB200_CLOCK_PERIOD", "0.5")))
 
     def result(self):
         import statistics
         return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.max_mhz,
+                "sm_mhz_mean": statistics.fmean(self.sm) if self.sm else None, "sm_mhz_min": min(self.sm) if self.sm else None,
+                "power_w_mean": statistics.fmean(self.power) if self.power else None,
+                "power_w_max": max(self.power) if self.power else None,
                 "reasons": sorted(self.reasons), "samples": len(self.sm)}
 
 
@@ -510,30 +517,40 @@ def main():
     host_out = torch.empty((H, W, 4), dtype=torch.float32, pin_memory=True)
     h2d = 0
 
-    def e2e_step():
+    e2e_parts = {"commit_ms": 0.0, "create_ms": 0.0, "render_device_ms": 0.0, "reduce_and_readback_ms": 0.0}
+
+    def e2e_step(record=False):
         nonlocal h2d
         s2 = make_scene()                                   # host-side flat arrays (outside the timed region)
         t0 = time.perf_counter()
         s2.commit()                                         # H2D of the scene + GPU BVH build
+        t1 = time.perf_counter()
         r2 = pt.Renderer(s2, W, H)
+        t2 = time.perf_counter()
         r2.render(first, spp, clear=True)
+        t3 = time.perf_counter()
         if comm is not None:
             comm.reduce(r2, 0)
         if rank == 0:                                       # D2H of the float4 accumulation buffer
             _check_rc(lib, lib.pt_read_accum(r2.h, host_out.data_ptr()))
         torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
+        t4 = time.perf_counter()
+        if record:
+            e2e_parts["commit_ms"] += (t1 - t0) * 1e3
+            e2e_parts["create_ms"] += (t2 - t1) * 1e3
+            e2e_parts["render_device_ms"] += r2.stats().ms_total
+            e2e_parts["reduce_and_readback_ms"] += (t4 - t3) * 1e3
         h2d = scene_host_bytes(s2.desc())
         r2.close()
         s2.close()
-        return dt
+        return t4 - t0
 
     e2e_step()
     if world > 1:
         dist.barrier()
     t_e2e = 0.0
     for _ in range(e2e_steps):
-        t_e2e += e2e_step()
+        t_e2e += e2e_step(record=True)
     te = torch.tensor([t_e2e], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
@@ -647,6 +664,11 @@ def main():
             "clocks": sampler.result(),
             "e2e": {"value": e2e_val, "unit": "Msamples/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(W * H * 16), "steps": e2e_steps,
+                    "wall_ms_per_step": float(te[0]) / e2e_steps * 1e3,
+                    "rank0_breakdown_ms_per_step": {k: v / e2e_steps for k, v in e2e_parts.items()},
+                    "note": "wall clock around commit + renderer creation + render + reduce + read-back of a FRESH scene and "
+                            "renderer per step; the render inside it is a single render after ~1 s of host-side scene "
+                            "building, the device-timed `value` is the mean of back-to-back renders (sustained clocks)",
                     "includes": "scene upload (H2D), GPU alias-table + BVH build, render, NCCL reduce (N>1), accumulation "
                                 "read-back (D2H) through the C ABI",
                     "excludes": f"host-side scene construction (the facade's scene function: OBJ / HDR parse and flat arrays, "
