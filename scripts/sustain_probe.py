@@ -27,3 +27,14 @@ for k in range(4):
     run(1, "1 s pause each    ")
 sc.commit()
 run(4, "re-committed scene")
+# with an L2 flush (256 MiB write) between renders, like bench.py's timed loop
+import torch
+flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+t = []
+for _ in range(6):
+    flush.zero_()
+    torch.cuda.synchronize()
+    r.render(0, SPP, clear=True)
+    t.append(round(r.stats().ms_total, 1))
+print("flush before each ", t, flush=True)
+run(3, "no flush again    ")
