@@ -737,10 +737,11 @@ SchedParams sched_params(const SceneDev& sc) {
   return p;
 }
 // ray sets handed to pt_trace_rays are arbitrary (the benchmark's are incoherent secondary rays): their lanes
-// finish at very different times and the smaller retire batch wins (1.73 vs 1.62 Gray/s on 1 M triangles)
+// finish at very different times and the smaller retire batch wins (round 1: 12 instead of 20, 1.73 vs 1.62 Gray/s on
+// 1 M triangles; with the round-2 tree 8: 2.05 vs 2.00 Gray/s, 10 and 14 in between)
 SchedParams sched_params_rays(const SceneDev& sc) {
   SchedParams p = sched_params(sc);
-  if (!getenv("PTB200_REFILL_MIN")) p.refill_min = 12;
+  if (!getenv("PTB200_REFILL_MIN")) p.refill_min = 8;
   return p;
 }
 
