@@ -86,6 +86,7 @@ __device__ __forceinline__ void trace_persistent(const SceneDev& sc, int n, int*
     const bool can_recycle = fin != 0u || (!exhausted && idle != 0u);
     if (can_recycle && (__popc(fin | idle) >= sp_.refill_min || busy == 0u)) {
       if (finished) {
+        hit_resolve(hit);  // deferred divisions of a triangle hit: here the retiring lanes do them together
         pol.emit(ray, hit, fin);
         ray = -1;
       }
