@@ -32,10 +32,14 @@ extern "C" {
 
 #define PTB200_ABI_VERSION 3
 
-/* fixed limits of the renderer (the 64-byte path record packs pixel index | depth | specular flag into 32 bits):
- * larger images are rejected by pt_renderer_create, larger depths by pt_render (PT_ERR_INVALID).  3840x2160
- * is 8.3 M pixels; the reference's default maxDepth is 50 (host_includes/host_common.hpp:30). */
-#define PT_MAX_PIXELS (1 << 23)
+/* fixed limits of the renderer.  The 64-byte path record packs pixel index | depth | specular flag into 32 bits
+ * (23 + 8 + 1): larger depths are rejected by pt_render (PT_ERR_INVALID); the reference's default maxDepth is 50
+ * (host_includes/host_common.hpp:30).  An image of more than PT_BAND_PIXELS pixels (3840x2160 is 8.3 M, just below)
+ * is rendered as horizontal bands of at most that many pixels, one after the other inside pt_render, with the same
+ * per-pixel sample set (the seed is tea<64>(W*y + x, frame), raygen.cu:150): up to PT_MAX_PIXELS pixels per image,
+ * and at most PT_BAND_PIXELS per row; pt_renderer_create rejects anything larger. */
+#define PT_MAX_PIXELS (1 << 28)
+#define PT_BAND_PIXELS (1 << 23)
 #define PT_MAX_DEPTH 255
 
 typedef enum pt_status {

@@ -168,7 +168,7 @@ ABI_SYMBOLS = [
     "pt_release_caches", "pt_renderer_create_multi", "pt_split_frames", "pt_comm_unique_id", "pt_comm_create",
     "pt_comm_destroy", "pt_comm_reduce", "pt_split_frames_weighted",
 ]
-MAX_PIXELS, MAX_DEPTH, COMM_ID_BYTES = 1 << 23, 255, 128
+MAX_PIXELS, BAND_PIXELS, MAX_DEPTH, COMM_ID_BYTES = 1 << 28, 1 << 23, 255, 128
 
 
 class PtError(RuntimeError):

@@ -124,6 +124,10 @@ struct CtrlPoll {
 struct Params {
   int W, H, max_depth, russian, pool;  // (the first frame index lives in Ctrl so captured graphs stay valid)
   int tiled;                           // camera samples enumerated in 8x4 tiles (W % 8 == 0 && H % 4 == 0)
+  // An image of more than PT_BAND_PIXELS pixels is rendered as horizontal bands, one after the other: W x H are the
+  // rows [y0, y0 + H) of a W x Himg image, path records carry the pixel index WITHIN the band (23 bits), and the
+  // seed, the camera ray and the accumulation address use the image row y0 + y.  One band: y0 = 0, H = Himg.
+  int y0, Himg, ytop;  // ytop = Himg - 1 - y0: the accumulation buffer's row of the band's first image row
   float4* accum;
   uint32_t c16, c1;  // the constants 16 and 1 as run-time values, see pt_tea64_balanced
 };
@@ -152,7 +156,7 @@ __device__ __forceinline__ uint32_t pack_state(uint32_t pix, int depth, bool spe
 __device__ __forceinline__ void accumulate(const Params& p, uint32_t pix, float3 col) {
   col = pt_de_nan(col);
   int x = pix % p.W, y = pix / p.W;
-  float4* dst = p.accum + (size_t)(p.H - 1 - y) * p.W + x;  // raygen.cu:153
+  float4* dst = p.accum + (size_t)(p.ytop - y) * p.W + x;  // raygen.cu:153 (row Himg - 1 - (y0 + y))
   atomicAdd(dst, make_float4(col.x, col.y, col.z, 1.f));
 }
 
@@ -247,8 +251,9 @@ __global__ void k_generate(SceneDev sc, Params p, const Ctrl* c, PathBuf cur) {
     }
     uint32_t seed;
     float3 o, d;
-    seed = pt_tea64_balanced((uint32_t)p.W * (uint32_t)y + (uint32_t)x, (uint32_t)frame, p.c16, p.c1);
-    camera_ray_seeded(sc.camera, p.W, p.H, x, y, seed, o, d);
+    const int yi = y + p.y0;  // row of the image (the band starts at y0)
+    seed = pt_tea64_balanced((uint32_t)p.W * (uint32_t)yi + (uint32_t)x, (uint32_t)frame, p.c16, p.c1);
+    camera_ray_seeded(sc.camera, p.W, p.Himg, x, yi, seed, o, d);
     const float time = sc.camera.time0 + pt_rnd(seed) * (sc.camera.time1 - sc.camera.time0);  // raygen.cu:69
     int s = base + i;
     cur.f(P_OSEED, s) = make_float4(o.x, o.y, o.z, __uint_as_float(seed));
@@ -823,6 +828,7 @@ struct pt_renderer {
   // pt_render calls while the launch parameters stay the same
   cudaGraphExec_t gexec[2] = {nullptr, nullptr};
   int g_max_depth = -1, g_russian = -1, g_pool = -1, g_flags = -1, g_launches = 0;
+  int g_y0 = -1, g_rows = -1;  // the band of image rows the graphs were captured for
   unsigned long long g_commit_gen = 0;
   SceneDev g_scene{};  // kernel arguments are baked into the graphs: re-capture when they change
   pt_stats stats{};
@@ -956,6 +962,9 @@ void drop_graphs(pt_renderer* r) {
 }
 }  // namespace
 
+static int render_rows(pt_renderer* r, int y0, int rows, int32_t first_frame, int32_t nframes, int32_t max_depth,
+                       int32_t russian);
+
 extern "C" {
 
 int pt_renderer_create(pt_scene* scene, int32_t width, int32_t height, void* d_accum, pt_renderer** out) {
@@ -967,8 +976,8 @@ int pt_renderer_create(pt_scene* scene, int32_t width, int32_t height, void* d_a
     pt_set_error("pt_renderer_create: scene not committed");
     return PT_ERR_STATE;
   }
-  if ((long long)width * height > PT_MAX_PIXELS) {
-    pt_set_error("pt_renderer_create: more than 2^23 pixels (the path state packs the pixel index into 23 bits)");
+  if ((long long)width * height > PT_MAX_PIXELS || width > PT_BAND_PIXELS) {
+    pt_set_error("pt_renderer_create: more than 2^28 pixels, or a row of more than 2^23");
     return PT_ERR_INVALID;
   }
   DeviceGuard dg(scene->device);
@@ -1063,7 +1072,17 @@ int pt_render(pt_renderer* r, int32_t first_frame, int32_t nframes, int32_t max_
   }
   DeviceGuard dg(r->device);
   const long long total = (long long)r->W * r->H * nframes;
-  int rc = ensure_pool(r, total);
+  // Images of more than PT_BAND_PIXELS pixels are rendered in bands of whole rows, one after the other (the path
+  // record has 23 bits for the pixel index; see Params).  Band heights are multiples of 4 so that the 8x4 tiling of
+  // the camera samples applies.  PTB200_BAND_PIXELS (dev / tests) lowers the band size.
+  long long band_pixels = PT_BAND_PIXELS;
+  if (const char* e = getenv("PTB200_BAND_PIXELS")) band_pixels = std::max<long long>(1, std::min<long long>(atoll(e), PT_BAND_PIXELS));
+  int band_rows = r->H;
+  if ((long long)r->W * r->H > band_pixels) {
+    band_rows = (int)std::max<long long>(1, band_pixels / r->W);
+    if (band_rows >= 4) band_rows &= ~3;
+  }
+  int rc = ensure_pool(r, (long long)r->W * band_rows * nframes);
   if (rc) return rc;
   cudaStream_t st = r->stream;
   if (clear_accum || (first_frame == 0 && !r->started))
@@ -1080,7 +1099,37 @@ int pt_render(pt_renderer* r, int32_t first_frame, int32_t nframes, int32_t max_
     r->stats.samples = (uint64_t)total;
     return PT_OK;
   }
+  pt_stats sum{};
+  for (int y0 = 0; y0 < r->H; y0 += band_rows) {
+    rc = render_rows(r, y0, std::min(band_rows, r->H - y0), first_frame, nframes, max_depth, russian);
+    if (rc) return rc;
+    const pt_stats& b = r->stats;
+    sum.samples += b.samples;
+    sum.closest_rays += b.closest_rays;
+    sum.shadow_rays += b.shadow_rays;
+    sum.nodes_fetched += b.nodes_fetched;
+    sum.leaves_fetched += b.leaves_fetched;
+    sum.iterations += b.iterations;
+    sum.kernel_launches += b.kernel_launches;
+    sum.ms_total += b.ms_total;
+    sum.ms_generate += b.ms_generate;
+    sum.ms_trace_closest += b.ms_trace_closest;
+    sum.ms_shade += b.ms_shade;
+    sum.ms_trace_shadow += b.ms_trace_shadow;
+    sum.drained_paths |= b.drained_paths;
+  }
+  r->stats = sum;
+  return PT_OK;
+}
 
+}  // extern "C"
+
+// the wavefront loop over rows [y0, y0 + rows) of the image: all samples of `nframes` frames of those pixels
+static int render_rows(pt_renderer* r, int y0, int rows, int32_t first_frame, int32_t nframes, int32_t max_depth,
+                       int32_t russian) {
+  pt_scene* s = r->scene;
+  cudaStream_t st = r->stream;
+  const long long total = (long long)r->W * rows * nframes;
   Ctrl init{};
   init.total_samples = (unsigned long long)total;
   init.first_frame = first_frame;
@@ -1088,11 +1137,14 @@ int pt_render(pt_renderer* r, int32_t first_frame, int32_t nframes, int32_t max_
 
   Params p;
   p.W = r->W;
-  p.H = r->H;
+  p.H = rows;
+  p.y0 = y0;
+  p.Himg = r->H;
+  p.ytop = r->H - 1 - y0;
   p.max_depth = max_depth;
   p.russian = russian;
   p.pool = r->pool;
-  p.tiled = (r->W % 8 == 0 && r->H % 4 == 0 && !getenv("PTB200_NO_TILES")) ? 1 : 0;
+  p.tiled = (r->W % 8 == 0 && rows % 4 == 0 && !getenv("PTB200_NO_TILES")) ? 1 : 0;
   p.accum = r->accum;
   p.c16 = 16u;
   p.c1 = 1u;
@@ -1211,8 +1263,8 @@ int pt_render(pt_renderer* r, int32_t first_frame, int32_t nframes, int32_t max_
   // per-kernel timing mode launches directly instead.
   const bool use_graph = !timing && getenv("PTB200_NO_GRAPH") == nullptr;
   if (use_graph && (r->gexec[0] == nullptr || r->gexec[1] == nullptr || r->g_max_depth != max_depth ||
-                    r->g_russian != russian || r->g_pool != r->pool || r->g_flags != r->flags ||
-                    r->g_commit_gen != s->commit_gen || memcmp(&r->g_scene, &sc, sizeof(SceneDev)) != 0)) {
+                    r->g_russian != russian || r->g_pool != r->pool || r->g_flags != r->flags || r->g_y0 != y0 ||
+                    r->g_rows != rows || r->g_commit_gen != s->commit_gen || memcmp(&r->g_scene, &sc, sizeof(SceneDev)) != 0)) {
     drop_graphs(r);
     for (int parity = 0; parity < 2; parity++) {
       cudaGraph_t graph = nullptr;
@@ -1235,6 +1287,8 @@ int pt_render(pt_renderer* r, int32_t first_frame, int32_t nframes, int32_t max_
     r->g_russian = russian;
     r->g_pool = r->pool;
     r->g_flags = r->flags;
+    r->g_y0 = y0;
+    r->g_rows = rows;
     r->g_commit_gen = s->commit_gen;
     memcpy(&r->g_scene, &sc, sizeof(SceneDev));
   }
@@ -1327,6 +1381,8 @@ int pt_render(pt_renderer* r, int32_t first_frame, int32_t nframes, int32_t max_
   r->stats.drained_paths = drained ? 1u : 0u;
   return PT_OK;
 }
+
+extern "C" {
 
 int pt_renderer_sync(pt_renderer* r) {
   if (!r) return PT_ERR_INVALID;

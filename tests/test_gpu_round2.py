@@ -159,13 +159,16 @@ def test_switching_env_sampling_off_needs_a_new_commit(lib):
 
 # ---- fixed limits ---------------------------------------------------------------------------------------------
 def test_fixed_limits_are_enforced_and_usable(lib):
-    """PT_MAX_PIXELS = 2^23 and PT_MAX_DEPTH = 255 (the 64-byte path record packs pixel | depth | specular flag into
-    32 bits): the limits themselves work, one more is refused."""
+    """PT_MAX_DEPTH = 255 (the 64-byte path record packs pixel | depth | specular flag into 23 + 8 + 1 bits),
+    PT_BAND_PIXELS = 2^23 pixels per band and per row, PT_MAX_PIXELS = 2^28 per image: the limits themselves work,
+    one more is refused."""
     sc = h.build_cornell(64, 64, lib)
     sc.commit()
     with pytest.raises(pt.PtError):
-        pt.Renderer(sc, 4096, 2049)
-    r = pt.Renderer(sc, 4096, 2048)              # exactly 2^23 pixels
+        pt.Renderer(sc, 16384, 16385)            # > 2^28 pixels (refused before anything is allocated)
+    with pytest.raises(pt.PtError):
+        pt.Renderer(sc, (1 << 23) + 8, 1)        # a row that does not fit one band
+    r = pt.Renderer(sc, 4096, 2048)              # exactly 2^23 pixels: still one band
     r.set_pool(1 << 20)
     r.render(0, 1, max_depth=2)
     acc = r.read_accum()
@@ -182,6 +185,74 @@ def test_fixed_limits_are_enforced_and_usable(lib):
     small.render(0, 3, max_depth=0, clear=True)
     z = small.read_accum()
     assert (z[..., 3] == 3).all() and (z[..., :3] == 0).all()
+
+
+# ---- images of more than 2^23 pixels: rendered in bands of rows ------------------------------------------------
+@pytest.fixture
+def band_pixels():
+    def set_(n):
+        if n:
+            os.environ["PTB200_BAND_PIXELS"] = str(n)
+        else:
+            os.environ.pop("PTB200_BAND_PIXELS", None)
+    yield set_
+    os.environ.pop("PTB200_BAND_PIXELS", None)
+
+
+@pytest.mark.parametrize("W,H,band", [(256, 128, 256 * 36), (200, 150, 200 * 37), (96, 70, 96 * 3), (64, 64, 64)])
+def test_banded_render_is_the_unbanded_render(lib, band_pixels, W, H, band):
+    """pt_render splits an image of more than PT_BAND_PIXELS pixels into bands of whole rows.  The seed of a sample
+    is tea<64>(W*y + x, frame) (raygen.cu:150) and a pixel only ever receives its own samples, so a banded render
+    equals the unbanded one: bit for bit at one sample per pixel (one atomic add per pixel, no ordering), and up to
+    the order of the float additions beyond.  PTB200_BAND_PIXELS forces bands on a small image: tiled and untiled
+    enumeration, a last band of fewer rows, bands of fewer than four rows and of a single row."""
+    sc = h.build_cornell(W, H, lib) if W in (200, 64) else h.build_spheres(n_small=12, seed=5, W=W, H=H, lib=lib)
+    sc.commit()
+    r = pt.Renderer(sc, W, H)
+    r.render(0, 1)
+    whole = r.read_accum().copy()
+    st_whole = r.stats()
+    band_pixels(band)
+    r.render(0, 1, clear=True)
+    banded = r.read_accum().copy()
+    st = r.stats()
+    assert np.array_equal(whole.view(np.uint32), banded.view(np.uint32))
+    assert int(st.samples) == W * H and int(st.closest_rays) == int(st_whole.closest_rays)
+    assert int(st.shadow_rays) == int(st_whole.shadow_rays)
+    assert int(st.iterations) > int(st_whole.iterations)          # one wavefront loop per band
+    # several frames, continued from a first_frame > 0, instrumented kernels
+    r.set_flags(1)
+    r.render(0, 2, clear=True)
+    r.render(2, 3)
+    b5 = r.read_accum().copy()
+    n5 = int(r.stats().nodes_fetched)
+    band_pixels(0)
+    r.render(0, 2, clear=True)
+    r.render(2, 3)
+    w5 = r.read_accum()
+    assert (b5[..., 3] == 5).all() and (w5[..., 3] == 5).all()
+    assert np.abs(b5 - w5).max() <= 1e-5 * max(1.0, float(w5[..., :3].max()))
+    if W not in (200, 64):  # (the Cornell box is traversed flat by the wavefront kernels and as a BVH by the drain)
+        assert abs(n5 - int(r.stats().nodes_fetched)) <= 1e-3 * n5 and n5 > 0
+
+
+def test_image_larger_than_one_band_against_the_oracle(lib):
+    """4096 x 2056 = 2^23 + 32 768 pixels (two bands: 2048 + 8 rows) of an RTOW-style scene (gradient sky: no pixel
+    is black), through the C ABI, against the oracle's render of the same image; ABI 3 refused this size."""
+    W, H = 4096, 2056
+    sc = h.build_spheres(n_small=12, seed=2, W=W, H=H, lib=lib)
+    sc.commit()
+    r = pt.Renderer(sc, W, H)
+    r.set_pool(1 << 22)
+    r.render(0, 1)
+    g = r.read_accum()
+    assert int(r.stats().samples) == W * H and (g[..., 3] == 1).all()
+    a, st = h.OracleScene(sc).render(W, H, 0, 1)
+    d = pixel_diff(g, a)
+    assert (d > 1e-3).mean() <= 0.01, (d > 1e-3).mean()
+    # both bands carry the image: the rows of the second band (image rows 2048.., i.e. the TOP 8 rows of the buffer)
+    assert (pixel_diff(g[:8], a[:8]) > 1e-3).mean() <= 0.01 and g[:8, :, :3].min() > 0
+    assert abs(int(r.stats().closest_rays) - int(st.closest_rays)) <= 0.005 * st.closest_rays
 
 
 # ---- hit ids at the top of configuration 4's range -------------------------------------------------------------
