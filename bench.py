@@ -7,7 +7,7 @@ synthetic HDRI, 1920x1080 @ 512 spp - the north-star configuration): camera-ray 
 closest-hit + shadow traversal, material shading / MIS / Russian roulette, float4 accumulation
 and, for N > 1, the NCCL reduce of the accumulation buffers to rank 0.  N > 1 is STRONG scaling:
 the workload's spp are split over the ranks (frames are independent: seed = tea<64>(pixel, frame),
-programs/raygen.cu:150), scene + BVH replicated.  --workload c1|c2|c3|c4_10m|c5 select the others.
+programs/raygen.cu:150), scene + BVH replicated.  --workload c1|c2|c3|c4_8k|c4_10m|c5 select the others.
 
   value    whole-job Msamples/s, scene and BVH resident in HBM (device-timed)
   e2e      same metric through the C ABI from HOST buffers: scene upload (H2D), GPU BVH
@@ -43,12 +43,15 @@ WORKLOADS = {
     "c4": ("C4 procedural 1M-triangle mesh + synthetic HDRI env map 1920x1080 @ 512 spp", 1920, 1080, 512),
     "c4_10m": ("C4 procedural 10M-triangle mesh + synthetic HDRI env map 1920x1080 @ 512 spp (scene arrays built "
                "directly, not through the OBJ file)", 1920, 1080, 512),
+    # the same scene and the same number of samples as C4 on 16 times the pixels: 33 M pixels are four bands of rows
+    # inside pt_render (the path record indexes 2^23 pixels); shows what banded rendering costs
+    "c4_8k": ("C4 scene (1M-triangle mesh + HDRI) at 7680x4320 @ 32 spp: four bands of rows inside pt_render", 7680, 4320, 32),
     # the multi-GPU configuration: 4096 spp are SPLIT across the ranks (strong scaling)
     "c5": ("C5 procedural 1M-triangle mesh + HDRI 3840x2160 @ 4096 spp, sample-split across ranks", 3840, 2160, 4096),
 }
 
 
-FACADE_IDS = {"c1": 2, "c2": 0, "c3": 5, "c4": 6, "c5": 6}   # scene functions in host_includes/scenes.hpp
+FACADE_IDS = {"c1": 2, "c2": 0, "c3": 5, "c4": 6, "c4_8k": 6, "c5": 6}   # scene functions in host_includes/scenes.hpp
 
 
 class _StdoutToStderr:
@@ -88,7 +91,7 @@ def _build_scene(h, name, W, H, lib=None):
         return h.build_spheres(22, seed=0, W=W, H=H, lib=lib)
     if name == "c3":
         return h.build_material_zoo(W, H, lib)
-    if name in ("c4", "c5"):
+    if name in ("c4", "c4_8k", "c5"):
         return h.build_mesh_scene(708, W, H, lib)
     if name == "c4_10m":
         return h.build_mesh_scene(2237, W, H, lib)
@@ -407,7 +410,7 @@ def main():
     if args.spp:
         spp = args.spp
     warm = max(3, args.warmup)
-    mesh_scene = args.workload in ("c4", "c4_10m", "c5")
+    mesh_scene = args.workload in ("c4", "c4_8k", "c4_10m", "c5")
 
     def make_scene():
         s_ = build_scene(h, args.workload, W, H, lib)

@@ -128,6 +128,7 @@ struct Params {
   // rows [y0, y0 + H) of a W x Himg image, path records carry the pixel index WITHIN the band (23 bits), and the
   // seed, the camera ray and the accumulation address use the image row y0 + y.  One band: y0 = 0, H = Himg.
   int y0, Himg, ytop;  // ytop = Himg - 1 - y0: the accumulation buffer's row of the band's first image row
+  int group_log2;      // camera samples are enumerated in groups of 2^group_log2 frames (k_generate)
   float4* accum;
   uint32_t c16, c1;  // the constants 16 and 1 as run-time values, see pt_tea64_balanced
 };
@@ -222,33 +223,57 @@ __global__ void k_iter_begin(Ctrl* c, int pool) {
   c->stat_iters += 1;
 }
 
+// Order of the camera samples.  Sample ids are consumed in order, and the 32 ids a traversal warp fetches together
+// should be rays that walk the same BVH nodes: camera rays are more than half of all rays of the mesh scenes.
+//  * within a frame, pixels are enumerated in 8x4 tiles, and inside a tile in Morton order (2 consecutive ids = 2x1
+//    pixels, 4 = 2x2, 8 = 4x2, 16 = 4x4, 32 = the tile) instead of 32-pixel strips of a scanline;
+//  * frames are taken in groups of F = 2^group_log2: ids run over (group, pixel, frame within the group) with the
+//    frame fastest, so 32 consecutive ids are 32 / F neighbouring pixels x F samples of each (F >= 32: samples of ONE
+//    pixel) - the rays of one pixel differ by the sub-pixel jitter only.  Frames that do not fill a group follow in
+//    groups of the next smaller powers of two (nframes = 77, F = 32: 32 + 32 + 8 + 4 + 1).
+// The seed depends on (pixel, frame) only (raygen.cu:150) and every (pixel, frame) pair is still generated exactly
+// once: the set of samples of a pixel is unchanged, only the order of the float additions into it.
+// C4 (1 M triangles): F = 1 / 4 / 32 -> 1896 / 1970 / 2075 Msamples/s (profiles/r02_frame_groups.md).
 __global__ void k_generate(SceneDev sc, Params p, const Ctrl* c, PathBuf cur) {
   const int n = c->gen_n, base = c->gen_base;
   const unsigned long long sbase = c->sample_base;
   const uint32_t npix = (uint32_t)p.W * (uint32_t)p.H;
-  // sample id -> (frame, pixel): one 64-bit division per thread; inside the loop the offset from the
-  // first sample of this launch is < npix + pool < 2^26, so 32-bit arithmetic does
-  const int frame0 = c->first_frame + (int)(sbase / npix);
-  const uint32_t rem0 = (uint32_t)(sbase % npix);
+  // sample id -> (whole frames before it, offset): 64-bit divisions once per thread; inside the loop the offset from
+  // the first sample of this launch is < npix + pool < 2^26, so 32-bit arithmetic does
+  const uint32_t fb0 = (uint32_t)(sbase / npix);
+  const uint32_t rem0 = (uint32_t)(sbase - (unsigned long long)fb0 * npix);
+  const uint32_t nfr = (uint32_t)(c->total_samples / npix);  // frames of this render
+  const int kmax = p.group_log2;                             // host: npix << kmax <= 2^30
+  const uint32_t top = (nfr >> kmax) << kmax;                // frames in full groups
+  const int first_frame = c->first_frame;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const uint32_t t = rem0 + (uint32_t)i;
-    const uint32_t fr = t / npix;
-    int frame = frame0 + (int)fr;
-    uint32_t pix = t - fr * npix;
+    const uint32_t q = t / npix;
+    const uint32_t off = t - q * npix;
+    const uint32_t fb = fb0 + q;  // this sample is in the fb-th block of npix ids
+    // the group of 2^j frames [f0, f0 + 2^j) that block belongs to: full groups first, then the binary digits of the
+    // remaining frame count in descending order
+    int j = kmax;
+    uint32_t f0 = fb & ~((1u << kmax) - 1u);
+    if (fb >= top) {
+      const uint32_t nl = nfr - top, fl = fb - top;  // fl < nl: the highest differing bit is set in nl
+      j = 31 - __clz((int)(nl ^ fl));
+      f0 = top + ((nl >> (j + 1)) << (j + 1));
+    }
+    const uint32_t rem = (fb - f0) * npix + off;  // position inside the group: < npix << j
+    const uint32_t po = rem >> j;                 // position of the pixel in the enumeration of one frame
+    const int frame = first_frame + (int)(f0 + (rem & ((1u << j) - 1u)));
     int x, y;
     if (p.tiled) {
-      // samples of a frame are enumerated in 8x4-pixel tiles: the 32 camera rays a warp fetches together cover a
-      // compact patch of the image instead of a 32-pixel strip of one scanline, so they walk the same BVH nodes for
-      // longer.  The seed depends on (pixel, frame) only (raygen.cu:150): the set of samples per pixel is unchanged.
-      const uint32_t tile = pix >> 5, in = pix & 31u, tiles_x = (uint32_t)p.W >> 3;
+      const uint32_t tile = po >> 5, in = po & 31u, tiles_x = (uint32_t)p.W >> 3;
       const uint32_t ty = tile / tiles_x, tx = tile - ty * tiles_x;
-      x = (int)(tx * 8u + (in & 7u));
-      y = (int)(ty * 4u + (in >> 3));
-      pix = (uint32_t)y * (uint32_t)p.W + (uint32_t)x;
+      x = (int)(tx * 8u + ((in & 1u) | ((in >> 1) & 2u) | ((in >> 2) & 4u)));
+      y = (int)(ty * 4u + (((in >> 1) & 1u) | ((in >> 2) & 2u)));
     } else {
-      x = pix % p.W;
-      y = pix / p.W;
+      x = (int)(po % (uint32_t)p.W);
+      y = (int)(po / (uint32_t)p.W);
     }
+    const uint32_t pix = (uint32_t)y * (uint32_t)p.W + (uint32_t)x;
     uint32_t seed;
     float3 o, d;
     const int yi = y + p.y0;  // row of the image (the band starts at y0)
@@ -750,6 +775,22 @@ SchedParams sched_params_rays(const SceneDev& sc) {
   return p;
 }
 
+// frames per group in the enumeration of the camera samples (k_generate), as a power of two; PTB200_FRAME_GROUP
+// overrides (dev: 1, 2, 4, ... 256 frames)
+// (measured, profiles/r02_frame_groups.md: every configuration gains monotonically up to 128-256 frames per group)
+#ifndef PT_FRAME_GROUP_LOG2
+#define PT_FRAME_GROUP_LOG2 8
+#endif
+int frame_group_log2() {
+  int k = PT_FRAME_GROUP_LOG2;
+  if (const char* e = getenv("PTB200_FRAME_GROUP")) {
+    const int f = atoi(e);
+    k = 0;
+    while (k < 8 && (2 << k) <= f) k++;
+  }
+  return k;
+}
+
 // deep trees (>= PTB200_DEEP_MIN primitives, default 64 Ki) take two node steps per vote round
 long long deep_min_prims() {
   static const long long v = getenv("PTB200_DEEP_MIN") ? atoll(getenv("PTB200_DEEP_MIN")) : 65536;
@@ -829,6 +870,7 @@ struct pt_renderer {
   cudaGraphExec_t gexec[2] = {nullptr, nullptr};
   int g_max_depth = -1, g_russian = -1, g_pool = -1, g_flags = -1, g_launches = 0;
   int g_y0 = -1, g_rows = -1;  // the band of image rows the graphs were captured for
+  int g_group = -1;            // ... and the frame grouping of the camera samples
   unsigned long long g_commit_gen = 0;
   SceneDev g_scene{};  // kernel arguments are baked into the graphs: re-capture when they change
   pt_stats stats{};
@@ -1145,6 +1187,8 @@ static int render_rows(pt_renderer* r, int y0, int rows, int32_t first_frame, in
   p.russian = russian;
   p.pool = r->pool;
   p.tiled = (r->W % 8 == 0 && rows % 4 == 0 && !getenv("PTB200_NO_TILES")) ? 1 : 0;
+  p.group_log2 = frame_group_log2();
+  while (p.group_log2 > 0 && ((long long)r->W * rows << p.group_log2) > (1ll << 30)) p.group_log2--;  // 32-bit ids in k_generate
   p.accum = r->accum;
   p.c16 = 16u;
   p.c1 = 1u;
@@ -1264,7 +1308,7 @@ static int render_rows(pt_renderer* r, int y0, int rows, int32_t first_frame, in
   const bool use_graph = !timing && getenv("PTB200_NO_GRAPH") == nullptr;
   if (use_graph && (r->gexec[0] == nullptr || r->gexec[1] == nullptr || r->g_max_depth != max_depth ||
                     r->g_russian != russian || r->g_pool != r->pool || r->g_flags != r->flags || r->g_y0 != y0 ||
-                    r->g_rows != rows || r->g_commit_gen != s->commit_gen || memcmp(&r->g_scene, &sc, sizeof(SceneDev)) != 0)) {
+                    r->g_rows != rows || r->g_group != p.group_log2 || r->g_commit_gen != s->commit_gen || memcmp(&r->g_scene, &sc, sizeof(SceneDev)) != 0)) {
     drop_graphs(r);
     for (int parity = 0; parity < 2; parity++) {
       cudaGraph_t graph = nullptr;
@@ -1289,6 +1333,7 @@ static int render_rows(pt_renderer* r, int y0, int rows, int32_t first_frame, in
     r->g_flags = r->flags;
     r->g_y0 = y0;
     r->g_rows = rows;
+    r->g_group = p.group_log2;
     r->g_commit_gen = s->commit_gen;
     memcpy(&r->g_scene, &sc, sizeof(SceneDev));
   }

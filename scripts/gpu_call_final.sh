@@ -9,6 +9,7 @@ nvidia-smi --query-gpu=name,clocks.max.sm,clocks.max.mem,power.limit --format=cs
 timeout 200 python -m pytest tests -m gpu -q -s -rfE --timeout 150 -p no:cacheprovider > $O/${R}_gputest.txt 2>&1
 echo "pytest rc $?" >> $O/${R}_gputest.txt
 tail -3 $O/${R}_gputest.txt
+timeout 60 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
 timeout 200 python bench.py > $O/${R}_bench_c4.json 2> $O/${R}_bench_c4.err
 echo "bench rc $?"; cut -c1-400 $O/${R}_bench_c4.json | tail -1
 timeout 150 python scripts/ncu_traffic.py capture c4 c2 > $O/${R}_ncu_traffic.log 2>&1

@@ -236,6 +236,48 @@ def test_banded_render_is_the_unbanded_render(lib, band_pixels, W, H, band):
         assert abs(n5 - int(r.stats().nodes_fetched)) <= 1e-3 * n5 and n5 > 0
 
 
+@pytest.mark.parametrize("W,H,F,nframes,first", [(64, 48, 4, 7, 0), (40, 30, 8, 19, 3), (96, 64, 32, 77, 0), (64, 32, 16, 5, 2), (32, 32, 256, 300, 1)])
+def test_frame_groups_generate_every_sample_once(lib, band_pixels, W, H, F, nframes, first):
+    """k_generate enumerates camera samples in groups of F frames (frame fastest, Morton order inside 8x4 tiles) so
+    that the rays a warp fetches together are samples of the same few pixels.  Every (pixel, frame) pair must still be
+    generated exactly once with its own seed tea<64>(W*y + x, frame) (raygen.cu:150): a sample's value is a function
+    of its seed alone, so the image must equal the F = 1 image up to the order of the float additions - full groups, a remainder of frames that fill no group (nframes % F), tiled and untiled
+    enumeration (40 x 30 has no 8x4 tiling), a first frame > 0, and bands on top."""
+    sc = h.build_spheres(n_small=10, seed=9, W=W, H=H, lib=lib)
+    sc.commit()
+    r = pt.Renderer(sc, W, H)
+    old = os.environ.get("PTB200_FRAME_GROUP")
+    try:
+        imgs = {}
+        for f in (1, F):
+            os.environ["PTB200_FRAME_GROUP"] = str(f)
+            r.render(first, nframes, clear=True)
+            imgs[f] = r.read_accum().copy()
+            assert int(r.stats().samples) == W * H * nframes
+        band_pixels(W * 8)
+        r.render(first, nframes, clear=True)
+        banded = r.read_accum().copy()
+        # one frame: no grouping possible, bit-identical whatever F says
+        band_pixels(0)
+        r.render(first, 1, clear=True)
+        one_f = r.read_accum().copy()
+        os.environ["PTB200_FRAME_GROUP"] = "1"
+        r.render(first, 1, clear=True)
+        one_1 = r.read_accum().copy()
+    finally:
+        if old is None:
+            os.environ.pop("PTB200_FRAME_GROUP", None)
+        else:
+            os.environ["PTB200_FRAME_GROUP"] = old
+    for img in (imgs[1], imgs[F], banded):
+        assert (img[..., 3] == nframes).all()
+    tol = 2e-6 * nframes * max(1.0, float(imgs[1][..., :3].max()))
+    assert np.abs(imgs[F] - imgs[1]).max() <= tol and np.abs(banded - imgs[1]).max() <= tol
+    assert np.array_equal(one_f.view(np.uint32), one_1.view(np.uint32))
+    a, _ = h.OracleScene(sc).render(W, H, first, nframes)
+    assert (pixel_diff(imgs[F] / nframes, a / nframes) > 1e-3).mean() <= 0.02
+
+
 def test_image_larger_than_one_band_against_the_oracle(lib):
     """4096 x 2056 = 2^23 + 32 768 pixels (two bands: 2048 + 8 rows) of an RTOW-style scene (gradient sky: no pixel
     is black), through the C ABI, against the oracle's render of the same image; ABI 3 refused this size."""
