@@ -393,7 +393,11 @@ int pt_renderer_destroy(pt_renderer* r);
  * s in [first_frame, first_frame+nframes) (main.cpp:264-293).  frame 0 of a
  * renderer's life clears the accumulation buffer like raygen.cu:154 does
  * (clear_accum != 0 forces it).  Asynchronous w.r.t. the host only through
- * pt_renderer_sync. */
+ * pt_renderer_sync.  Every (pixel, frame) pair of the range is rendered exactly once with
+ * the seed tea<64>(W*y + x, frame) (raygen.cu:150); the ORDER inside one call is the
+ * library's (frames in groups, pixels in tiles, images above PT_BAND_PIXELS in bands of
+ * rows), so the accumulation buffer equals the reference's frame-by-frame loop up to the
+ * order of the fp32 additions into a pixel. */
 int pt_render(pt_renderer* r, int32_t first_frame, int32_t nframes, int32_t max_depth,
               int32_t russian, int32_t clear_accum);
 int pt_renderer_sync(pt_renderer* r);
