@@ -123,7 +123,7 @@ struct CtrlPoll {
 
 struct Params {
   int W, H, max_depth, russian, pool;  // (the first frame index lives in Ctrl so captured graphs stay valid)
-  int tiled;                           // camera samples enumerated in 8x4 tiles (W % 8 == 0 && H % 4 == 0)
+  int tiled;                           // pixels enumerated in 8x4 tiles, Morton order inside (W % 8 == 0 && H % 4 == 0)
   // An image of more than PT_BAND_PIXELS pixels is rendered as horizontal bands, one after the other: W x H are the
   // rows [y0, y0 + H) of a W x Himg image, path records carry the pixel index WITHIN the band (23 bits), and the
   // seed, the camera ray and the accumulation address use the image row y0 + y.  One band: y0 = 0, H = Himg.
