@@ -30,6 +30,7 @@
 #include <vector>
 
 #include "renderer_internal.h"
+#include "sample_order.h"
 #include "scene_host.h"
 #include "shading.h"
 #include "trace_sched.cuh"
@@ -223,17 +224,7 @@ __global__ void k_iter_begin(Ctrl* c, int pool) {
   c->stat_iters += 1;
 }
 
-// Order of the camera samples.  Sample ids are consumed in order, and the 32 ids a traversal warp fetches together
-// should be rays that walk the same BVH nodes: camera rays are more than half of all rays of the mesh scenes.
-//  * within a frame, pixels are enumerated in 8x4 tiles, and inside a tile in Morton order (2 consecutive ids = 2x1
-//    pixels, 4 = 2x2, 8 = 4x2, 16 = 4x4, 32 = the tile) instead of 32-pixel strips of a scanline;
-//  * frames are taken in groups of F = 2^group_log2: ids run over (group, pixel, frame within the group) with the
-//    frame fastest, so 32 consecutive ids are 32 / F neighbouring pixels x F samples of each (F >= 32: samples of ONE
-//    pixel) - the rays of one pixel differ by the sub-pixel jitter only.  Frames that do not fill a group follow in
-//    groups of the next smaller powers of two (nframes = 77, F = 32: 32 + 32 + 8 + 4 + 1).
-// The seed depends on (pixel, frame) only (raygen.cu:150) and every (pixel, frame) pair is still generated exactly
-// once: the set of samples of a pixel is unchanged, only the order of the float additions into it.
-// C4 (1 M triangles): F = 1 / 4 / 32 -> 1896 / 1970 / 2075 Msamples/s (profiles/r02_frame_groups.md).
+// camera rays for the free slots of the pool, in the order sample_order.h defines (frames in groups, pixels in tiles)
 __global__ void k_generate(SceneDev sc, Params p, const Ctrl* c, PathBuf cur) {
   const int n = c->gen_n, base = c->gen_base;
   const unsigned long long sbase = c->sample_base;
@@ -242,37 +233,15 @@ __global__ void k_generate(SceneDev sc, Params p, const Ctrl* c, PathBuf cur) {
   // the first sample of this launch is < npix + pool < 2^26, so 32-bit arithmetic does
   const uint32_t fb0 = (uint32_t)(sbase / npix);
   const uint32_t rem0 = (uint32_t)(sbase - (unsigned long long)fb0 * npix);
-  const uint32_t nfr = (uint32_t)(c->total_samples / npix);  // frames of this render
-  const int kmax = p.group_log2;                             // host: npix << kmax <= 2^30
-  const uint32_t top = (nfr >> kmax) << kmax;                // frames in full groups
+  const SampleOrder so = sample_order_make(p.W, p.H, (uint32_t)(c->total_samples / npix), p.group_log2, p.tiled);
   const int first_frame = c->first_frame;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const uint32_t t = rem0 + (uint32_t)i;
     const uint32_t q = t / npix;
-    const uint32_t off = t - q * npix;
-    const uint32_t fb = fb0 + q;  // this sample is in the fb-th block of npix ids
-    // the group of 2^j frames [f0, f0 + 2^j) that block belongs to: full groups first, then the binary digits of the
-    // remaining frame count in descending order
-    int j = kmax;
-    uint32_t f0 = fb & ~((1u << kmax) - 1u);
-    if (fb >= top) {
-      const uint32_t nl = nfr - top, fl = fb - top;  // fl < nl: the highest differing bit is set in nl
-      j = 31 - __clz((int)(nl ^ fl));
-      f0 = top + ((nl >> (j + 1)) << (j + 1));
-    }
-    const uint32_t rem = (fb - f0) * npix + off;  // position inside the group: < npix << j
-    const uint32_t po = rem >> j;                 // position of the pixel in the enumeration of one frame
-    const int frame = first_frame + (int)(f0 + (rem & ((1u << j) - 1u)));
     int x, y;
-    if (p.tiled) {
-      const uint32_t tile = po >> 5, in = po & 31u, tiles_x = (uint32_t)p.W >> 3;
-      const uint32_t ty = tile / tiles_x, tx = tile - ty * tiles_x;
-      x = (int)(tx * 8u + ((in & 1u) | ((in >> 1) & 2u) | ((in >> 2) & 4u)));
-      y = (int)(ty * 4u + (((in >> 1) & 1u) | ((in >> 2) & 2u)));
-    } else {
-      x = (int)(po % (uint32_t)p.W);
-      y = (int)(po / (uint32_t)p.W);
-    }
+    uint32_t fr;
+    sample_order_decode(so, fb0 + q, t - q * npix, x, y, fr);
+    const int frame = first_frame + (int)fr;
     const uint32_t pix = (uint32_t)y * (uint32_t)p.W + (uint32_t)x;
     uint32_t seed;
     float3 o, d;

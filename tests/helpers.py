@@ -319,7 +319,8 @@ def hostsim():
     d = os.path.join(ROOT, "tests", "hostsim")
     so = os.path.join(d, "libhostsim.so")
     srcs = [os.path.join(d, "sim.cpp")] + [os.path.join(PKG_DIR, "csrc", f)
-                                            for f in ("hd.h", "bvh_core.h", "traverse.h", "shading.h", "scene_dev.h")]
+                                            for f in ("hd.h", "bvh_core.h", "traverse.h", "shading.h", "scene_dev.h",
+                                                      "sample_order.h")]
     if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(f) for f in srcs):
         _run(["/usr/bin/g++", "-O2", "-fopenmp", "-ffp-contract=off", "-fPIC", "-shared", "-std=c++17", "-w",
               "-o", so, "sim.cpp"], d)
@@ -335,6 +336,7 @@ def hostsim():
     s.sim_perm8.restype = C.c_uint
     s.sim_perm8.argtypes = [C.c_uint, C.c_uint]
     s.sim_node_invariant_violations.argtypes = [vp]
+    s.sim_sample_order.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_ulonglong, C.c_int, vp]
     _sim = s
     return s
 

@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "../../optix-path-tracer_b200/csrc/bvh_core.h"
+#include "../../optix-path-tracer_b200/csrc/sample_order.h"
 #include "../../optix-path-tracer_b200/csrc/shading.h"
 #include "../../optix-path-tracer_b200/csrc/traverse.h"
 
@@ -613,6 +614,27 @@ int sim_render(const Sim* s, int W, int H, int first_frame, int nframes, int max
         px[2] += col.z;
         px[3] += 1.f;
       }
+  return 0;
+}
+
+// k_generate's enumeration of the camera samples (csrc/sample_order.h), ids [sbase, sbase + n) of a render of
+// `nframes` frames of a W x H band, exactly as the kernel walks them (32-bit offsets from the launch's first id):
+// out[3 * i] = x, y, frame (relative to the first frame)
+int sim_sample_order(int W, int H, int tiled, int kmax, int nframes, unsigned long long sbase, int n, int* out) {
+  const uint32_t npix = (uint32_t)W * (uint32_t)H;
+  const uint32_t fb0 = (uint32_t)(sbase / npix);
+  const uint32_t rem0 = (uint32_t)(sbase - (unsigned long long)fb0 * npix);
+  const SampleOrder so = sample_order_make(W, H, (uint32_t)nframes, kmax, tiled);
+  for (int i = 0; i < n; i++) {
+    const uint32_t t = rem0 + (uint32_t)i;
+    const uint32_t q = t / npix;
+    int x, y;
+    uint32_t fr;
+    sample_order_decode(so, fb0 + q, t - q * npix, x, y, fr);
+    out[3 * i] = x;
+    out[3 * i + 1] = y;
+    out[3 * i + 2] = (int)fr;
+  }
   return 0;
 }
 

@@ -366,3 +366,58 @@ def test_node_encoding_invariants_the_hit_mask_assembly_relies_on(builder):
           "cornell": lambda: h.build_cornell(32, 32)}[builder]()
     sim = h.SimScene(sc)
     assert sim.s.sim_node_invariant_violations(sim.h) == 0
+
+
+# ---- order of the camera samples (csrc/sample_order.h, the function k_generate calls) ---------------------------
+def _sample_order(W, H, tiled, kmax, nframes, chunks_seed=0, max_chunk=5000):
+    """ids 0 .. W*H*nframes in launches of random sizes, as the renderer's iterations walk them"""
+    sim = h.hostsim()
+    total = W * H * nframes
+    out = np.empty((total, 3), dtype=np.int32)
+    rng = np.random.default_rng(chunks_seed)
+    s = 0
+    while s < total:
+        n = int(min(total - s, rng.integers(1, max_chunk)))
+        sim.sim_sample_order(W, H, tiled, kmax, nframes, s, n, out[s:].ctypes.data)
+        s += n
+    return out
+
+
+@pytest.mark.parametrize("W,H,tiled,kmax,nframes", [
+    (16, 8, 1, 0, 3), (16, 8, 1, 2, 8), (16, 8, 1, 2, 7), (24, 12, 1, 5, 77), (10, 7, 0, 3, 19), (8, 4, 1, 8, 300),
+    (8, 4, 1, 5, 1), (32, 16, 1, 6, 63), (32, 16, 1, 6, 65), (40, 30, 0, 8, 5), (64, 32, 1, 8, 256), (8, 8, 1, 3, 2)])
+def test_sample_order_generates_every_sample_once(W, H, tiled, kmax, nframes):
+    """k_generate may emit the (pixel, frame) pairs of a render in any order (seed = tea<64>(W*y + x, frame),
+    programs/raygen.cu:150; accumulation is a sum, :166) but must emit each exactly once - full groups of 2^kmax
+    frames, the remainder in groups of the smaller powers of two, tiled and untiled, whatever the launch boundaries -
+    and a pixel's frames must come in ascending order (the serial sum of a pixel then adds in the reference's order)."""
+    o = _sample_order(W, H, tiled, kmax, nframes)
+    x, y, f = o[:, 0].astype(np.int64), o[:, 1].astype(np.int64), o[:, 2].astype(np.int64)
+    assert x.min() == 0 and x.max() == W - 1 and y.min() == 0 and y.max() == H - 1
+    assert f.min() == 0 and f.max() == nframes - 1
+    key = (f * H + y) * W + x
+    assert len(np.unique(key)) == W * H * nframes == len(key)
+    pix = y * W + x
+    order = np.argsort(pix, kind="stable")          # ids of one pixel, in emission order
+    fs = f[order].reshape(W * H, nframes)
+    assert (np.diff(fs, axis=1) > 0).all()
+    # the same ids whatever the launch boundaries
+    assert np.array_equal(o, _sample_order(W, H, tiled, kmax, nframes, chunks_seed=7, max_chunk=97))
+
+
+def test_sample_order_keeps_a_warp_on_one_pixel_and_a_tile_compact():
+    """What the order is for: with F >= 32 frames per group, 32 consecutive ids inside a full group are samples of ONE
+    pixel; with F = 1, 2^m consecutive positions of a tile are a compact block (2x1, 2x2, 4x2, 4x4, 8x4); with F = 4,
+    32 consecutive ids are 8 pixels (a 4x2 block) x 4 frames."""
+    W, H = 64, 32
+    o = _sample_order(W, H, 1, 5, 64).reshape(-1, 32, 3)
+    assert (o[:, :, 0] == o[:, :1, 0]).all() and (o[:, :, 1] == o[:, :1, 1]).all()
+    assert (np.diff(o[:, :, 2], axis=1) == 1).all()
+    o = _sample_order(W, H, 1, 0, 1)
+    for m, (bw, bh) in enumerate([(2, 1), (2, 2), (4, 2), (4, 4), (8, 4)], start=1):
+        b = o.reshape(-1, 1 << m, 3)
+        assert ((b[:, :, 0].max(1) - b[:, :, 0].min(1)) == bw - 1).all()
+        assert ((b[:, :, 1].max(1) - b[:, :, 1].min(1)) == bh - 1).all()
+    o = _sample_order(W, H, 1, 2, 8).reshape(-1, 32, 3)
+    assert ((o[:, :, 0].max(1) - o[:, :, 0].min(1)) == 3).all() and ((o[:, :, 1].max(1) - o[:, :, 1].min(1)) == 1).all()
+    assert (o[:, :, 2].max(1) - o[:, :, 2].min(1) == 3).all()
