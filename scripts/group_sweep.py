@@ -16,7 +16,8 @@ import helpers as h  # noqa: E402
 pt = h.pt
 lib = pt.load()
 specs = sys.argv[1:] or ["c4:128", "c2:64", "c1:64", "c3:64"]
-FS = [int(f) for f in os.environ.get("SWEEP_F", "1 2 4 8 16 32").split()]
+FS = [int(f) for f in os.environ.get("SWEEP_F", "1 2 4 8 16 32 64 128 256").split()]
+VAR = os.environ.get("SWEEP_VAR", "PTB200_FRAME_GROUP")   # any switch the library reads per render
 for spec in specs:
     name, spp, *rest = spec.split(":")
     spp = int(spp)
@@ -30,7 +31,7 @@ for spec in specs:
     ref = None
     line = [f"{name:7s} {W}x{H}@{spp}" + (f" pool {pool}" if pool else "")]
     for F in FS:
-        os.environ["PTB200_FRAME_GROUP"] = str(F)
+        os.environ[VAR] = str(F)
         r.render(0, spp, clear=True)
         ms = []
         for _ in range(3):
