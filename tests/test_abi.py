@@ -27,6 +27,21 @@ def test_header_symbols_exported(lib):
     assert lib.pt_abi_version() == 3
 
 
+def test_limits_match_header():
+    """PT_MAX_PIXELS / PT_BAND_PIXELS / PT_MAX_DEPTH of the header are what the Python binding exports"""
+    src = open(HDR).read()
+
+    def define(name):
+        m = re.search(r"#define\s+%s\s+\(?\s*(\d+)\s*(?:<<\s*(\d+))?\s*\)?" % name, src)
+        assert m, name
+        return int(m.group(1)) << int(m.group(2) or 0)
+
+    assert define("PT_MAX_PIXELS") == pt.MAX_PIXELS == 1 << 28
+    assert define("PT_BAND_PIXELS") == pt.BAND_PIXELS == 1 << 23
+    assert define("PT_MAX_DEPTH") == pt.MAX_DEPTH == 255
+    assert define("PTB200_ABI_VERSION") == 3
+
+
 def test_struct_layout_matches_header():
     # sizes the C header implies (plain 4-byte fields, no padding)
     assert C.sizeof(pt.Sphere) == 16 and C.sizeof(pt.Rect) == 28 and C.sizeof(pt.Box) == 24
